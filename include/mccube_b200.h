@@ -1,0 +1,195 @@
+/*
+ * mccube_b200 -- C ABI of the B200-native MCCube hot path (sm_100a).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / jax types.  Every
+ * entry point only ENQUEUES work on the caller's CUDA stream and returns; nothing
+ * synchronises, nothing allocates (scratch is caller-provided through the
+ * *_workspace_bytes() queries), results stay on the device.  That is the contract an
+ * XLA-FFI custom call needs (INTEGRATION.md shows the jax.ffi binding for each one)
+ * and it makes every call CUDA-graph capturable.
+ *
+ * The reference (tttc3/MCCube v0.0.3) is pure Python on JAX; the "FFI for this path"
+ * is the set of XLA ops its step lowers to.  Each function below names the reference
+ * lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - particle state is row-major float32 [n, ld] with ld = d (+1 when weighted: the
+ *     weight is the LAST column, mccube/_utils.py:47-51,82-84);
+ *   - child id c of the expansion is c = i*k + j  (parent i, cubature point j;
+ *     mccube/_solvers.py:136); ids are uint32 (n*k <= 2^32);
+ *   - return value: 0 on success, negative mccb200_status on error;
+ *     mccb200_last_error() returns a thread-local message.
+ */
+#ifndef MCCUBE_B200_H_
+#define MCCUBE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCCB200_VERSION 100
+#define MCCB200_API __attribute__((visibility("default")))
+
+typedef enum {
+  MCCB200_OK = 0,
+  MCCB200_ERR_INVALID_ARGUMENT = -1,
+  MCCB200_ERR_WORKSPACE_TOO_SMALL = -2,
+  MCCB200_ERR_CUDA = -3,
+  MCCB200_ERR_UNSUPPORTED = -4
+} mccb200_status;
+
+MCCB200_API int mccb200_version(void);
+MCCB200_API const char* mccb200_last_error(void);
+/* Number of SMs of the current device (grid sizing is done inside the library). */
+MCCB200_API int mccb200_sm_count(void);
+
+/* ------------------------------------------------------------------ RNG description
+ * The key MonteCarloKernel uses at time t (mccube/_kernels/random.py:56-58):
+ *     _t   = bitcast_int32(float32(t))            diffrax._misc.force_bitcast_convert_type
+ *     key  = jr.fold_in(self.key, _t)
+ *     key  = split_by_tree(key, particles)[leaf]  == jr.split(key, n_leaves)[leaf]
+ * key_dev / t_dev let the words come from device memory (what an XLA custom call gets
+ * inside diffrax's while_loop); when NULL the by-value fields are used. */
+typedef struct {
+  uint32_t key[2];          /* jr.key(seed) words: {seed >> 32, seed & 0xffffffff}      */
+  const uint32_t* key_dev;  /* optional: 2 words on the device                          */
+  float t;                  /* time the kernel is called with (outer t0, _solvers.py:144) */
+  const float* t_dev;       /* optional: float32 t on the device                        */
+  uint32_t leaf;            /* position of the array in the particles PyTree            */
+  uint32_t n_leaves;        /* number of PyTree leaves (1 for a single array)           */
+  int32_t partitionable;    /* jax_threefry_partitionable flag (0 = JAX < 0.5 default)  */
+  int32_t fold_time;        /* 1: apply the fold_in/split chain above; 0: use key as is */
+} mccb200_rng;
+
+/* ------------------------------------------------------------------ A8: resampling indices
+ * jr.choice(key, p[n_inputs, .], (count,), replace, p=None)  (random.py:65) as an INDEX
+ * vector:  replace=0 -> _shuffle(key, arange(n_inputs))[:count]  (`rounds` stable
+ * sort_key_val rounds over fresh 32-bit threefry keys); replace=1 -> randint(key, 0, n_inputs).
+ * Bit-exact with jax.random for both threefry modes.  n_inputs < 2^32 - 1. */
+MCCB200_API size_t mccb200_mc_indices_workspace_bytes(uint64_t n_inputs, uint64_t count, int replace);
+MCCB200_API int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, int replace,
+                       uint32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stable LSD radix sort of (uint32 key, uint32 value) pairs on bits [0, key_bits)
+ * == lax.sort_key_val(keys, values, is_stable=True) (jax _shuffle) / jnp.argsort
+ * (stratified.py:43).  values_in == NULL sorts an implicit iota (argsort).
+ * Sorted pairs land in keys_out / values_out (keys_out may be NULL). */
+MCCB200_API size_t mccb200_sort_pairs_workspace_bytes(uint64_t count);
+MCCB200_API int mccb200_sort_pairs(const uint32_t* keys_in, const uint32_t* values_in, uint64_t count, int key_bits,
+                       uint32_t* keys_out, uint32_t* values_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------ drift description (A6)
+ * kind 0: no drift.  kind 1: f[n, d] evaluated by the caller (any user callable,
+ * README.md:76; evaluated on PARENTS only, mccube/_term.py:58-63).  kind 2: fused
+ * analytic drift of a diagonal Gaussian target, f = (mean - y) * inv_var. */
+typedef struct {
+  int32_t kind;
+  const float* f;        /* kind 1: [n, d]  */
+  const float* mean;     /* kind 2: [d]     */
+  const float* inv_var;  /* kind 2: [d]     */
+} mccb200_drift;
+
+/* Cubature description (A4/A5).  points == NULL selects the Hadamard formula
+ * (mccube/_formulae.py:211-227): sign(M[j,c]) = (-1)^popcount((j mod k/2) & c), negated
+ * for j >= k/2, generated in-kernel; noise = +-scale with scale = g*sqrt(dt)
+ * (mccube/_path.py:60-71, _term.py:70-77).  Otherwise points is the [k, d] table
+ * g * (coeff * M) already scaled by the caller. */
+typedef struct {
+  int32_t k;             /* point count */
+  const float* points;   /* optional [k, d] scaled table */
+  float scale;           /* Hadamard: fl(g * fl(sqrt(dt))) */
+  const float* lam;      /* [k] cubature weights (weighted state only), may be NULL = 1/k */
+} mccb200_cubature;
+
+/* ------------------------------------------------------------------ A1-A5 + gather
+ * Fused expand+select: for every output row r the selected child id is
+ *     c = perm ? perm[(r / out_per_part) * in_per_part + idx[r % out_per_part]] : idx[r]
+ * (the second form is PartitioningRecombinationKernel's shared local index vector,
+ * mccube/_kernels/base.py:159-177, quirk Q4), and
+ *     y1[r, :] = y0[i, :] + (dt * f(y0[i, :]) + noise[j, :]),   i = c / k, j = c % k
+ * in exactly that fp32 op order, no FMA contraction (diffrax Euler.step through
+ * mccube/_term.py:77).  The n*k*d expansion of _solvers.py:136 never exists.
+ * weighted != 0: ld = d + 1 and the child weight is w[c % n] * lam[c / n]
+ * (_solvers.py:138-141 lays weights out k-major: quirk Q3), unnormalised. */
+MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
+                          float dt, const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* perm,
+                          uint64_t out_per_part, uint64_t in_per_part, uint64_t n_out, float* y1,
+                          void* stream);
+
+/* Materialise the full [n*k, ld] expansion (what _solvers.py:136 builds).  Only for the
+ * generic kernel protocol (user-defined recombination kernels) and for parity tests. */
+MCCB200_API int mccb200_expand_all(const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
+                       float dt, const mccb200_cubature* cub, float* y1, void* stream);
+
+/* out[r, :] = in[idx[r], :]  (jnp.take / p[indices]: stratified.py:45, tree.py:58, random.py:65). */
+MCCB200_API int mccb200_gather_rows(const float* in, int ld, const uint32_t* idx, uint64_t n_out, float* out, void* stream);
+
+/* Weight renormalisation of pack_particles(*unpack_particles(.)) (_solvers.py:146,
+ * _utils.py:47-51): last column divided by its sum.  workspace: 1 double. */
+MCCB200_API int mccb200_normalise_weights(float* y, uint64_t n, int ld, double* workspace, void* stream);
+
+/* ------------------------------------------------------------------ A10: partitioning keys
+ * StratifiedPartitioningKernel (mccube/_kernels/stratified.py:36-45): key = ||p - com||_2
+ * as an order-preserving uint32 (fp32 sequential sum of squares, sqrt).  com[d] on device. */
+MCCB200_API int mccb200_stratified_keys(const float* p, uint64_t n, int d, int ld, const float* com, uint32_t* keys,
+                            void* stream);
+
+/* BoxPartitionKernel (NEW: absent from the reference).  n_dims key
+ * dimensions dims[i] (host array), `bits` bits per dimension:
+ *     cell = clamp(floor((x - lo) * inv_h), 0, 2^bits - 1);  key = lexicographic cell id.
+ * bounds = device [2 * n_dims]: lo[0..), inv_h[0..).  mccb200_box_bounds fills it with
+ * the bounding box of the rows (lo = min, inv_h = 2^bits / (max - min)). */
+#define MCCB200_BOX_MAX_DIMS 8
+MCCB200_API int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int32_t* dims_host, int n_dims, int bits,
+                       float* bounds, void* workspace, size_t workspace_bytes, void* stream);
+MCCB200_API size_t mccb200_box_bounds_workspace_bytes(void);
+MCCB200_API int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32_t* dims_host, int n_dims, int bits,
+                     const float* bounds, uint32_t* keys, void* stream);
+
+/* Same two operations on the IMPLICIT children of y0 (never materialised): bounds and
+ * keys of child c = i*k + j computed from parent i in-kernel. */
+MCCB200_API int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
+                             const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                             float* bounds, void* workspace, size_t workspace_bytes, void* stream);
+MCCB200_API int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
+                           const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                           const float* bounds, uint32_t* keys, void* stream);
+
+/* Fused BoxPartitionKernel + PartitioningRecombinationKernel + MonteCarloKernel step on
+ * the implicit children (Hadamard cubature only): counting-sort ranks of all n*k
+ * children by box key (stable in child id) without storing keys or ids, then selection of
+ * local positions idx_local[0..out_per_part) in every partition of in_per_part children,
+ * then the fused Euler update of the selected children.  Result == expand_all ->
+ * box_keys -> sort_pairs -> expand_select(perm) bit for bit.  n_dims*bits <= 12. */
+MCCB200_API size_t mccb200_box_prk_step_workspace_bytes(uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part);
+MCCB200_API int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                         const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                         const float* bounds, const uint32_t* idx_local, uint64_t out_per_part,
+                         uint64_t in_per_part, float* y1, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------ A11: moments
+ * One pass each: sums[d] (+ weight sum) and centred second moments [d, d] in fp64:
+ *     mean = sum_r w_r p_r / sum_r w_r          (center_of_mass, mccube/_metrics.py:96)
+ *     m2   = sum_r w_r (p_r - c)(p_r - c)^T     (jnp.cov, README.md:86), c = centre[d]
+ * w == NULL -> unit weights.  Outputs are accumulated INTO the fp64 buffers (zero them
+ * first; cross-GPU reduction = one all-reduce of d + d*d + 1 doubles). */
+MCCB200_API int mccb200_moments_sum(const float* p, uint64_t n, int d, int ld, const float* w, int w_stride,
+                        double* sum_out /*[d+1]: sums then weight total*/, void* stream);
+MCCB200_API int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, const float* w, int w_stride,
+                       const float* centre, double* m2_out /*[d*d]*/, void* stream);
+
+/* Full-covariance Gaussian drift f = -(y - mean) @ prec (config 4) written to f[n, d];
+ * 3xTF32-free fp32 SIMT tiles in this round. */
+MCCB200_API int mccb200_gaussian_full_drift(const float* y, uint64_t n, int d, int ld, const float* mean,
+                                const float* prec /*[d, d] row-major*/, float* f, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCUBE_B200_H_ */

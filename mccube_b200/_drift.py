@@ -1,0 +1,42 @@
+"""Analytic drifts the fused kernels recognise.
+
+The reference takes any callable as the ODE vector field (README.md:72-76 uses
+`vmap(grad(multivariate_normal.logpdf))`).  A callable of one of these classes is
+pattern-matched by `MCCSolver.step` and evaluated inside the fused kernel; any other
+callable is evaluated by the caller on the parents `[n, d]` and handed to the kernel as
+an array (drift kind 1) -- the generic path, never a silent CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class GaussianDiagDrift:
+    """grad log N(y; mean, diag(var)) = (mean - y) * (1 / var)   [drift kind 2]."""
+
+    def __init__(self, mean, var, device="cuda"):
+        mean = np.asarray(mean, dtype=np.float64)
+        var = np.broadcast_to(np.asarray(var, dtype=np.float64), mean.shape)
+        self.mean = torch.tensor(mean, dtype=torch.float32, device=device)
+        self.inv_var = torch.tensor((1.0 / var).astype(np.float32), dtype=torch.float32, device=device)
+
+    def __call__(self, t, y, args=None):
+        # generic-path evaluation (same values as the fused form)
+        return (self.mean - y) * self.inv_var
+
+
+class GaussianFullDrift:
+    """grad log N(y; mean, cov) = -(y - mean) @ cov^-1 for a full covariance (config 4).
+    Evaluated by the library's GEMM kernel into an [n, d] array (drift kind 1)."""
+
+    def __init__(self, mean, cov, device="cuda"):
+        cov = np.asarray(cov, dtype=np.float64)
+        self.mean = torch.tensor(np.asarray(mean), dtype=torch.float32, device=device)
+        self.prec = torch.tensor(np.linalg.inv(cov).astype(np.float32), dtype=torch.float32, device=device)
+
+    def __call__(self, t, y, args=None):
+        d = self.mean.numel()
+        return _lib.gaussian_full_drift(y.contiguous(), d, self.mean, self.prec)

@@ -1,0 +1,98 @@
+"""Monte Carlo recombination / partitioning
+(mirror of /root/reference/mccube/_kernels/random.py:22-115).
+
+The index vector `jr.choice` would gather with is produced on the GPU by
+`mccb200_mc_indices` (in-kernel threefry2x32 + stable radix-sort shuffle), bit-exact
+with jax.random on the integer branches (p = None).  Weighted sampling with a real
+`weighting_function` (Gumbel top-k / inverse-CDF, random.py:62-65) is float arithmetic
+that cannot be promised bit-exact across XLA-CPU and CUDA libm and is not part of this
+round: it raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import _lib
+from .._tree import tree_map_with_index
+from .._utils import nop, unpack_particles
+from .base import AbstractPartitioningKernel, AbstractRecombinationKernel
+
+
+def key_words(key):
+    """Accepts `(k0, k1)`, an int seed (`jr.key(seed)`), or a 2-element array/tensor."""
+    if isinstance(key, int):
+        return ((key >> 32) & 0xFFFFFFFF, key & 0xFFFFFFFF)
+    if isinstance(key, torch.Tensor):
+        key = key.detach().cpu().tolist()
+    k0, k1 = key
+    return (int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF)
+
+
+class MonteCarloKernel(AbstractRecombinationKernel):
+    """`MonteCarloKernel(recombination_count, with_replacement=False, weighting_function=nop, *, key)`
+    (random.py:22-68).  `threefry_partitionable` mirrors the `jax_threefry_partitionable`
+    flag of the JAX the reference would run under (False = the reference's era)."""
+
+    def __init__(self, recombination_count, with_replacement: bool = False, weighting_function=nop, *, key,
+                 threefry_partitionable: bool = False):
+        super().__init__(recombination_count)
+        self.with_replacement = with_replacement
+        self.weighting_function = weighting_function
+        self.key = key_words(key)
+        self.threefry_partitionable = threefry_partitionable
+
+    # -- index vector (what jr.choice gathers with; the reference never exposes it)
+    def indices(self, t, n_inputs: int, count, device, leaf: int = 0, n_leaves: int = 1) -> torch.Tensor:
+        shape = tuple(count) if isinstance(count, (tuple, list)) else (count,)
+        rng = _lib.make_rng(self.key, t, leaf=leaf, n_leaves=n_leaves, partitionable=self.threefry_partitionable)
+        return _lib.mc_indices(rng, n_inputs, math.prod(shape), self.with_replacement, device)
+
+    def _probabilities(self, p, weighted):
+        if not weighted:
+            return None
+        _, w = unpack_particles(p, True)
+        w = self.weighting_function(w)
+        if w is not None:
+            raise NotImplementedError(
+                "MonteCarloKernel with a non-trivial weighting_function (Gumbel top-k / inverse-CDF sampling, "
+                "random.py:62-65) is not implemented on the CUDA path yet")
+        return None
+
+    def __call__(self, t, particles, args, weighted: bool = False):
+        def _choice(i, n_leaves, p, count):
+            self._probabilities(p, weighted)
+            shape = tuple(count) if isinstance(count, (tuple, list)) else (count,)
+            idx = self.indices(t, p.shape[0], shape, p.device, i, n_leaves)
+            out = _lib.gather_rows(p.contiguous(), idx)
+            return out.reshape(*shape, p.shape[-1])
+
+        return tree_map_with_index(_choice, particles, self.recombination_count)
+
+    # -- all partitions at once with the shared local index vector (quirk Q4)
+    def call_batched(self, t, part, args, weighted, count):
+        m, per, ld = part.shape
+        self._probabilities(part[0], weighted)
+        idx_local = self.indices(t, per, count, part.device)
+        idx = (torch.arange(m, device=part.device, dtype=torch.int64)[:, None] * per
+               + idx_local.to(torch.int64)[None, :]).reshape(-1).to(torch.int32)
+        return _lib.gather_rows(part.reshape(m * per, ld).contiguous(), idx).reshape(m, -1, ld)
+
+
+class MonteCarloPartitioningKernel(AbstractPartitioningKernel):
+    """Random assignment to `m` equal partitions (random.py:71-115): the wrapped kernel is
+    called with `recombination_count = (m, n // m)`."""
+
+    def __init__(self, partition_count, monte_carlo_kernel: MonteCarloKernel):
+        super().__init__(partition_count)
+        self.monte_carlo_kernel = monte_carlo_kernel
+
+    def __call__(self, t, particles, args, weighted: bool = False):
+        from .._tree import tree_map
+        from .base import _call_with_count
+
+        def _one(p, c):
+            return _call_with_count(self.monte_carlo_kernel, (c, p.shape[0] // c), t, p, args, weighted)
+
+        return tree_map(_one, particles, self.partition_count)

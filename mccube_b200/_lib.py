@@ -1,0 +1,376 @@
+"""ctypes binding of the C ABI declared in `include/mccube_b200.h`.
+
+This is the ONLY way the Python layer reaches the GPU kernels, and there is no CPU
+fallback: if `libmccube_b200.so` is missing or a call fails, an exception is raised.
+torch is used for device memory and streams only (`tensor.data_ptr()` in, results in
+pre-allocated tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmccube_b200.so"
+
+BOX_MAX_DIMS = 8
+
+
+class MccubeB200Error(RuntimeError):
+    pass
+
+
+class Rng(C.Structure):
+    _fields_ = [
+        ("key", C.c_uint32 * 2),
+        ("key_dev", C.c_void_p),
+        ("t", C.c_float),
+        ("t_dev", C.c_void_p),
+        ("leaf", C.c_uint32),
+        ("n_leaves", C.c_uint32),
+        ("partitionable", C.c_int32),
+        ("fold_time", C.c_int32),
+    ]
+
+
+class Drift(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("f", C.c_void_p), ("mean", C.c_void_p), ("inv_var", C.c_void_p)]
+
+
+class Cubature(C.Structure):
+    _fields_ = [("k", C.c_int32), ("points", C.c_void_p), ("scale", C.c_float), ("lam", C.c_void_p)]
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "mccb200_version": (C.c_int, []),
+    "mccb200_last_error": (C.c_char_p, []),
+    "mccb200_sm_count": (C.c_int, []),
+    "mccb200_mc_indices_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64, C.c_int]),
+    "mccb200_mc_indices": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    "mccb200_sort_pairs_workspace_bytes": (C.c_size_t, [C.c_uint64]),
+    "mccb200_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_expand_select": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
+                                        C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                        C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_expand_all": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
+                                     C.POINTER(Cubature), C.c_void_p, C.c_void_p]),
+    "mccb200_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_normalise_weights": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
+    "mccb200_stratified_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "mccb200_box_bounds_workspace_bytes": (C.c_size_t, []),
+    "mccb200_box_bounds": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_box_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mccb200_box_child_bounds": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
+                                           C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_box_child_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
+                                         C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "mccb200_box_prk_step_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "mccb200_box_prk_step": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                       C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p]),
+    "mccb200_moments_sum": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
+    "mccb200_moments_m2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "mccb200_gaussian_full_drift": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the C-ABI library (no fallback: raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MccubeB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m mccube_b200._build` "
+            "(there is no CPU fallback for the CUDA path)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mccb200_last_error().decode(errors="replace")
+        raise MccubeB200Error(f"{what} failed (status {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MccubeB200Error("mccube_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise MccubeB200Error(f"expected contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+# ------------------------------------------------------------------ descriptors
+def make_rng(key, t, *, leaf=0, n_leaves=1, partitionable=False, fold_time=True) -> Rng:
+    r = Rng()
+    r.key[0], r.key[1] = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    r.key_dev = None
+    r.t = float(np.float32(t))
+    r.t_dev = None
+    r.leaf, r.n_leaves = leaf, n_leaves
+    r.partitionable = int(bool(partitionable))
+    r.fold_time = int(bool(fold_time))
+    return r
+
+
+def make_drift(kind=0, f=None, mean=None, inv_var=None) -> Drift:
+    d = Drift()
+    d.kind = kind
+    d.f, d.mean, d.inv_var = _ptr(f), _ptr(mean), _ptr(inv_var)
+    d._keep = (f, mean, inv_var)
+    return d
+
+
+def make_cubature(k, scale=0.0, points=None, lam=None) -> Cubature:
+    c = Cubature()
+    c.k = int(k)
+    c.scale = float(np.float32(scale))
+    c.points, c.lam = _ptr(points), _ptr(lam)
+    c._keep = (points, lam)
+    return c
+
+
+def _dims_array(dims):
+    arr = (C.c_int32 * len(dims))(*[int(x) for x in dims])
+    return arr
+
+
+# ------------------------------------------------------------------ workspace cache
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (the C ABI never allocates)."""
+    key = (torch.device(device).index or 0)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _ws_cache[key] = buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    return buf
+
+
+def release_workspace():
+    _ws_cache.clear()
+
+
+# ------------------------------------------------------------------ calls
+def mc_indices(rng: Rng, n_inputs: int, count: int, replace: bool, device, out=None) -> torch.Tensor:
+    lib = load()
+    out = torch.empty(count, dtype=torch.int32, device=device) if out is None else out
+    _require_cuda(out)
+    nbytes = lib.mccb200_mc_indices_workspace_bytes(n_inputs, count, int(replace))
+    ws = workspace(nbytes, device)
+    _check(lib.mccb200_mc_indices(C.byref(rng), n_inputs, count, int(replace), out.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), _stream()), "mc_indices")
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, values, key_bits: int = 32, want_keys: bool = False):
+    """Stable argsort / sort_key_val of uint32 keys (int32 tensors reinterpreted)."""
+    lib = load()
+    _require_cuda(keys, values)
+    n = keys.numel()
+    vals_out = torch.empty(n, dtype=torch.int32, device=keys.device)
+    keys_out = torch.empty(n, dtype=torch.int32, device=keys.device) if want_keys else None
+    ws = workspace(lib.mccb200_sort_pairs_workspace_bytes(n), keys.device)
+    _check(lib.mccb200_sort_pairs(keys.data_ptr(), _ptr(values), n, key_bits, _ptr(keys_out), vals_out.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream()), "sort_pairs")
+    return (keys_out, vals_out) if want_keys else vals_out
+
+
+def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=None, out_per_part=1, in_per_part=1,
+                  n_out=None, out=None):
+    lib = load()
+    _require_cuda(y0, idx, perm)
+    _f32c(y0)
+    n, ld = y0.shape
+    n_out = idx.numel() if n_out is None else n_out
+    out = torch.empty((n_out, ld), dtype=torch.float32, device=y0.device) if out is None else out
+    _check(lib.mccb200_expand_select(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
+                                     C.byref(cub), idx.data_ptr(), _ptr(perm), out_per_part, in_per_part, n_out,
+                                     out.data_ptr(), _stream()), "expand_select")
+    return out
+
+
+def expand_all(y0, d, weighted, drift: Drift, dt, cub: Cubature):
+    lib = load()
+    _require_cuda(y0)
+    _f32c(y0)
+    n, ld = y0.shape
+    out = torch.empty((n * cub.k, ld), dtype=torch.float32, device=y0.device)
+    _check(lib.mccb200_expand_all(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
+                                  C.byref(cub), out.data_ptr(), _stream()), "expand_all")
+    return out
+
+
+def gather_rows(p, idx):
+    lib = load()
+    _require_cuda(p, idx)
+    _f32c(p)
+    out = torch.empty((idx.numel(), p.shape[1]), dtype=torch.float32, device=p.device)
+    _check(lib.mccb200_gather_rows(p.data_ptr(), p.shape[1], idx.data_ptr(), idx.numel(), out.data_ptr(), _stream()),
+           "gather_rows")
+    return out
+
+
+def normalise_weights_(y):
+    lib = load()
+    _require_cuda(y)
+    _f32c(y)
+    ws = torch.empty(1, dtype=torch.float64, device=y.device)
+    _check(lib.mccb200_normalise_weights(y.data_ptr(), y.shape[0], y.shape[1], ws.data_ptr(), _stream()),
+           "normalise_weights")
+    return y
+
+
+def stratified_keys(p, d, com):
+    lib = load()
+    _require_cuda(p, com)
+    _f32c(p)
+    keys = torch.empty(p.shape[0], dtype=torch.int32, device=p.device)
+    _check(lib.mccb200_stratified_keys(p.data_ptr(), p.shape[0], d, p.shape[1], com.data_ptr(), keys.data_ptr(),
+                                       _stream()), "stratified_keys")
+    return keys
+
+
+def box_bounds(p, dims, bits):
+    lib = load()
+    _require_cuda(p)
+    _f32c(p)
+    bounds = torch.empty(2 * len(dims), dtype=torch.float32, device=p.device)
+    ws = workspace(lib.mccb200_box_bounds_workspace_bytes(), p.device)
+    _check(lib.mccb200_box_bounds(p.data_ptr(), p.shape[0], p.shape[1], _dims_array(dims), len(dims), bits,
+                                  bounds.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "box_bounds")
+    return bounds
+
+
+def box_keys(p, dims, bits, bounds):
+    lib = load()
+    _require_cuda(p, bounds)
+    _f32c(p)
+    keys = torch.empty(p.shape[0], dtype=torch.int32, device=p.device)
+    _check(lib.mccb200_box_keys(p.data_ptr(), p.shape[0], p.shape[1], _dims_array(dims), len(dims), bits,
+                                bounds.data_ptr(), keys.data_ptr(), _stream()), "box_keys")
+    return keys
+
+
+def box_child_bounds(y0, d, drift, dt, cub, dims, bits):
+    lib = load()
+    _require_cuda(y0)
+    _f32c(y0)
+    bounds = torch.empty(2 * len(dims), dtype=torch.float32, device=y0.device)
+    ws = workspace(lib.mccb200_box_bounds_workspace_bytes(), y0.device)
+    _check(lib.mccb200_box_child_bounds(y0.data_ptr(), y0.shape[0], d, y0.shape[1], C.byref(drift),
+                                        float(np.float32(dt)), C.byref(cub), _dims_array(dims), len(dims), bits,
+                                        bounds.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "box_child_bounds")
+    return bounds
+
+
+def box_child_keys(y0, d, drift, dt, cub, dims, bits, bounds):
+    lib = load()
+    _require_cuda(y0, bounds)
+    _f32c(y0)
+    keys = torch.empty(y0.shape[0] * cub.k, dtype=torch.int32, device=y0.device)
+    _check(lib.mccb200_box_child_keys(y0.data_ptr(), y0.shape[0], d, y0.shape[1], C.byref(drift),
+                                      float(np.float32(dt)), C.byref(cub), _dims_array(dims), len(dims), bits,
+                                      bounds.data_ptr(), keys.data_ptr(), _stream()), "box_child_keys")
+    return keys
+
+
+def box_prk_step(y0, d, drift, dt, cub, dims, bits, bounds, idx_local, in_per_part, out=None):
+    lib = load()
+    _require_cuda(y0, bounds, idx_local)
+    _f32c(y0)
+    n = y0.shape[0]
+    out = torch.empty_like(y0) if out is None else out
+    nbytes = lib.mccb200_box_prk_step_workspace_bytes(n, cub.k, len(dims), bits, in_per_part)
+    ws = workspace(nbytes, y0.device)
+    _check(lib.mccb200_box_prk_step(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                    _dims_array(dims), len(dims), bits, bounds.data_ptr(), idx_local.data_ptr(),
+                                    idx_local.numel(), in_per_part, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _stream()), "box_prk_step")
+    return out
+
+
+def column_means(p, d, weights=None):
+    """(mean[d] float64, weight_total) -- center_of_mass."""
+    lib = load()
+    _require_cuda(p, weights)
+    _f32c(p)
+    n, ld = p.shape
+    sums = torch.zeros(d + 1, dtype=torch.float64, device=p.device)
+    ws = 1 if weights is None else weights.stride(0)
+    _check(lib.mccb200_moments_sum(p.data_ptr(), n, d, ld, _ptr(weights), ws, sums.data_ptr(), _stream()),
+           "moments_sum")
+    return sums[:d] / sums[d], sums[d]
+
+
+def moments(p, d, weights=None):
+    """(sum[d], weight_total, m2[d, d]) in float64 about the weighted mean."""
+    lib = load()
+    _require_cuda(p, weights)
+    _f32c(p)
+    n, ld = p.shape
+    w_stride = 1 if weights is None else weights.stride(0)
+    sums = torch.zeros(d + 1, dtype=torch.float64, device=p.device)
+    _check(lib.mccb200_moments_sum(p.data_ptr(), n, d, ld, _ptr(weights), w_stride, sums.data_ptr(), _stream()),
+           "moments_sum")
+    mean64 = sums[:d] / sums[d]
+    centre = mean64.to(torch.float32).contiguous()
+    m2 = torch.zeros((d, d), dtype=torch.float64, device=p.device)
+    _check(lib.mccb200_moments_m2(p.data_ptr(), n, d, ld, _ptr(weights), w_stride, centre.data_ptr(), m2.data_ptr(),
+                                  _stream()), "moments_m2")
+    # exact shift back from the fp32 centre to the fp64 mean: sum w (x-c)(x-c)^T - W (m-c)(m-c)^T
+    delta = mean64 - centre.to(torch.float64)
+    m2 = m2 - sums[d] * torch.outer(delta, delta)
+    return mean64, sums[d], m2
+
+
+def gaussian_full_drift(y, d, mean, prec):
+    lib = load()
+    _require_cuda(y, mean, prec)
+    _f32c(y)
+    f = torch.empty((y.shape[0], d), dtype=torch.float32, device=y.device)
+    _check(lib.mccb200_gaussian_full_drift(y.data_ptr(), y.shape[0], d, y.shape[1], mean.data_ptr(), prec.data_ptr(),
+                                           f.data_ptr(), _stream()), "gaussian_full_drift")
+    return f

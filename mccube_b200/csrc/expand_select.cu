@@ -1,0 +1,305 @@
+// Fused expand + select: the MCCSolver step without the n*k*d expansion (sm_100a).
+//
+// Replaces, for /root/reference/mccube/_solvers.py:125-144,
+//   Euler.step (y0 + vf_prod) -> MCCTerm.prod broadcast add (_term.py:70-77)
+//   -> reshape [n*k, d] (_solvers.py:136) -> kernel gather p[idx] (random.py:65 /
+//   base.py:170-177 with the shared local index vector of quirk Q4).
+// Only the selected children are ever computed: read n_out parent rows, write n_out rows
+// (2 * n_out * d * 4 algorithmic bytes).  HBM-bound; 128-bit loads/stores when d % 4 == 0.
+//
+// fp32 op order is the reference's, with explicit round-to-nearest intrinsics so ptxas
+// cannot contract into FMA:   y1 = y0 + (dt * f + noise).
+#include "common.cuh"
+#include "expand.cuh"
+
+namespace mccb {
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+  using T = typename VecT<VEC>::type;
+  T t = __ldg(reinterpret_cast<const T*>(p));
+  const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+
+// Streaming (read-once) load: bypass L1 allocation.
+template <int VEC>
+__device__ __forceinline__ void load_vec_stream(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  } else if constexpr (VEC == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[0]) : "l"(p));
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_stream(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  } else if constexpr (VEC == 2) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+  } else {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v[0]) : "memory");
+  }
+}
+
+
+constexpr int EX_THREADS = 256;
+constexpr int EX_UNROLL = 4;
+
+__device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r) {
+  if (a.perm) {
+    uint32_t b = (uint32_t)(r / a.out_per_part);
+    uint32_t l = (uint32_t)(r - (uint64_t)b * a.out_per_part);
+    return a.perm[(uint64_t)b * a.in_per_part + a.idx[l]];
+  }
+  return a.idx ? a.idx[r] : (uint32_t)r;
+}
+
+template <int VEC, int DRIFT, bool TABLE>
+__global__ void __launch_bounds__(EX_THREADS)
+expand_kernel(const ExpandArgs a) {
+  const int row_in_iter = threadIdx.x / a.vpr;
+  const int col = (threadIdx.x - row_in_iter * a.vpr) * VEC;
+  const bool active = row_in_iter < a.rows_per_iter;
+  if (!active) return;
+
+  float mean[VEC], ivar[VEC];
+  if (DRIFT == 2) {
+    load_vec<VEC>(a.mean + col, mean);
+    load_vec<VEC>(a.inv_var + col, ivar);
+  }
+  const bool do_w = a.weighted && col == 0;
+
+  const uint64_t rows_per_cta_iter = (uint64_t)a.rows_per_iter * EX_UNROLL;
+  for (uint64_t base = (uint64_t)blockIdx.x * rows_per_cta_iter; base < a.n_out;
+       base += (uint64_t)gridDim.x * rows_per_cta_iter) {
+    uint32_t c[EX_UNROLL];
+    uint64_t r[EX_UNROLL];
+    bool ok[EX_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EX_UNROLL; ++u) {
+      r[u] = base + (uint64_t)u * a.rows_per_iter + row_in_iter;
+      ok[u] = r[u] < a.n_out;
+      c[u] = ok[u] ? child_of_row(a, r[u]) : 0u;
+    }
+    float y[EX_UNROLL][VEC], f[EX_UNROLL][VEC];
+    uint32_t pi[EX_UNROLL], pj[EX_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EX_UNROLL; ++u) {
+      if (a.k_shift != 0xFFFFFFFFu) {
+        pi[u] = c[u] >> a.k_shift;
+        pj[u] = c[u] & (a.k - 1u);
+      } else {
+        pi[u] = c[u] / a.k;
+        pj[u] = c[u] - pi[u] * a.k;
+      }
+      if (ok[u]) {
+        load_vec_stream<VEC>(a.y0 + (uint64_t)pi[u] * a.ld + col, y[u]);
+        if (DRIFT == 1) load_vec_stream<VEC>(a.f + (uint64_t)pi[u] * a.d + col, f[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EX_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      float out[VEC];
+      float tab[VEC];
+      if (TABLE) load_vec<VEC>(a.points + (uint64_t)pj[u] * a.d + col, tab);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float fv;
+        if (DRIFT == 2) fv = __fmul_rn(__fsub_rn(mean[e], y[u][e]), ivar[e]);
+        else if (DRIFT == 1) fv = f[u][e];
+        else fv = 0.0f;
+        float noise;
+        if (TABLE) noise = tab[e];
+        else noise = hadamard_neg(pj[u], a.half_mask, (uint32_t)(col + e)) ? -a.scale : a.scale;
+        float step = __fadd_rn(__fmul_rn(a.dt, fv), noise);
+        out[e] = __fadd_rn(y[u][e], step);
+      }
+      store_vec_stream<VEC>(a.y1 + r[u] * a.ld + col, out);
+      if (do_w) {
+        // quirk Q3 (_solvers.py:138-141): weights are flattened from a [k, n] array
+        uint64_t cc = c[u];
+        uint32_t jn = (uint32_t)(cc / a.n);
+        uint64_t in = cc - (uint64_t)jn * a.n;
+        float lam = a.lam ? a.lam[jn] : __fdiv_rn(1.0f, (float)a.k);
+        a.y1[r[u] * a.ld + a.d] = __fmul_rn(a.y0[in * a.ld + a.d], lam);
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(EX_THREADS)
+gather_kernel(const float* __restrict__ in, int ld, int vpr, int rows_per_iter, int tail_col, int tail,
+              const uint32_t* __restrict__ idx, uint64_t n_out, float* __restrict__ out) {
+  const int row_in_iter = threadIdx.x / vpr;
+  const int col = (threadIdx.x - row_in_iter * vpr) * VEC;
+  if (row_in_iter >= rows_per_iter) return;
+  (void)tail_col; (void)tail;
+  for (uint64_t r = (uint64_t)blockIdx.x * rows_per_iter + row_in_iter; r < n_out;
+       r += (uint64_t)gridDim.x * rows_per_iter) {
+    float v[VEC];
+    load_vec_stream<VEC>(in + (uint64_t)idx[r] * ld + col, v);
+    store_vec_stream<VEC>(out + r * ld + col, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+weight_sum_kernel(const float* __restrict__ y, uint64_t n, int ld, double* __restrict__ out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+    acc += (double)y[r * ld + (ld - 1)];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+weight_div_kernel(float* __restrict__ y, uint64_t n, int ld, const double* __restrict__ total) {
+  const float s = (float)*total;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+    y[r * ld + (ld - 1)] = __fdiv_rn(y[r * ld + (ld - 1)], s);
+}
+
+static int pick_vec(int d, int ld, const void* p0, const void* p1) {
+  uintptr_t a = (uintptr_t)p0 | (uintptr_t)p1;
+  if (d % 4 == 0 && ld % 4 == 0 && a % 16 == 0) return 4;
+  if (d % 2 == 0 && ld % 2 == 0 && a % 8 == 0) return 2;
+  return 1;
+}
+
+template <int VEC>
+static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
+  const bool table = a.points != nullptr;
+#define MCCB_LAUNCH(D, T) expand_kernel<VEC, D, T><<<grid, EX_THREADS, 0, st>>>(a)
+  if (a.drift_kind == 2) { if (table) MCCB_LAUNCH(2, true); else MCCB_LAUNCH(2, false); }
+  else if (a.drift_kind == 1) { if (table) MCCB_LAUNCH(1, true); else MCCB_LAUNCH(1, false); }
+  else { if (table) MCCB_LAUNCH(0, true); else MCCB_LAUNCH(0, false); }
+#undef MCCB_LAUNCH
+}
+
+int fill_expand_args(ExpandArgs& a, const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
+                     float dt, const mccb200_cubature* cub) {
+  MCCB_REQUIRE(y0 && drift && cub, "expand: NULL argument");
+  MCCB_REQUIRE(d >= 1 && d <= 4096, "expand: d=%d out of range", d);
+  MCCB_REQUIRE(cub->k >= 1, "expand: k=%d", cub->k);
+  MCCB_REQUIRE((uint64_t)n * (uint64_t)cub->k <= 0x100000000ull, "expand: n*k=%llu exceeds 2^32 child ids",
+               (unsigned long long)(n * (uint64_t)cub->k));
+  MCCB_REQUIRE(drift->kind >= 0 && drift->kind <= 2, "expand: drift kind %d", drift->kind);
+  MCCB_REQUIRE(drift->kind != 1 || drift->f, "expand: drift kind 1 needs f");
+  MCCB_REQUIRE(drift->kind != 2 || (drift->mean && drift->inv_var), "expand: drift kind 2 needs mean, inv_var");
+  a.y0 = y0; a.n = n; a.d = d; a.ld = d + (weighted ? 1 : 0); a.weighted = weighted;
+  a.drift_kind = drift->kind; a.f = drift->f; a.mean = drift->mean; a.inv_var = drift->inv_var;
+  a.dt = dt;
+  a.k = (uint32_t)cub->k;
+  const bool pow2 = (a.k & (a.k - 1u)) == 0;
+  a.k_shift = 0xFFFFFFFFu;
+  if (pow2) { a.k_shift = 0; while ((1u << a.k_shift) < a.k) ++a.k_shift; }
+  a.points = cub->points; a.scale = cub->scale; a.lam = cub->lam;
+  if (!a.points) {
+    MCCB_REQUIRE(pow2 && a.k >= 2, "expand: Hadamard cubature needs k = power of two >= 2 (k=%u)", a.k);
+    MCCB_REQUIRE((uint32_t)d <= a.k / 2 || d == 1, "expand: Hadamard cubature needs d <= k/2 (d=%d, k=%u)", d, a.k);
+    a.half_mask = a.k / 2 - 1u;
+  } else {
+    a.half_mask = 0;
+  }
+  return MCCB200_OK;
+}
+
+}  // namespace mccb
+
+using namespace mccb;
+
+static int run_expand(ExpandArgs& a, cudaStream_t st) {
+  if (a.n_out == 0) return MCCB200_OK;
+  int vec = a.weighted ? 1 : pick_vec(a.d, a.ld, a.y0, a.y1);
+  if (a.drift_kind == 1 && ((uintptr_t)a.f % 16 != 0)) vec = 1;
+  if (a.points && ((uintptr_t)a.points % 16 != 0)) vec = 1;
+  if (a.drift_kind == 2 && (((uintptr_t)a.mean | (uintptr_t)a.inv_var) % 16 != 0)) vec = 1;
+  a.vpr = a.d / vec;
+  MCCB_REQUIRE(a.vpr <= EX_THREADS, "expand: d=%d too wide for the row mapping", a.d);
+  a.rows_per_iter = EX_THREADS / a.vpr;
+  uint64_t rows_per_cta = (uint64_t)a.rows_per_iter * EX_UNROLL;
+  uint64_t want = (a.n_out + rows_per_cta - 1) / rows_per_cta;
+  int grid = (int)min(want, (uint64_t)sm_count() * 8);
+  if (vec == 4) launch_expand<4>(a, grid, st);
+  else if (vec == 2) launch_expand<2>(a, grid, st);
+  else launch_expand<1>(a, grid, st);
+  return check_launch("expand");
+}
+
+extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
+                                     float dt, const mccb200_cubature* cub, const uint32_t* idx,
+                                     const uint32_t* perm, uint64_t out_per_part, uint64_t in_per_part,
+                                     uint64_t n_out, float* y1, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, weighted, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(idx && y1, "expand_select: NULL idx / y1");
+  if (perm) {
+    MCCB_REQUIRE(out_per_part >= 1 && in_per_part >= 1 && n_out % out_per_part == 0,
+                 "expand_select: n_out=%llu not a multiple of out_per_part=%llu", (unsigned long long)n_out,
+                 (unsigned long long)out_per_part);
+    MCCB_REQUIRE(out_per_part < 0x100000000ull && in_per_part < 0x100000000ull, "expand_select: partition too large");
+  }
+  a.idx = idx; a.perm = perm; a.out_per_part = (uint32_t)out_per_part; a.in_per_part = (uint32_t)in_per_part;
+  a.n_out = n_out; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_expand_all(const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
+                                  float dt, const mccb200_cubature* cub, float* y1, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, weighted, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(y1, "expand_all: NULL y1");
+  a.idx = nullptr; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
+  a.n_out = n * (uint64_t)cub->k; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_gather_rows(const float* in, int ld, const uint32_t* idx, uint64_t n_out, float* out,
+                                   void* stream) {
+  MCCB_REQUIRE(in && idx && out && ld >= 1, "gather_rows: bad argument");
+  if (n_out == 0) return MCCB200_OK;
+  int vec = pick_vec(ld, ld, in, out);
+  int vpr = ld / vec;
+  MCCB_REQUIRE(vpr <= EX_THREADS, "gather_rows: ld=%d too wide", ld);
+  int rpi = EX_THREADS / vpr;
+  int grid = (int)min((n_out + rpi - 1) / rpi, (uint64_t)sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 4) gather_kernel<4><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
+  else if (vec == 2) gather_kernel<2><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
+  else gather_kernel<1><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
+  return check_launch("gather_rows");
+}
+
+extern "C" int mccb200_normalise_weights(float* y, uint64_t n, int ld, double* workspace, void* stream) {
+  MCCB_REQUIRE(y && workspace && ld >= 2, "normalise_weights: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(workspace, 0, sizeof(double), st) != cudaSuccess)
+    return fail(MCCB200_ERR_CUDA, "normalise_weights: memset failed");
+  int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
+  if (grid < 1) grid = 1;
+  weight_sum_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);
+  weight_div_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);
+  return check_launch("normalise_weights");
+}

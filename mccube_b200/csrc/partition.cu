@@ -1,0 +1,232 @@
+// Partitioning keys (sm_100a): stratified norms and integer box keys, on materialised rows
+// and on the implicit children of an expansion step.
+//
+// Replaces /root/reference/mccube/_kernels/stratified.py:36-45 (COM-centre -> norm ->
+// argsort; the argsort itself is radix_sort.cu) and provides BoxPartitionKernel's key, a
+// kernel the brief names but the reference does not contain: its
+// definition is oracle/mccube_ref.py::box_keys.
+#include "common.cuh"
+#include "expand.cuh"
+
+namespace mccb {
+
+struct BoxSpec {
+  int n_dims, bits;
+  int dims[MCCB200_BOX_MAX_DIMS];
+};
+
+constexpr int BB_THREADS = 256;
+constexpr int BB_MAX_CTAS = 1024;
+
+__global__ void __launch_bounds__(256)
+stratified_keys_kernel(const float* __restrict__ p, uint64_t n, int d, int ld, const float* __restrict__ com,
+                       uint32_t* __restrict__ keys) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const float* row = p + r * ld;
+    float acc = 0.0f;
+    for (int c = 0; c < d; ++c) {
+      float v = __fsub_rn(row[c], __ldg(com + c));
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
+    // norm >= 0 (or NaN): the IEEE bit pattern of a non-negative float is order preserving.
+    keys[r] = __float_as_uint(__fsqrt_rn(acc));
+  }
+}
+
+__device__ __forceinline__ void block_minmax(float lo, float hi, float* out_lo, float* out_hi) {
+  __shared__ float s_lo[BB_THREADS / 32], s_hi[BB_THREADS / 32];
+  for (int o = 16; o; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < BB_THREADS / 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+    *out_lo = lo; *out_hi = hi;
+  }
+}
+
+// partials layout: [cta][dim][2]
+__global__ void __launch_bounds__(BB_THREADS)
+box_bounds_rows_kernel(const float* __restrict__ p, uint64_t n, int ld, BoxSpec spec, float* __restrict__ partials) {
+  for (int q = 0; q < spec.n_dims; ++q) {
+    float lo = INFINITY, hi = -INFINITY;
+    const int c = spec.dims[q];
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+      float v = p[r * ld + c];
+      lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    block_minmax(lo, hi, partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
+                 partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
+  }
+}
+
+__global__ void __launch_bounds__(BB_THREADS)
+box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ partials) {
+  for (int q = 0; q < spec.n_dims; ++q) {
+    float lo = INFINITY, hi = -INFINITY;
+    const int c = spec.dims[q];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+      float y = a.y0[i * a.ld + c];
+      float fv = drift_value(a, i, c, y);
+      if (a.points) {
+        for (uint32_t j = 0; j < a.k; ++j) {
+          float v = child_value(a, y, fv, noise_value(a, j, c));
+          lo = fminf(lo, v); hi = fmaxf(hi, v);
+        }
+      } else {
+        // every Hadamard column takes both signs over the k rows (rows j and j + k/2 negate)
+        float v0 = child_value(a, y, fv, -a.scale), v1 = child_value(a, y, fv, a.scale);
+        lo = fminf(lo, fminf(v0, v1)); hi = fmaxf(hi, fmaxf(v0, v1));
+      }
+    }
+    block_minmax(lo, hi, partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
+                 partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
+  }
+}
+
+__global__ void box_bounds_final_kernel(const float* __restrict__ partials, int n_ctas, BoxSpec spec,
+                                        float* __restrict__ bounds) {
+  const int q = threadIdx.x;
+  if (q >= spec.n_dims) return;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int b = 0; b < n_ctas; ++b) {
+    lo = fminf(lo, partials[((size_t)b * spec.n_dims + q) * 2]);
+    hi = fmaxf(hi, partials[((size_t)b * spec.n_dims + q) * 2 + 1]);
+  }
+  float rng = __fsub_rn(hi, lo);
+  bounds[q] = lo;
+  bounds[spec.n_dims + q] = rng > 0.0f ? __fdiv_rn((float)(1 << spec.bits), rng) : 0.0f;
+}
+
+__device__ __forceinline__ uint32_t box_cell(float x, float lo, float inv_h, int bits) {
+  float v = __fmul_rn(__fsub_rn(x, lo), inv_h);
+  float c = fminf(fmaxf(floorf(v), 0.0f), (float)((1 << bits) - 1));
+  return (uint32_t)c;  // NaN -> 0
+}
+
+__global__ void __launch_bounds__(256)
+box_keys_rows_kernel(const float* __restrict__ p, uint64_t n, int ld, BoxSpec spec, const float* __restrict__ bounds,
+                     uint32_t* __restrict__ keys) {
+  float lo[MCCB200_BOX_MAX_DIMS], ih[MCCB200_BOX_MAX_DIMS];
+  for (int q = 0; q < spec.n_dims; ++q) { lo[q] = bounds[q]; ih[q] = bounds[spec.n_dims + q]; }
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t key = 0;
+    for (int q = 0; q < spec.n_dims; ++q)
+      key = (key << spec.bits) | box_cell(p[r * ld + spec.dims[q]], lo[q], ih[q], spec.bits);
+    keys[r] = key;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+box_keys_children_kernel(ExpandArgs a, BoxSpec spec, const float* __restrict__ bounds, uint32_t* __restrict__ keys) {
+  float lo[MCCB200_BOX_MAX_DIMS], ih[MCCB200_BOX_MAX_DIMS];
+  for (int q = 0; q < spec.n_dims; ++q) { lo[q] = bounds[q]; ih[q] = bounds[spec.n_dims + q]; }
+  const uint64_t total = a.n * (uint64_t)a.k;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = c / a.k;
+    const uint32_t j = (uint32_t)(c - i * a.k);
+    uint32_t key = 0;
+    for (int q = 0; q < spec.n_dims; ++q) {
+      const int col = spec.dims[q];
+      float y = __ldg(a.y0 + i * a.ld + col);
+      float x = child_value(a, y, drift_value(a, i, col, y), noise_value(a, j, col));
+      key = (key << spec.bits) | box_cell(x, lo[q], ih[q], spec.bits);
+    }
+    keys[c] = key;
+  }
+}
+
+int make_box_spec(BoxSpec& s, const int32_t* dims_host, int n_dims, int bits, int d) {
+  MCCB_REQUIRE(dims_host && n_dims >= 1 && n_dims <= MCCB200_BOX_MAX_DIMS, "box: n_dims=%d out of range", n_dims);
+  MCCB_REQUIRE(bits >= 1 && n_dims * bits <= 32, "box: n_dims*bits=%d exceeds 32", n_dims * bits);
+  s.n_dims = n_dims; s.bits = bits;
+  for (int q = 0; q < n_dims; ++q) {
+    MCCB_REQUIRE(dims_host[q] >= 0 && dims_host[q] < d, "box: dim %d out of range [0, %d)", dims_host[q], d);
+    s.dims[q] = dims_host[q];
+  }
+  return MCCB200_OK;
+}
+
+}  // namespace mccb
+
+using namespace mccb;
+
+extern "C" size_t mccb200_box_bounds_workspace_bytes(void) {
+  return (size_t)BB_MAX_CTAS * MCCB200_BOX_MAX_DIMS * 2 * sizeof(float);
+}
+
+extern "C" int mccb200_stratified_keys(const float* p, uint64_t n, int d, int ld, const float* com, uint32_t* keys,
+                                       void* stream) {
+  MCCB_REQUIRE(p && com && keys && d >= 1 && ld >= d, "stratified_keys: bad argument");
+  if (n == 0) return MCCB200_OK;
+  int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
+  stratified_keys_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, d, ld, com, keys);
+  return check_launch("stratified_keys");
+}
+
+extern "C" int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int32_t* dims_host, int n_dims, int bits,
+                                  float* bounds, void* workspace, size_t workspace_bytes, void* stream) {
+  BoxSpec s;
+  int rc = make_box_spec(s, dims_host, n_dims, bits, ld);
+  if (rc) return rc;
+  MCCB_REQUIRE(p && bounds && n >= 1, "box_bounds: bad argument");
+  if (!workspace || workspace_bytes < mccb200_box_bounds_workspace_bytes())
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "box_bounds: workspace too small");
+  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 4));
+  cudaStream_t st = (cudaStream_t)stream;
+  box_bounds_rows_kernel<<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
+  box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  return check_launch("box_bounds");
+}
+
+extern "C" int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32_t* dims_host, int n_dims, int bits,
+                                const float* bounds, uint32_t* keys, void* stream) {
+  BoxSpec s;
+  int rc = make_box_spec(s, dims_host, n_dims, bits, ld);
+  if (rc) return rc;
+  MCCB_REQUIRE(p && bounds && keys, "box_keys: NULL argument");
+  if (n == 0) return MCCB200_OK;
+  int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
+  box_keys_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, ld, s, bounds, keys);
+  return check_launch("box_keys");
+}
+
+extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
+                                        float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
+                                        int bits, float* bounds, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  BoxSpec s;
+  int rc = make_box_spec(s, dims_host, n_dims, bits, d);
+  if (rc) return rc;
+  ExpandArgs a{};
+  rc = fill_expand_args(a, y0, n, d, ld != d, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(bounds && n >= 1, "box_child_bounds: bad argument");
+  if (!workspace || workspace_bytes < mccb200_box_bounds_workspace_bytes())
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "box_child_bounds: workspace too small");
+  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 4));
+  cudaStream_t st = (cudaStream_t)stream;
+  box_bounds_children_kernel<<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
+  box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  return check_launch("box_child_bounds");
+}
+
+extern "C" int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
+                                      float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
+                                      int bits, const float* bounds, uint32_t* keys, void* stream) {
+  BoxSpec s;
+  int rc = make_box_spec(s, dims_host, n_dims, bits, d);
+  if (rc) return rc;
+  ExpandArgs a{};
+  rc = fill_expand_args(a, y0, n, d, ld != d, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(bounds && keys, "box_child_keys: NULL argument");
+  if (n == 0) return MCCB200_OK;
+  uint64_t total = n * (uint64_t)cub->k;
+  int grid = (int)min((total + 255) / 256, (uint64_t)sm_count() * 16);
+  box_keys_children_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, s, bounds, keys);
+  return check_launch("box_child_keys");
+}

@@ -1,0 +1,166 @@
+// Resampling indices of MonteCarloKernel, bit-exact with jax.random (sm_100a).
+//
+// Replaces, for /root/reference/mccube/_kernels/random.py:56-65,
+//   force_bitcast_convert_type -> jr.fold_in -> split_by_tree -> jr.choice
+// i.e. (jax/_src/random.py) choice -> permutation -> _shuffle -> random_bits + sort_key_val
+// when replace=False, and choice -> randint when replace=True.  Both values of
+// jax_threefry_partitionable are implemented.  The oracle restatement is
+// oracle/jax_random.py; SURVEY.md Appendix A states the algorithm.
+#include "common.cuh"
+
+namespace mccb {
+
+int sort_pairs_impl(const uint32_t*, const uint32_t*, uint64_t, int, uint32_t*, uint32_t*, void*, size_t,
+                    cudaStream_t);
+size_t sort_pairs_ws(uint64_t);
+
+constexpr int MAX_ROUNDS = 8;
+
+// Derived keys, produced on the device so key / t may live in device memory.
+struct DerivedKeys {
+  u32x2 step_key;               // key handed to jr.choice
+  u32x2 round_sub[MAX_ROUNDS];  // sort-key generator of each _shuffle round
+  u32x2 randint_hi, randint_lo; // k1, k2 of randint
+};
+
+__global__ void derive_keys_kernel(mccb200_rng rng, int rounds, DerivedKeys* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  u32x2 key = {rng.key[0], rng.key[1]};
+  if (rng.key_dev) key = {rng.key_dev[0], rng.key_dev[1]};
+  const bool part = rng.partitionable != 0;
+  if (rng.fold_time) {
+    float t = rng.t_dev ? *rng.t_dev : rng.t;
+    key = fold_in_key(key, __float_as_uint(t));
+    key = split_key(key, rng.n_leaves, rng.leaf, part);
+  }
+  out->step_key = key;
+  out->randint_hi = split_key(key, 2, 0, part);
+  out->randint_lo = split_key(key, 2, 1, part);
+  u32x2 k = key;
+  for (int r = 0; r < rounds && r < MAX_ROUNDS; ++r) {
+    u32x2 nk = split_key(k, 2, 0, part);
+    out->round_sub[r] = split_key(k, 2, 1, part);
+    k = nk;
+  }
+}
+
+// random_bits(sub, 32, (n,)).  Original mode: one threefry block yields elements i and
+// i + ceil(n/2), so each thread produces a pair; partitionable mode: one block per element.
+__global__ void __launch_bounds__(256)
+random_bits_kernel(const DerivedKeys* __restrict__ dk, int round, uint32_t n, int partitionable,
+                   uint32_t* __restrict__ out) {
+  const u32x2 key = dk->round_sub[round];
+  const uint32_t h = (n + 1u) >> 1;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  if (partitionable) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      u32x2 o = threefry2x32(key.x, key.y, 0u, i);
+      out[i] = o.x ^ o.y;
+    }
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < h; i += stride) {
+      uint32_t hi = i + h;
+      u32x2 o = threefry2x32(key.x, key.y, i, hi < n ? hi : 0u);
+      out[i] = o.x;
+      if (hi < n) out[hi] = o.y;
+    }
+  }
+}
+
+// jr.randint(key, (count,), 0, span) for int32 (jax/_src/random.py randint).
+__global__ void __launch_bounds__(256)
+randint_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint32_t span, int partitionable,
+               uint32_t* __restrict__ out) {
+  const u32x2 k1 = dk->randint_hi, k2 = dk->randint_lo;
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  const bool part = partitionable != 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    uint32_t hi = random_bits32_at(k1, i, count, part);
+    uint32_t lo = random_bits32_at(k2, i, count, part);
+    uint32_t off = (hi % span) * mult + (lo % span);
+    out[i] = off % span;
+  }
+}
+
+static int shuffle_rounds(uint64_t size) {
+  if (size < 1) size = 1;
+  return (int)ceil(3.0 * log((double)size) / log(4294967295.0));
+}
+
+struct IdxPlan {
+  size_t off_dk, off_keys, off_va, off_vb, off_sort, total;
+  int rounds;
+};
+
+static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
+  IdxPlan p{};
+  p.rounds = replace ? 0 : shuffle_rounds(n_inputs);
+  p.off_dk = 0;
+  size_t cur = align_up(sizeof(DerivedKeys), 256);
+  if (!replace) {
+    size_t arr = align_up((size_t)n_inputs * 4, 256);
+    p.off_keys = cur; cur += arr;
+    p.off_va = cur; cur += arr;
+    p.off_vb = cur; cur += arr;
+    p.off_sort = cur; cur += sort_pairs_ws(n_inputs);
+  }
+  p.total = cur;
+  (void)count;
+  return p;
+}
+
+}  // namespace mccb
+
+using namespace mccb;
+
+extern "C" size_t mccb200_mc_indices_workspace_bytes(uint64_t n_inputs, uint64_t count, int replace) {
+  return make_idx_plan(n_inputs, count, replace).total;
+}
+
+extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, int replace,
+                                  uint32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MCCB_REQUIRE(rng && idx_out, "mc_indices: NULL argument");
+  MCCB_REQUIRE(n_inputs >= 1 && n_inputs < 0xFFFFFFFFull, "mc_indices: n_inputs %llu out of range",
+               (unsigned long long)n_inputs);
+  MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "mc_indices: bad leaf %u / %u", rng->leaf,
+               rng->n_leaves);
+  MCCB_REQUIRE(replace || count <= n_inputs, "mc_indices: cannot draw %llu > %llu without replacement",
+               (unsigned long long)count, (unsigned long long)n_inputs);
+  IdxPlan p = make_idx_plan(n_inputs, count, replace);
+  MCCB_REQUIRE(p.rounds <= MAX_ROUNDS, "mc_indices: too many rounds");
+  if (workspace_bytes < p.total || workspace == nullptr)
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_indices: workspace %zu < %zu", workspace_bytes, p.total);
+  if (count == 0) return MCCB200_OK;
+  char* w = (char*)workspace;
+  DerivedKeys* dk = (DerivedKeys*)(w + p.off_dk);
+  derive_keys_kernel<<<1, 32, 0, st>>>(*rng, p.rounds, dk);
+  const int sms = sm_count();
+  if (replace) {
+    int grid = (int)min((uint64_t)(count + 255) / 256, (uint64_t)sms * 8);
+    randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out);
+    return check_launch("mc_indices(randint)");
+  }
+  uint32_t* keys = (uint32_t*)(w + p.off_keys);
+  uint32_t* va = (uint32_t*)(w + p.off_va);
+  uint32_t* vb = (uint32_t*)(w + p.off_vb);
+  void* sort_ws = w + p.off_sort;
+  size_t sort_ws_bytes = p.total - p.off_sort;
+  const uint32_t n = (uint32_t)n_inputs;
+  const uint32_t work = rng->partitionable ? n : (n + 1) / 2;
+  int grid = (int)min(((uint64_t)work + 255) / 256, (uint64_t)sms * 8);
+  const uint32_t* src = nullptr;  // implicit arange(n)
+  uint32_t* dst = va;
+  for (int r = 0; r < p.rounds; ++r) {
+    random_bits_kernel<<<grid, 256, 0, st>>>(dk, r, n, rng->partitionable, keys);
+    int rc = sort_pairs_impl(keys, src, n, 32, nullptr, dst, sort_ws, sort_ws_bytes, st);
+    if (rc) return rc;
+    src = dst;
+    dst = (dst == va) ? vb : va;
+  }
+  if (cudaMemcpyAsync(idx_out, src, (size_t)count * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return fail(MCCB200_ERR_CUDA, "mc_indices: copy failed");
+  return check_launch("mc_indices(shuffle)");
+}
