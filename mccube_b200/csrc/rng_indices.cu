@@ -84,6 +84,10 @@ randint_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint32_t span
   }
 }
 
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t count, uint32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
 static int shuffle_rounds(uint64_t size) {
   if (size < 1) size = 1;
   return (int)ceil(3.0 * log((double)size) / log(4294967295.0));
@@ -142,6 +146,10 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
     int grid = (int)min((uint64_t)(count + 255) / 256, (uint64_t)sms * 8);
     randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out);
     return check_launch("mc_indices(randint)");
+  }
+  if (p.rounds == 0) {  // n_inputs == 1: _shuffle runs zero rounds, the permutation is the identity
+    iota_kernel<<<1, 256, 0, st>>>((uint32_t)count, idx_out);
+    return check_launch("mc_indices(identity)");
   }
   uint32_t* keys = (uint32_t*)(w + p.off_keys);
   uint32_t* va = (uint32_t*)(w + p.off_va);

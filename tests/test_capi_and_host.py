@@ -1,0 +1,139 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol that
+include/mccube_b200.h declares (no compute calls), and the host-side mirror of the reference
+API behaves like the reference's own tests expect."""
+import re
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import mccube_b200 as mccube
+from mccube_b200 import _lib
+from mccube_b200 import diffrax_compat as dfx
+from oracle import mccube_ref as ref
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "mccube_b200.h").read_text()
+    declared = set(re.findall(r"MCCB200_API[^;(]*?\b(mccb200_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert lib.mccb200_version() == 100
+    # host-only entry points are callable without a GPU
+    assert lib.mccb200_sort_pairs_workspace_bytes(1 << 20) > 3 * 4 * (1 << 20)
+    assert lib.mccb200_mc_indices_workspace_bytes(1 << 14, 512, 1) < 4096
+
+
+def test_no_cpu_fallback():
+    p = torch.ones(4, 2)
+    with pytest.raises(_lib.MccubeB200Error, match="CUDA"):
+        _lib.gather_rows(p, torch.zeros(1, dtype=torch.int32))
+    k = mccube.MonteCarloKernel(2, key=42)
+    solver = mccube.MCCSolver(dfx.Euler(), k)
+    with pytest.raises(_lib.MccubeB200Error, match="CUDA"):
+        solver.step(None, 0.0, 0.05, p, None, None, False)
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "mccube_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_solver_init_errors_and_warnings():
+    # /root/reference/tests/test_solvers.py:55-64,78-79
+    with pytest.raises(ValueError) as e, pytest.warns(UserWarning) as w:
+        mccube.MCCSolver(dfx.EulerHeun(), mccube.MonteCarloKernel(10, key=42), 0)
+    assert "n_substeps must be at least one;" in e.value.args[0]
+    assert len(w) == 1 and "diffrax.Euler solver" in w[0].message.args[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        s = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(10, key=42))
+    assert s.term_structure is mccube.MCCTerm and s.interpolation_cls is dfx.LocalLinearInterpolation
+
+
+def test_step_times_match_oracle():
+    for (t0, t1, dt0, td) in [(0.0, 25.6, 0.05, np.float32), (0.0, 51.2, 0.05, np.float64), (1.0, 1.37, 0.1, np.float32)]:
+        assert dfx.step_times(t0, t1, dt0, td) == ref.step_times(t0, t1, dt0, td)
+    s = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(10, key=42), n_substeps=3)
+    assert s.substep_times(np.float32(0.3), np.float32(0.35)) == ref.substep_times(np.float32(0.3), np.float32(0.35), 3)
+
+
+@pytest.mark.parametrize("d", [3, 5, 10])
+def test_local_linear_cubature_path(d):
+    # /root/reference/tests/test_path.py:10-23
+    f = mccube.Hadamard(mccube.GaussianRegion(d))
+    path = mccube.LocalLinearCubaturePath(f)
+    assert np.array_equal(np.abs(path.evaluate(0.0)), np.zeros(f.stacked_points.shape))
+    assert np.array_equal(path.evaluate(1.0), path.evaluate(0.0, 1.0))
+    assert np.array_equal(path.evaluate(0.0, 1.0), f.stacked_points.astype(np.float32))
+    assert np.array_equal(path.evaluate(0.0, 0.5), (np.float32(np.sqrt(np.float32(0.5))) * path.evaluate(0.0, 1.0)))
+    assert np.array_equal(path.weights, f.stacked_weights)
+    assert np.array_equal(f.points, ref.hadamard_points(d)) and f.point_count == ref.hadamard_point_count(d)
+
+
+def test_mcc_term_shapes():
+    # /root/reference/tests/test_term.py:8-48
+    class Control:
+        t0, t1 = 0, 1
+
+        def evaluate(self, t0, t1=None, left=True):
+            return {"y": torch.ones((8, 2))}
+
+    ode = dfx.ODETerm(lambda t, y, args: {"y": -y["y"]})
+    cde = dfx.WeaklyDiagonalControlTerm(lambda t, y, args: {"y": 1.0}, Control())
+    term = mccube.MCCTerm(ode, cde)
+    dx = term.contr(0, 1)
+    y = {"y": torch.tensor([[1.0, 2.0], [2.0, 4.0], [5.0, 6.0]])[:, None, :]}
+    vf = term.vf(0, y, None)
+    vf_prod = term.vf_prod(0, y, None, dx)
+    assert np.shape(dx[0]) == () and tuple(dx[1]["y"].shape) == (8, 2)
+    assert tuple(vf[0]["y"].shape) == (3, 2) and vf[1]["y"] == 1.0
+    assert torch.equal(vf[0]["y"], -y["y"].squeeze())
+    assert tuple(vf_prod["y"].shape) == (3, 8, 2)
+    y2 = vf_prod
+    vf2 = term.vf(0, y2, None)
+    assert tuple(vf2[0]["y"].shape) == (24, 2)
+    assert tuple(term.vf_prod(0, y2, None, dx)["y"].shape) == (24, 8, 2)
+
+
+def test_pack_unpack():
+    # /root/reference/tests/test_utils.py:6-24
+    p = torch.ones((4, 4)); w = torch.full((4, 1), 0.25)
+    exp = torch.cat([p, w], 1)
+    assert torch.equal(exp, mccube.pack_particles(p, w))
+    assert torch.equal(exp, mccube.pack_particles(p, w * 4))
+    assert mccube.pack_particles(p, None) is p
+    x = torch.cat([torch.ones((3, 4)), torch.zeros((3, 1))], 1)
+    assert mccube.unpack_particles(x, False)[1] is None
+    a, b = mccube.unpack_particles(x, True)
+    assert torch.equal(a, x[:, :-1]) and torch.equal(b, x[:, -1])
+
+
+def test_gaussian_wasserstein_metric():
+    # /root/reference/tests/test_metrics.py:8-21
+    d = 3
+    dist = mccube.gaussian_wasserstein_metric((np.ones(d), np.ones(d)), (np.eye(d), np.eye(d)))
+    assert dist == np.complex128(0.0) and dist.dtype == np.complex128
+    dist = mccube.gaussian_wasserstein_metric((np.ones(d), 2 * np.ones(d)), (np.eye(d), 2 * np.eye(d)))
+    assert abs(dist - (3 + 3 * (1 + 2 - 2 * np.sqrt(2)))) < 1e-12
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=(2, 5, 5))
+    c1, c2 = a @ a.T + np.eye(5), b @ b.T + np.eye(5)
+    m1, m2 = rng.normal(size=(2, 5))
+    assert abs(mccube.gaussian_wasserstein_metric((m1, m2), (c1, c2)) - ref.gaussian_wasserstein_metric((m1, m2), (c1, c2))) < 1e-12
+
+
+def test_prk_recombination_count():
+    mc = mccube.MonteCarloKernel(4, key=42)
+    prk = mccube.PartitioningRecombinationKernel(mccube.BoxPartitionKernel(8), mc)
+    assert prk.recombination_count == 32
+    assert mccube.BoxPartitionKernel(8).resolve_dims(64) == (0, 1, 2, 3)
+    with pytest.raises(ValueError):
+        mccube.BoxPartitionKernel(8, dims=range(8), bits=5).resolve_dims(64)

@@ -1,0 +1,356 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the oracle and the
+committed golden vectors.  Integer / index work must be BIT-EXACT; fp32 particle states are
+bit-exact too for the elementwise drifts (same op order, no FMA), and within 1e-5 relative
+(the north-star tolerance) wherever a reduction order differs; W2 within 1e-4."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mccube_b200 as mccube
+from mccube_b200 import _lib
+from mccube_b200 import diffrax_compat as dfx
+from oracle import jax_random as jr
+from oracle import mccube_ref as ref
+
+from .conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+KEY = (0, 42)
+SQRT2 = np.float32(np.sqrt(2.0))
+
+
+def u32(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+
+
+def cuda(a, dev):
+    return torch.tensor(np.ascontiguousarray(a), device=dev)
+
+
+# ------------------------------------------------------------------ A8: indices
+def test_mc_indices_golden(dev):
+    z = np.load(GOLDEN / "mc_indices.npz")
+    for name in z.files:
+        P, n, t, r, p = name.split("_")
+        P, n, t, r, p = int(P[1:]), int(n[1:]), float(t[1:]), bool(int(r[1:])), bool(int(p[1:]))
+        rng = _lib.make_rng(KEY, t, partitionable=p)
+        got = u32(_lib.mc_indices(rng, P, n, r, dev))
+        assert np.array_equal(got, z[name]), name
+
+
+@pytest.mark.parametrize("partitionable", [False, True])
+@pytest.mark.parametrize("replace", [False, True])
+def test_mc_indices_vs_oracle_ragged(dev, partitionable, replace):
+    for (P, n, t, leaf, n_leaves) in [(1, 1, 0.0, 0, 1), (2, 2, 0.3, 0, 1), (4097, 4097, -1.5, 1, 3),
+                                      ((1 << 20) + 3, 5000, 12.75, 0, 2)]:
+        key = jr.mc_step_key(jr.prng_key(42), t, leaf=leaf, n_leaves=n_leaves, partitionable=partitionable)
+        want = jr.choice_indices(key, P, n, replace, partitionable=partitionable)
+        rng = _lib.make_rng(KEY, t, leaf=leaf, n_leaves=n_leaves, partitionable=partitionable)
+        got = u32(_lib.mc_indices(rng, P, n, replace, dev))
+        assert np.array_equal(got, want), (P, n, t)
+        if not replace:
+            assert len(np.unique(got)) == n
+
+
+def test_mc_indices_config2_size_properties(dev):
+    """BASELINE config 2 (n=2^20, d=10 -> P=2^25, 3 rounds): full-size run; a permutation
+    prefix has no repeats, and the head agrees with the oracle's (slow) full shuffle."""
+    P, n = 1 << 25, 1 << 20
+    rng = _lib.make_rng(KEY, 0.05)
+    got = u32(_lib.mc_indices(rng, P, n, False, dev))
+    assert got.max() < P and len(np.unique(got)) == n
+    want = jr.choice_indices(jr.mc_step_key(jr.prng_key(42), 0.05), P, n, False)
+    assert np.array_equal(got, want)
+
+
+def test_sort_pairs_stable(dev):
+    rs = np.random.default_rng(0)
+    for n, hi, bits in [(1, 10, 32), (31, 4, 8), (4096, 1 << 32, 32), (4097, 256, 8), (100003, 1 << 12, 12),
+                        (1 << 20, 1 << 32, 32), (300000, 7, 3)]:
+        keys = rs.integers(0, hi, size=n, dtype=np.uint64).astype(np.uint32)
+        vals = rs.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+        order = np.argsort(keys, kind="stable")
+        kt, vt = cuda(keys.view(np.int32), dev), cuda(vals.view(np.int32), dev)
+        assert np.array_equal(u32(_lib.sort_pairs(kt, None, bits)), order)
+        ko, vo = _lib.sort_pairs(kt, vt, bits, want_keys=True)
+        assert np.array_equal(u32(ko), keys[order]) and np.array_equal(u32(vo), vals[order])
+
+
+# ------------------------------------------------------------------ A1-A5: expansion
+def _setup(n, d, seed=0, iso=False):
+    rs = np.random.default_rng(seed)
+    y0 = rs.normal(size=(n, d)).astype(np.float32)
+    mean = (2 * np.ones(d) if iso else rs.normal(size=d)).astype(np.float32)
+    inv_var = (np.ones(d) / 3.0 if iso else 1.0 / rs.uniform(0.5, 4.0, size=d)).astype(np.float32)
+    return y0, mean, inv_var
+
+
+@pytest.mark.parametrize("d", [1, 3, 10, 64, 130])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_expand_all_bit_exact(dev, d, kind):
+    n = 37
+    y0, mean, inv_var = _setup(n, d, seed=d)
+    t0s, t1s = np.float32(0.05), np.float32(0.1)
+    if kind == 2:
+        fn = lambda y: ref.gaussian_diag_drift(y, mean, inv_var)  # noqa: E731
+    elif kind == 1:
+        fn = lambda y: (np.sin(y) - y).astype(np.float32)  # noqa: E731
+    else:
+        fn = lambda y: np.zeros_like(y)  # noqa: E731
+    M, lam = ref.hadamard_points(d), ref.hadamard_weights(d)
+    want = ref.euler_expand(y0, fn, M, SQRT2, t0s, t1s)
+    k = M.shape[0]
+    dt = np.float32(t1s - t0s)
+    scale = np.float32(SQRT2 * np.float32(np.sqrt(dt)))
+    y0t = cuda(y0, dev)
+    if kind == 2:
+        drift = _lib.make_drift(2, mean=cuda(mean, dev), inv_var=cuda(inv_var, dev))
+    elif kind == 1:
+        drift = _lib.make_drift(1, f=cuda(fn(y0), dev))
+    else:
+        drift = _lib.make_drift(0)
+    got = _lib.expand_all(y0t, d, False, drift, dt, _lib.make_cubature(k, scale=scale)).cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # generic [k, d] point table (any cubature formula): same bits as the Hadamard closed form
+    table = (SQRT2 * ref.path_evaluate(M, t0s, t1s, np.float32)).astype(np.float32)
+    got2 = _lib.expand_all(y0t, d, False, drift, dt, _lib.make_cubature(k, points=cuda(table, dev))).cpu().numpy()
+    assert np.array_equal(got2, want)
+    # select form
+    idx = np.random.default_rng(1).integers(0, n * k, size=55)
+    got3 = _lib.expand_select(y0t, d, False, drift, dt, _lib.make_cubature(k, scale=scale),
+                              cuda(idx.astype(np.int32), dev)).cpu().numpy()
+    assert np.array_equal(got3, want[idx])
+
+
+def _terms(d, mean, inv_var, dev, fused=True):
+    if fused:
+        f = mccube.GaussianDiagDrift(mean, 1.0 / inv_var.astype(np.float64), device=dev)
+        f.inv_var = cuda(inv_var, dev)  # exact fp32 bits of the test vector
+        f.mean = cuda(mean, dev)
+    else:
+        mt, it = cuda(mean, dev), cuda(inv_var, dev)
+        f = lambda t, y, args: (mt - y) * it  # noqa: E731
+    ode = dfx.ODETerm(f)
+    cde = dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                        mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d))))
+    return mccube.MCCTerm(ode, cde)
+
+
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("partitionable", [False, True])
+@pytest.mark.parametrize("fused_drift", [True, False])
+def test_step_monte_carlo_kernel_bit_exact(dev, replace, partitionable, fused_drift):
+    n, d = 300, 10
+    y0, mean, inv_var = _setup(n, d, seed=3)
+    t0, t1 = np.float32(0.35), np.float32(0.4)
+    kern = ref.MonteCarloKernel(n, replace, key=jr.prng_key(42), partitionable=partitionable)
+    want = ref.mcc_step(y0, t0, t1, lambda y: ref.gaussian_diag_drift(y, mean, inv_var), ref.hadamard_points(d),
+                        ref.hadamard_weights(d), SQRT2, kern)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=42,
+                                                                   threefry_partitionable=partitionable))
+    y1, err, dense, state, res = solver.step(_terms(d, mean, inv_var, dev, fused_drift), t0, t1, cuda(y0, dev), None,
+                                             None, False)
+    assert solver.last_path.startswith("fused") and err is None and res == dfx.RESULTS.successful
+    assert set(dense) == {"y0", "y1"}
+    assert np.array_equal(y1.cpu().numpy(), want)
+
+
+def test_readme_example_trajectory(dev):
+    """BASELINE config 1 / README.md:60-89 in float32, through the mirrored public API."""
+    z = np.load(GOLDEN / "readme_trajectory.npz")
+    n, d = 512, 10
+    t0, dt0 = 0.0, 0.05
+    t1 = t0 + dt0 * 512
+    for replace in (False, True):
+        tag = f"r{int(replace)}"
+        terms = _terms(d, (2 * np.ones(d)).astype(np.float32), (np.ones(d) / 3.0).astype(np.float32), dev)
+        solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=42))
+        y0 = torch.ones((n, d), device=dev)
+        sol = dfx.diffeqsolve(terms, solver, t0, t1, dt0, y0, saveat=dfx.SaveAt(steps=True))
+        assert sol.ys.shape[0] == int(z[f"n_steps_{tag}"])
+        for s in (0, 1, 63, sol.ys.shape[0] - 1):
+            assert np.array_equal(sol.ys[s].cpu().numpy(), z[f"y_step{s}_{tag}"]), (tag, s)
+        mean, cov = mccube.mean_and_cov(sol.ys[-1])
+        w2 = mccube.gaussian_wasserstein_metric((2 * np.ones(d), mean), (3 * np.eye(d), cov))
+        assert abs(w2.real - float(z[f"w2_{tag}"])) < 1e-4
+
+
+def test_table_cubature_and_generic_kernel_protocol(dev):
+    """User-defined kernels go through the generic path (expansion materialised on the GPU):
+    /root/reference/tests/test_kernels.py:19-60 on a PyTree, plus a solver step."""
+
+    class PartitioningKernel(mccube.AbstractPartitioningKernel):
+        def __call__(self, t, particles, args, weighted=False):
+            from mccube_b200._tree import tree_map
+            return tree_map(lambda p, c: p.reshape(-1, c, p.shape[-1]), particles, self.partition_count)
+
+    class RecombinationKernel(mccube.AbstractRecombinationKernel):
+        def __call__(self, t, particles, args, weighted=False):
+            from mccube_b200._tree import tree_map
+            return tree_map(lambda p, c: p[:c], particles, self.recombination_count)
+
+    y0 = torch.tensor([[2.0, 4.0, 6.0, 8.0]], device=dev).T
+    y1 = torch.tensor([[1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0]], device=dev).T
+    tree = [y0, y1]
+    kernel = mccube.PartitioningRecombinationKernel(PartitioningKernel([2, 3]), RecombinationKernel([2, 3]))
+    out = kernel(0.0, tree, None)
+    assert all(torch.equal(a, b) for a, b in zip(out, tree))
+    treew = [mccube.pack_particles(x, torch.ones(x.shape[0], device=dev)) for x in tree]
+    outw = kernel(0.0, treew, None, weighted=True)
+    assert all(torch.equal(a, b) for a, b in zip(outw, treew))
+
+    n, d = 12, 3
+    yy, mean, inv_var = _setup(n, d, seed=5)
+    solver = mccube.MCCSolver(dfx.Euler(), RecombinationKernel(n))
+    got, *_ = solver.step(_terms(d, mean, inv_var, dev), np.float32(0), np.float32(0.05), cuda(yy, dev), None, None, False)
+    want = ref.expand(yy, np.float32(0), np.float32(0.05), lambda y: ref.gaussian_diag_drift(y, mean, inv_var),
+                      ref.hadamard_points(d), ref.hadamard_weights(d), SQRT2)[:n]
+    assert solver.last_path.startswith("generic") and np.array_equal(got.cpu().numpy(), want)
+
+
+def test_substeps_and_weighted_step(dev):
+    """n_substeps=2 and the weighted state layout (quirk Q3) through the generic path
+    (/root/reference/tests/test_solvers.py:93-125)."""
+    n, d = 16, 3
+    yy, mean, inv_var = _setup(n, d, seed=9)
+    drift = lambda y: ref.gaussian_diag_drift(y, mean, inv_var)  # noqa: E731
+    M, lam = ref.hadamard_points(d), ref.hadamard_weights(d)
+    t0, t1 = np.float32(0.1), np.float32(0.15)
+    want = ref.mcc_step(yy, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, key=jr.prng_key(7)), n_substeps=2)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=7), n_substeps=2)
+    got, *_ = solver.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(yy, dev), None, None, False)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+    w0 = np.random.default_rng(2).uniform(0.5, 1.5, size=n).astype(np.float32)
+    yw = ref.pack_particles(yy, w0)
+    want_w = ref.mcc_step(yw, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, key=jr.prng_key(7)), n_substeps=2,
+                          weighted=True)
+    solver_w = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=7), n_substeps=2, weighted=True)
+    got_w, *_ = solver_w.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(yw, dev), None, None, False)
+    got_w = got_w.cpu().numpy()
+    assert got_w.shape == (n, d + 1) and abs(got_w[:, -1].sum() - 1.0) < 1e-5
+    assert np.array_equal(got_w[:, :-1], want_w[:, :-1])
+    np.testing.assert_allclose(got_w[:, -1], want_w[:, -1], rtol=1e-5)
+
+
+# ------------------------------------------------------------------ A9/A10: partitioning
+def test_stratified_reference_expectations(dev):
+    # /root/reference/tests/test_kernels.py:95-133
+    y0 = torch.tensor([[-4.0, -3.0, -2.0, -1.0, 1.0, 2.0, 3.0, 4.0]], device=dev).T
+    exp = torch.tensor([[[-1.0], [1.0]], [[-2.0], [2.0]], [[-3.0], [3.0]], [[-4.0], [4.0]]], device=dev)
+    k = mccube.StratifiedPartitioningKernel(4)
+    v = k(0.0, y0, ...)
+    assert v.shape == (4, 2, 1) and torch.equal(v, exp)
+    y3 = y0.repeat(1, 3)
+    assert torch.equal(k(0.0, y3, ...), exp.repeat(1, 1, 3))
+    yw = y3.clone(); yw[:, -1] = yw[:, -1].abs()
+    ew = exp.repeat(1, 1, 3).clone(); ew[:, :, -1] = ew[:, :, -1].abs()
+    assert torch.equal(k(0.0, yw, ..., weighted=True), ew)
+    assert torch.equal(mccube.StratifiedPartitioningKernel(4, norm=None)(0.0, yw, ...), yw.reshape(4, -1, 3))
+
+
+def test_partitioners_vs_oracle(dev):
+    rs = np.random.default_rng(11)
+    p = rs.normal(size=(4096, 7)).astype(np.float32)
+    pt = cuda(p, dev)
+    # stratified
+    want_idx, _, _ = ref.stratified_indices(p, 64)
+    got_idx = u32(mccube.StratifiedPartitioningKernel(64).indices(pt, 64))
+    assert np.array_equal(got_idx, want_idx)
+    # box, bounding-box bounds and fixed bounds
+    for kw in (dict(dims=(0, 3, 6), bits=3), dict(bits=2), dict(dims=(1,), bits=8),
+               dict(dims=(0, 1), bits=4, bounds=([-2.0, -2.0], [2.0, 2.0]))):
+        want = ref.BoxPartitionKernel(64, **kw).indices(p)
+        got = u32(mccube.BoxPartitionKernel(64, **kw).indices(pt, 64))
+        assert np.array_equal(got, want), kw
+    out = mccube.BoxPartitionKernel(64, bits=2)(0.0, pt, None)
+    assert out.shape == (64, 64, 7)
+    assert np.array_equal(out.cpu().numpy(), ref.BoxPartitionKernel(64, bits=2)(0.0, p))
+    # binary tree: same sklearn host callback as the reference (tests/test_kernels.py:136-154)
+    for mode in ("KDTree", "BallTree"):
+        v = mccube.BinaryTreePartitioningKernel({"y0": 3, "y1": 4}, mode)(0.0, {"y0": pt[:6, :2].contiguous(), "y1": pt[:4, :2].contiguous()}, None)
+        assert v["y0"].shape == (3, 2, 2) and v["y1"].shape == (4, 1, 2)
+        assert np.array_equal(v["y0"].cpu().numpy(), ref.BinaryTreePartitioningKernel(3, mode)(0.0, p[:6, :2]))
+    # Monte Carlo partitioning (tests/test_kernels.py:69-81): shape + multiset preserved
+    y0 = torch.tensor([[1.0, 0.01], [2.0, 1.0], [3.0, 100.0], [4.0, 10000.0]], device=dev)
+    v = mccube.MonteCarloPartitioningKernel(4, mccube.MonteCarloKernel(None, key=42))(0.0, y0, ...)
+    assert v.shape == (4, 1, 2)
+    assert torch.equal(torch.sort(v.reshape(-1, 2), dim=0)[0], torch.sort(y0, dim=0)[0])
+    want = ref.MonteCarloPartitioningKernel(4, ref.MonteCarloKernel(None, key=jr.prng_key(42)))(0.0, y0.cpu().numpy())
+    assert np.array_equal(v.cpu().numpy(), want)
+
+
+def test_partitioned_step_golden(dev):
+    """PartitioningRecombinationKernel(Box | Stratified, MonteCarloKernel) through
+    MCCSolver.step vs the committed oracle fixture (shared local indices, quirk Q4)."""
+    z = np.load(GOLDEN / "partition_step.npz")
+    y0, mean, inv_var = z["y0"], z["mean"], z["inv_var"]
+    n, d = y0.shape
+    terms = _terms(d, mean, inv_var, dev)
+    y0t = cuda(y0, dev)
+    k = ref.hadamard_point_count(d)
+    # children and their partition indices
+    solver0 = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=42))
+    drift, cub, dt, kk, dd = solver0._describe(terms, y0t, *solver0.substep_times(z["t0"], z["t1"])[0], None)
+    children = _lib.expand_all(y0t, d, False, drift, dt, cub)
+    assert np.array_equal(children.cpu().numpy(), z["children"])
+    box = mccube.BoxPartitionKernel(32, dims=(0, 2, 5), bits=2)
+    assert np.array_equal(u32(box.indices(children, 32)), z["box_idx"])
+    assert np.array_equal(u32(mccube.StratifiedPartitioningKernel(32).indices(children, 32)), z["strat_idx"])
+    # implicit-children bounds / keys == materialised ones
+    b_rows = _lib.box_bounds(children, (0, 2, 5), 2).cpu().numpy()
+    b_child = _lib.box_child_bounds(y0t, d, drift, dt, cub, (0, 2, 5), 2).cpu().numpy()
+    assert np.array_equal(b_rows, b_child)
+    k_rows = u32(_lib.box_keys(children, (0, 2, 5), 2, cuda(b_rows, dev)))
+    k_child = u32(_lib.box_child_keys(y0t, d, drift, dt, cub, (0, 2, 5), 2, cuda(b_rows, dev)))
+    assert np.array_equal(k_rows, k_child)
+    # full steps
+    for part, name in ((box, "box_step"), (mccube.StratifiedPartitioningKernel(32), "strat_step")):
+        for use_kernel in (True, False):
+            solver = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+                part, mccube.MonteCarloKernel(n // 32, key=42)))
+            solver.use_box_prk_kernel = use_kernel
+            got, *_ = solver.step(terms, z["t0"], z["t1"], y0t, None, None, False)
+            assert np.array_equal(got.cpu().numpy(), z[name]), (name, solver.last_path)
+
+
+# ------------------------------------------------------------------ A11: metrics
+def test_moments_and_w2(dev):
+    rs = np.random.default_rng(5)
+    for n, d in [(1000, 3), (50000, 10), (20000, 64), (3000, 130)]:
+        p = (rs.normal(size=(n, d)) * rs.uniform(0.5, 2, size=d) + rs.normal(size=d) * 3).astype(np.float32)
+        w = rs.uniform(0.1, 1.0, size=n).astype(np.float32)
+        pt = cuda(p, dev)
+        mean, cov = mccube.mean_and_cov(pt)
+        p64 = p.astype(np.float64)
+        np.testing.assert_allclose(mean.cpu().numpy(), p64.mean(0), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(cov.cpu().numpy(), np.cov(p64, rowvar=False), rtol=1e-5, atol=1e-6)
+        mw, cw = mccube.mean_and_cov(pt, cuda(w, dev), ddof=0)
+        np.testing.assert_allclose(mw.cpu().numpy(), np.average(p64, axis=0, weights=w.astype(np.float64)), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(cw.cpu().numpy(), np.cov(p64, rowvar=False, ddof=0, aweights=w.astype(np.float64)),
+                                   rtol=1e-5, atol=1e-6)
+        tm, tc = np.zeros(d), np.eye(d) * 2
+        w2 = mccube.gaussian_wasserstein_metric((tm, mean), (tc, cov))
+        w2_ref = ref.gaussian_wasserstein_metric((tm, p64.mean(0)), (tc, np.cov(p64, rowvar=False)))
+        assert abs(w2 - w2_ref) < 1e-4
+    # center_of_mass (/root/reference/tests/test_metrics.py:24-34)
+    y0 = torch.tensor([[1.0, 2.0], [3.0, -4.0], [5.0, 6.0]], device=dev)
+    assert torch.allclose(mccube.center_of_mass(y0, None), torch.tensor([3.0, 4.0 / 3.0], device=dev))
+    yu, wu = mccube.unpack_particles(y0, True)
+    assert torch.allclose(mccube.center_of_mass(yu.contiguous(), wu), torch.tensor([5.0], device=dev))
+
+
+def test_full_covariance_drift(dev):
+    rs = np.random.default_rng(1)
+    n, d = 1000, 96
+    a = rs.normal(size=(d, d))
+    cov = a @ a.T / d + np.eye(d)
+    mean = rs.normal(size=d)
+    y = rs.normal(size=(n, d)).astype(np.float32)
+    f = mccube.GaussianFullDrift(mean, cov, device=dev)
+    got = f(0.0, cuda(y, dev)).cpu().numpy()
+    want = -(y.astype(np.float64) - mean) @ np.linalg.inv(cov)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
