@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of one MCCSolver step (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[2], the configuration the metric is quoted
+on: n = 2^24 particles, d = 64 (Hadamard k = 128 -> 2^31 implicit children per step),
+BoxPartitionKernel + PartitioningRecombinationKernel(MonteCarloKernel), isotropic Gaussian
+target N(2, 3 I), dt0 = 0.05, diffusion sqrt(2).  A "step" is one MCCSolver.step over all n
+particles; consecutive steps feed on each other (a real trajectory, t advances in float32).
+
+  value     whole-job particle-steps/s with the state resident in HBM (CUDA events, max over ranks)
+  e2e       same through the public API with HOST (pinned) buffers: H2D of the state, the
+            step, D2H of the result inside the timed region
+  roofline  dominant kernel (box_select_kernel): algorithmic bytes 2*n*d*4 / its measured
+            duration (events recorded by the library on the launching stream) vs the measured
+            HBM peak of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+            the NumPy oracle restatement of the reference path (oracle/mccube_ref.py; the
+            reference itself is JAX code that cannot be installed here) on the host cores,
+            on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): every rank owns an independent shard of n particles
+and partitions it device-locally (partitioned recombination shards with no
+collective) -> "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DT0 = 0.05
+TARGET_MEAN, TARGET_VAR = 2.0, 3.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-log2", type=int, default=24)
+    ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--part-size-log2", type=int, default=6, help="recombined particles per partition = 2^this")
+    ap.add_argument("--box-dims", type=int, default=4)
+    ap.add_argument("--box-bits", type=int, default=3)
+    ap.add_argument("--workload", default="box_prk", choices=["box_prk", "mc", "mc_replace"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-n-log2", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    k = 2 ** (math.ceil(math.log2(a.d)) + 1)
+    base = f"n=2^{a.n_log2} d={a.d} Hadamard(k={k}) Gaussian N(2,3I) dt0=0.05"
+    if a.workload == "box_prk":
+        return (f"BASELINE config 3: {base} BoxPartitionKernel(m=n/2^{a.part_size_log2}, dims=0..{a.box_dims - 1}, "
+                f"bits={a.box_bits}) + PartitioningRecombinationKernel(MonteCarloKernel(2^{a.part_size_log2}))")
+    return f"{base} MonteCarloKernel(n, with_replacement={a.workload == 'mc_replace'})"
+
+
+# ------------------------------------------------------------------ CPU arm (oracle)
+def run_oracle(a, n_log2, steps, warmup):
+    """Times the NumPy restatement of the reference step on the host; returns
+    (particle-steps/s, ms/step, description)."""
+    from oracle import jax_random as jr
+    from oracle import mccube_ref as ref
+
+    n, d = 1 << n_log2, a.d
+    rs = np.random.default_rng(0)
+    y = rs.standard_normal((n, d), dtype=np.float32)
+    mean = np.full(d, TARGET_MEAN, np.float32)
+    inv_var = np.full(d, 1.0 / TARGET_VAR, np.float32)
+    drift = lambda yy: ref.gaussian_diag_drift(yy, mean, inv_var)  # noqa: E731
+    M, lam, g = ref.hadamard_points(d), ref.hadamard_weights(d), np.float32(np.sqrt(2.0))
+    key = jr.prng_key(42)
+    if a.workload == "box_prk":
+        per = 1 << a.part_size_log2
+        m = max(1, n // per)
+        kern = ref.PartitioningRecombinationKernel(
+            ref.BoxPartitionKernel(m, dims=tuple(range(a.box_dims)), bits=a.box_bits),
+            ref.MonteCarloKernel(n // m, key=key))
+    else:
+        kern = ref.MonteCarloKernel(n, a.workload == "mc_replace", key=key)
+    times = ref.step_times(0.0, DT0 * (steps + warmup), DT0, np.float32)
+    for (t0, t1) in times[:warmup]:
+        y = ref.mcc_step(y, t0, t1, drift, M, lam, g, kern)
+    tic = time.perf_counter()
+    for (t0, t1) in times[warmup:warmup + steps]:
+        y = ref.mcc_step(y, t0, t1, drift, M, lam, g, kern)
+    el = time.perf_counter() - tic
+    sample = f"oracle/mccube_ref.py (NumPy restatement, not JAX) on n=2^{n_log2} of the same workload, {steps} steps"
+    return n * steps / el, 1e3 * el / steps, sample
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return 1
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, a.cpu_steps))
+    val, ms, sample = run_oracle(a, a.cpu_n_log2, steps, 1)
+    line = {
+        "impl": "reference", "metric": "particle_steps_per_sec", "value": val, "unit": "particle-steps/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "cpu_sample": sample},
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "blas_threads": host_threads()},
+        "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(a, dev):
+    import torch
+
+    import mccube_b200 as mccube
+    from mccube_b200 import diffrax_compat as dfx
+
+    n, d = 1 << a.n_log2, a.d
+    drift = mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev)
+    terms = mccube.MCCTerm(
+        dfx.ODETerm(drift),
+        dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                      mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+    if a.workload == "box_prk":
+        per = 1 << a.part_size_log2
+        m = n // per
+        kernel = mccube.PartitioningRecombinationKernel(
+            mccube.BoxPartitionKernel(m, dims=tuple(range(a.box_dims)), bits=a.box_bits),
+            mccube.MonteCarloKernel(per, key=42))
+    else:
+        kernel = mccube.MonteCarloKernel(n, a.workload == "mc_replace", key=42)
+    solver = mccube.MCCSolver(dfx.Euler(), kernel)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + int(os.environ.get("RANK", "0")))
+    y0 = torch.randn((n, d), generator=gen, device=dev, dtype=torch.float32)
+    return terms, solver, y0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    import torch
+
+    from mccube_b200 import _build, _lib
+    from mccube_b200 import diffrax_compat as dfx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.load()
+
+    n, d = 1 << a.n_log2, a.d
+    terms, solver, y = build_problem(a, dev)
+    K, W = a.steps, max(a.warmup, 3)
+    times = dfx.step_times(0.0, DT0 * (K + W + 8), DT0, np.float32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(W):
+        y, *_ = solver.step(terms, times[i][0], times[i][1], y, None, None, False)
+    path = solver.last_path
+    barrier()
+
+    # ---- timed region (device-resident state; 4 GiB per state >> 126 MB L2, no flush needed)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(W, W + K):
+        y, *_ = solver.step(terms, times[i][0], times[i][1], y, None, None, False)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * n * K / (ms_total * 1e-3)
+
+    # ---- per-phase timing of the same step (library events on the launching stream)
+    phases = {}
+    if rank == 0:
+        _lib.profile_enable(True)
+        reps = min(K, 5)
+        yy = y
+        for i in range(W + K, W + K + reps):
+            yy, *_ = solver.step(terms, times[i][0], times[i][1], yy, None, None, False)
+        for name, ms in _lib.profile_read():
+            phases.setdefault(name, []).append(ms)
+        _lib.profile_enable(False)
+        del yy
+    phase_ms = {k_: float(np.mean(v)) * (len(v) / min(K, 5)) for k_, v in phases.items()}  # ms per step
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not a.no_e2e:
+        Ke = max(1, min(a.e2e_steps, K))
+        host_in = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
+        host_out = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
+        host_in.copy_(y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(Ke):
+            yd = host_in.to(dev, non_blocking=True)                                    # H2D of the step's input
+            y1, *_ = solver.step(terms, times[W + K + i][0], times[W + K + i][1], yd, None, None, False)
+            host_out.copy_(y1, non_blocking=True)                                      # D2H of the step's result
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * n * Ke / (ms_e * 1e-3), "unit": "particle-steps/s", "steps": Ke,
+               "ms_per_step": ms_e / Ke, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4}
+        del host_in, host_out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    dom_name = {"fused:box_prk_step": "box_prk.select", "fused:mc_indices+expand_select": "expand_select",
+                "fused:box_child_keys+sort+expand_select": "sort_pairs"}.get(path, None)
+    roofline = None
+    if dom_name and dom_name in phase_ms:
+        alg_bytes = 2.0 * n * d * 4
+        dur_ms = phase_ms[dom_name]
+        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dur_ms,
+                    "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9)}
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline:
+        val, ms, sample = run_oracle(a, a.cpu_n_log2, a.cpu_steps, 1)
+        cpu_baseline = {"value": val, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                        "ms_per_step": ms, "host_cpus": os.cpu_count(), "blas_threads": host_threads()}
+
+    line = {
+        "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "path": path, "n_per_gpu": n, "d": d,
+                   "l2": "state is 4 GiB per array (>> 126 MB L2): no flush between iterations",
+                   "threefry_partitionable": False, "phase_ms_per_step": phase_ms},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,14 @@ MCCB200_API int mccb200_version(void);
 MCCB200_API const char* mccb200_last_error(void);
 /* Number of SMs of the current device (grid sizing is done inside the library). */
 MCCB200_API int mccb200_sm_count(void);
+/* Number of kernels (and device-side copies) this library has enqueued so far in this
+ * process: the evidence behind bench.py's gpu_launches. */
+MCCB200_API unsigned long long mccb200_launch_count(void);
+/* Optional phase timing for benchmarks: when enabled, every kernel group of the library
+ * records a CUDA event on the launching stream; profile_read synchronises on the last one
+ * and returns (phase name, milliseconds) pairs in launch order.  Off by default. */
+MCCB200_API void mccb200_profile_enable(int on);
+MCCB200_API int mccb200_profile_read(const char** names, float* ms, int max_entries);
 
 /* ------------------------------------------------------------------ RNG description
  * The key MonteCarloKernel uses at time t (mccube/_kernels/random.py:56-58):

@@ -50,6 +50,9 @@ _SIGNATURES = {
     "mccb200_version": (C.c_int, []),
     "mccb200_last_error": (C.c_char_p, []),
     "mccb200_sm_count": (C.c_int, []),
+    "mccb200_launch_count": (C.c_ulonglong, []),
+    "mccb200_profile_enable": (None, [C.c_int]),
+    "mccb200_profile_read": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]),
     "mccb200_mc_indices_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64, C.c_int]),
     "mccb200_mc_indices": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),
@@ -109,6 +112,22 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    return int(load().mccb200_launch_count())
+
+
+def profile_enable(on: bool):
+    load().mccb200_profile_enable(int(on))
+
+
+def profile_read(max_entries: int = 4096):
+    """[(phase, ms), ...] in launch order since the last profile_enable(True)."""
+    names = (C.c_char_p * max_entries)()
+    ms = (C.c_float * max_entries)()
+    n = load().mccb200_profile_read(names, ms, max_entries)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
 
 def exported_symbols():
@@ -315,6 +334,14 @@ def box_child_keys(y0, d, drift, dt, cub, dims, bits, bounds):
                                       float(np.float32(dt)), C.byref(cub), _dims_array(dims), len(dims), bits,
                                       bounds.data_ptr(), keys.data_ptr(), _stream()), "box_child_keys")
     return keys
+
+
+def box_prk_supported(n, d, cub, dims, bits, in_per_part) -> bool:
+    """Whether the fused counting-sort kernel covers this shape (Hadamard, n_dims*bits <= 12,
+    k <= 1024); the workspace query returns 0 otherwise."""
+    if cub.points is not None:
+        return False
+    return load().mccb200_box_prk_step_workspace_bytes(n, cub.k, len(dims), bits, in_per_part) > 0
 
 
 def box_prk_step(y0, d, drift, dt, cub, dims, bits, bounds, idx_local, in_per_part, out=None):

@@ -182,14 +182,10 @@ class MCCSolver(AbstractWrappedSolver):
         if bounds is None:
             bounds = _lib.box_child_bounds(y0c, d, drift, dt, cub, dims, part.bits)
         idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
-        if cub.points is None and len(dims) * part.bits <= 12 and getattr(self, "use_box_prk_kernel", True):
-            try:
-                out = _lib.box_prk_step(y0c, d, drift, dt, cub, dims, part.bits, bounds, idx_local, in_per_part)
-                self.last_path = "fused:box_prk_step"
-                return out
-            except _lib.MccubeB200Error as e:  # only "unsupported shape" is allowed to reroute
-                if "status -4" not in str(e):
-                    raise
+        if getattr(self, "use_box_prk_kernel", True) and _lib.box_prk_supported(n, d, cub, dims, part.bits, in_per_part):
+            out = _lib.box_prk_step(y0c, d, drift, dt, cub, dims, part.bits, bounds, idx_local, in_per_part)
+            self.last_path = "fused:box_prk_step"
+            return out
         keys = _lib.box_child_keys(y0c, d, drift, dt, cub, dims, part.bits, bounds)
         perm = _lib.sort_pairs(keys, None, len(dims) * part.bits)
         out = _lib.expand_select(y0c, d, False, drift, dt, cub, idx_local, perm=perm, out_per_part=out_per_part,

@@ -34,6 +34,23 @@ int check_launch(const char* what) {
   return MCCB200_OK;
 }
 
+// ---- optional phase timing (bench.py roofline): events recorded on the launching stream
+struct PhaseMark { const char* name; cudaEvent_t ev; };
+static bool g_prof_on = false;
+static PhaseMark g_marks[4096];
+static int g_n_marks = 0;
+
+void phase_mark(const char* name, cudaStream_t st) {
+  if (!g_prof_on || g_n_marks >= 4096) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_marks[g_n_marks++] = {name, ev};
+}
+
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static thread_local int cached_dev = -1;
   static thread_local int cached = 0;
@@ -53,3 +70,28 @@ int sm_count() {
 extern "C" int mccb200_version(void) { return MCCB200_VERSION; }
 extern "C" const char* mccb200_last_error(void) { return mccb::g_err; }
 extern "C" int mccb200_sm_count(void) { return mccb::sm_count(); }
+
+extern "C" void mccb200_profile_enable(int on) {
+  for (int i = 0; i < mccb::g_n_marks; ++i) cudaEventDestroy(mccb::g_marks[i].ev);
+  mccb::g_n_marks = 0;
+  mccb::g_prof_on = on != 0;
+}
+
+// Duration of phase i = time from its mark to the next mark ("end" marks close a call).
+// Synchronises on the last recorded event.  Returns the number of phases written.
+extern "C" int mccb200_profile_read(const char** names, float* ms, int max_entries) {
+  using namespace mccb;
+  if (g_n_marks < 2) return 0;
+  cudaEventSynchronize(g_marks[g_n_marks - 1].ev);
+  int out = 0;
+  for (int i = 0; i + 1 < g_n_marks && out < max_entries; ++i) {
+    if (strcmp(g_marks[i].name, "end") == 0) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_marks[i].ev, g_marks[i + 1].ev) != cudaSuccess) continue;
+    names[out] = g_marks[i].name;
+    ms[out] = t;
+    ++out;
+  }
+  return out;
+}
+extern "C" unsigned long long mccb200_launch_count(void) { return __atomic_load_n(&mccb::g_launches, __ATOMIC_RELAXED); }

@@ -48,4 +48,11 @@ __device__ __forceinline__ float child_value(const ExpandArgs& a, float y, float
   return __fadd_rn(y, __fadd_rn(__fmul_rn(a.dt, fv), noise));
 }
 
+// Key dimensions / resolution of BoxPartitionKernel.
+struct BoxSpec {
+  int n_dims, bits;
+  int dims[MCCB200_BOX_MAX_DIMS];
+};
+int make_box_spec(BoxSpec& s, const int32_t* dims_host, int n_dims, int bits, int d);
+
 }  // namespace mccb

@@ -228,7 +228,11 @@ int fill_expand_args(ExpandArgs& a, const float* y0, uint64_t n, int d, int weig
 
 using namespace mccb;
 
-static int run_expand(ExpandArgs& a, cudaStream_t st) {
+namespace mccb { int run_expand_select(ExpandArgs& a, cudaStream_t st); }
+
+static int run_expand(ExpandArgs& a, cudaStream_t st) { return mccb::run_expand_select(a, st); }
+
+int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
   if (a.n_out == 0) return MCCB200_OK;
   int vec = a.weighted ? 1 : pick_vec(a.d, a.ld, a.y0, a.y1);
   if (a.drift_kind == 1 && ((uintptr_t)a.f % 16 != 0)) vec = 1;
@@ -240,9 +244,12 @@ static int run_expand(ExpandArgs& a, cudaStream_t st) {
   uint64_t rows_per_cta = (uint64_t)a.rows_per_iter * EX_UNROLL;
   uint64_t want = (a.n_out + rows_per_cta - 1) / rows_per_cta;
   int grid = (int)min(want, (uint64_t)sm_count() * 8);
+  phase_mark(a.idx ? "expand_select" : "expand_all", st);
   if (vec == 4) launch_expand<4>(a, grid, st);
   else if (vec == 2) launch_expand<2>(a, grid, st);
   else launch_expand<1>(a, grid, st);
+  phase_mark("end", st);
+  count_launches(1);
   return check_launch("expand");
 }
 
@@ -289,6 +296,7 @@ extern "C" int mccb200_gather_rows(const float* in, int ld, const uint32_t* idx,
   if (vec == 4) gather_kernel<4><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
   else if (vec == 2) gather_kernel<2><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
   else gather_kernel<1><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
+  count_launches(1);
   return check_launch("gather_rows");
 }
 
@@ -301,5 +309,6 @@ extern "C" int mccb200_normalise_weights(float* y, uint64_t n, int ld, double* w
   if (grid < 1) grid = 1;
   weight_sum_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);
   weight_div_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);
+  count_launches(3);
   return check_launch("normalise_weights");
 }

@@ -184,6 +184,7 @@ extern "C" int mccb200_moments_sum(const float* p, uint64_t n, int d, int ld, co
   if (n == 0) return MCCB200_OK;
   int grid = (int)min((n + 7) / 8, (uint64_t)sm_count() * 8);
   moments_sum_kernel<<<grid, MS_THREADS, 0, (cudaStream_t)stream>>>(p, n, d, ld, w, w_stride, sum_out);
+  count_launches(1);
   return check_launch("moments_sum");
 }
 
@@ -197,6 +198,7 @@ extern "C" int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, con
   rows_per_cta = (rows_per_cta + M2_ROWS - 1) / M2_ROWS * M2_ROWS;
   dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)(tiles * tiles));
   moments_m2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, d, ld, w, w_stride, centre, rows_per_cta, m2_out);
+  count_launches(1);
   return check_launch("moments_m2");
 }
 
@@ -207,5 +209,6 @@ extern "C" int mccb200_gaussian_full_drift(const float* y, uint64_t n, int d, in
   MCCB_REQUIRE((n + GD_BM - 1) / GD_BM < 0x7FFFFFFFull, "gaussian_full_drift: n too large");
   dim3 grid((unsigned)((n + GD_BM - 1) / GD_BM), (unsigned)((d + GD_BN - 1) / GD_BN));
   gaussian_full_drift_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, n, d, ld, mean, prec, f);
+  count_launches(1);
   return check_launch("gaussian_full_drift");
 }

@@ -10,11 +10,6 @@
 
 namespace mccb {
 
-struct BoxSpec {
-  int n_dims, bits;
-  int dims[MCCB200_BOX_MAX_DIMS];
-};
-
 constexpr int BB_THREADS = 256;
 constexpr int BB_MAX_CTAS = 1024;
 
@@ -65,26 +60,35 @@ box_bounds_rows_kernel(const float* __restrict__ p, uint64_t n, int ld, BoxSpec 
 
 __global__ void __launch_bounds__(BB_THREADS)
 box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ partials) {
-  for (int q = 0; q < spec.n_dims; ++q) {
-    float lo = INFINITY, hi = -INFINITY;
-    const int c = spec.dims[q];
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
-      float y = a.y0[i * a.ld + c];
-      float fv = drift_value(a, i, c, y);
-      if (a.points) {
-        for (uint32_t j = 0; j < a.k; ++j) {
-          float v = child_value(a, y, fv, noise_value(a, j, c));
-          lo = fminf(lo, v); hi = fmaxf(hi, v);
+  // one pass: every thread keeps the running min/max of all key dims of its parents
+  float lo[MCCB200_BOX_MAX_DIMS], hi[MCCB200_BOX_MAX_DIMS];
+#pragma unroll
+  for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) {
+      if (q < spec.n_dims) {
+        const int c = spec.dims[q];
+        const float y = __ldg(a.y0 + i * a.ld + c);
+        const float fv = drift_value(a, i, c, y);
+        if (a.points) {
+          for (uint32_t j = 0; j < a.k; ++j) {
+            const float v = child_value(a, y, fv, noise_value(a, j, c));
+            lo[q] = fminf(lo[q], v); hi[q] = fmaxf(hi[q], v);
+          }
+        } else {
+          // every Hadamard column takes both signs over the k rows (rows j and j + k/2 negate)
+          const float v0 = child_value(a, y, fv, -a.scale), v1 = child_value(a, y, fv, a.scale);
+          lo[q] = fminf(lo[q], fminf(v0, v1)); hi[q] = fmaxf(hi[q], fmaxf(v0, v1));
         }
-      } else {
-        // every Hadamard column takes both signs over the k rows (rows j and j + k/2 negate)
-        float v0 = child_value(a, y, fv, -a.scale), v1 = child_value(a, y, fv, a.scale);
-        lo = fminf(lo, fminf(v0, v1)); hi = fmaxf(hi, fmaxf(v0, v1));
       }
     }
-    block_minmax(lo, hi, partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
-                 partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
   }
+#pragma unroll
+  for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q)
+    if (q < spec.n_dims)
+      block_minmax(lo[q], hi[q], partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
+                   partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
 }
 
 __global__ void box_bounds_final_kernel(const float* __restrict__ partials, int n_ctas, BoxSpec spec,
@@ -164,6 +168,7 @@ extern "C" int mccb200_stratified_keys(const float* p, uint64_t n, int d, int ld
   if (n == 0) return MCCB200_OK;
   int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
   stratified_keys_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, d, ld, com, keys);
+  count_launches(1);
   return check_launch("stratified_keys");
 }
 
@@ -179,6 +184,7 @@ extern "C" int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int3
   cudaStream_t st = (cudaStream_t)stream;
   box_bounds_rows_kernel<<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
   box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  count_launches(2);
   return check_launch("box_bounds");
 }
 
@@ -191,6 +197,7 @@ extern "C" int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32_
   if (n == 0) return MCCB200_OK;
   int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
   box_keys_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, ld, s, bounds, keys);
+  count_launches(1);
   return check_launch("box_keys");
 }
 
@@ -207,10 +214,13 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   MCCB_REQUIRE(bounds && n >= 1, "box_child_bounds: bad argument");
   if (!workspace || workspace_bytes < mccb200_box_bounds_workspace_bytes())
     return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "box_child_bounds: workspace too small");
-  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 4));
+  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 6));
   cudaStream_t st = (cudaStream_t)stream;
+  phase_mark("box_child_bounds", st);
   box_bounds_children_kernel<<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
   box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  phase_mark("end", st);
+  count_launches(2);
   return check_launch("box_child_bounds");
 }
 
@@ -227,6 +237,9 @@ extern "C" int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld
   if (n == 0) return MCCB200_OK;
   uint64_t total = n * (uint64_t)cub->k;
   int grid = (int)min((total + 255) / 256, (uint64_t)sm_count() * 16);
+  phase_mark("box_child_keys", (cudaStream_t)stream);
   box_keys_children_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, s, bounds, keys);
+  phase_mark("end", (cudaStream_t)stream);
+  count_launches(1);
   return check_launch("box_child_keys");
 }

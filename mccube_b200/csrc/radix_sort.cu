@@ -275,6 +275,7 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
   if (passes == 0) passes = 1;  // still produces a copy (all digits 0 -> identity permutation)
   const int grid = (int)min((uint64_t)p.num_tiles, (uint64_t)sm_count() * 8);
 
+  phase_mark("sort_pairs", st);
   const uint32_t* src_k = keys_in;
   const uint32_t* src_v = vals_in;
   for (int pass = 0; pass < passes; ++pass) {
@@ -299,6 +300,8 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
     src_k = dst_k;
     src_v = dst_v;
   }
+  phase_mark("end", st);
+  count_launches(5 * passes);
   return check_launch("sort_pairs");
 }
 

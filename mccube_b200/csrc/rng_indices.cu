@@ -140,15 +140,19 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   if (count == 0) return MCCB200_OK;
   char* w = (char*)workspace;
   DerivedKeys* dk = (DerivedKeys*)(w + p.off_dk);
+  phase_mark("mc_indices", st);
   derive_keys_kernel<<<1, 32, 0, st>>>(*rng, p.rounds, dk);
   const int sms = sm_count();
   if (replace) {
     int grid = (int)min((uint64_t)(count + 255) / 256, (uint64_t)sms * 8);
     randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out);
+    phase_mark("end", st);
+    count_launches(2);
     return check_launch("mc_indices(randint)");
   }
   if (p.rounds == 0) {  // n_inputs == 1: _shuffle runs zero rounds, the permutation is the identity
     iota_kernel<<<1, 256, 0, st>>>((uint32_t)count, idx_out);
+    count_launches(2);
     return check_launch("mc_indices(identity)");
   }
   uint32_t* keys = (uint32_t*)(w + p.off_keys);
@@ -170,5 +174,7 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   }
   if (cudaMemcpyAsync(idx_out, src, (size_t)count * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return fail(MCCB200_ERR_CUDA, "mc_indices: copy failed");
+  phase_mark("end", st);
+  count_launches(2 + p.rounds);
   return check_launch("mc_indices(shuffle)");
 }

@@ -354,3 +354,60 @@ def test_full_covariance_drift(dev):
     got = f(0.0, cuda(y, dev)).cpu().numpy()
     want = -(y.astype(np.float64) - mean) @ np.linalg.inv(cov)
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+# ------------------------------------------------------------------ fused Box + PRK kernel
+@pytest.mark.parametrize("n,d,dims,bits,m,replace,kind", [
+    (96, 6, (0, 2, 5), 2, 32, False, 2),
+    (1000, 10, (0, 1, 2, 3), 3, 125, False, 2),      # in_per_part = 256, k = 32
+    (1000, 10, (9,), 8, 50, True, 1),                 # duplicates in idx_local, in_per_part = 640 (not pow2)
+    (777, 3, (0, 1, 2), 4, 21, False, 0),             # k = 8 < 32 lanes, in_per_part = 296
+    (4096, 64, (0, 1, 2, 3), 3, 2048, False, 2),      # config-3 shape family: k = 128, in_per_part = 256
+    (3000, 64, (5, 40, 63), 4, 3000, True, 2),        # one output per partition, dims across lane slots
+    (2048, 100, (0, 33, 66, 99), 3, 64, False, 1),    # CPL = 4, k = 256 (8 rounds)
+    (50000, 20, (0, 1, 2, 3, 4, 5), 2, 1000, False, 2),  # 64 classes: unsupported by the fused kernel
+    (50000, 20, (0, 3, 7, 12, 19), 2, 1000, False, 2),   # 32 classes per parent
+    (5, 2, (0, 1), 1, 1, False, 2),                   # fewer parents than segments
+])
+def test_box_prk_step_matches_sort_path_and_oracle(dev, n, d, dims, bits, m, replace, kind):
+    """The fused counting-sort kernel must equal child keys -> stable sort -> expand_select
+    bit for bit, and (at sizes the oracle can materialise) the oracle's partitioned step."""
+    y0, mean, inv_var = _setup(n, d, seed=n + d)
+    y0 *= 1.7
+    k = ref.hadamard_point_count(d)
+    total = n * k
+    assert total % m == 0
+    in_per, out_per = total // m, max(1, n // m)
+    t0, t1 = np.float32(0.55), np.float32(0.6)
+    y0t = cuda(y0, dev)
+    if kind == 2:
+        fn = lambda y: ref.gaussian_diag_drift(y, mean, inv_var)  # noqa: E731
+        drift = _lib.make_drift(2, mean=cuda(mean, dev), inv_var=cuda(inv_var, dev))
+    elif kind == 1:
+        fn = lambda y: (np.cos(y) - 0.5 * y).astype(np.float32)  # noqa: E731
+        drift = _lib.make_drift(1, f=cuda(fn(y0), dev))
+    else:
+        fn = lambda y: np.zeros_like(y)  # noqa: E731
+        drift = _lib.make_drift(0)
+    (a, b), = ref.substep_times(t0, t1, 1)
+    dt = np.float32(b - a)
+    cub = _lib.make_cubature(k, scale=np.float32(SQRT2 * np.float32(np.sqrt(dt))))
+    bounds = _lib.box_child_bounds(y0t, d, drift, dt, cub, dims, bits)
+    idx_local = _lib.mc_indices(_lib.make_rng(KEY, t0), in_per, out_per, replace, dev)
+    if len(dims) > 5:   # > 32 classes per parent: the solver routes this shape to the sort path
+        assert not _lib.box_prk_supported(n, d, cub, dims, bits, in_per)
+        return
+    assert _lib.box_prk_supported(n, d, cub, dims, bits, in_per)
+    got = _lib.box_prk_step(y0t, d, drift, dt, cub, dims, bits, bounds, idx_local, in_per).cpu().numpy()
+    keys = _lib.box_child_keys(y0t, d, drift, dt, cub, dims, bits, bounds)
+    perm = _lib.sort_pairs(keys, None, len(dims) * bits)
+    want = _lib.expand_select(y0t, d, False, drift, dt, cub, idx_local, perm=perm, out_per_part=out_per,
+                              in_per_part=in_per, n_out=m * out_per).cpu().numpy()
+    assert got.shape == (m * out_per, d)
+    assert np.array_equal(got, want)
+    if total * d <= 1 << 24:
+        kern = ref.PartitioningRecombinationKernel(
+            ref.BoxPartitionKernel(m, dims=dims, bits=bits),
+            ref.MonteCarloKernel(out_per, replace, key=jr.prng_key(42)))
+        oracle = ref.mcc_step(y0, t0, t1, fn, ref.hadamard_points(d), ref.hadamard_weights(d), SQRT2, kern)
+        assert np.array_equal(got, oracle)
