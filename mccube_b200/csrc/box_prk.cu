@@ -65,6 +65,7 @@ struct BoxPrkParams {
   // selection tables
   const uint32_t* pre;         // [in_per_part + 1]  #selected entries with position < pos
   const uint2* sp;             // [out_per_part]     (position, l) sorted by position
+  uint32_t* pdesc;             // [n] per-parent K0 | D << 12 | S << 24 (written by pass A)
   uint32_t* table;             // [n_segments + 1][n_keys]
   uint32_t* idx_out;           // [n_out] selected child ids
   int warps_per_cta;
@@ -215,6 +216,7 @@ box_count_kernel(const BoxPrkParams p) {
   for (uint64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     uint32_t K0, D, S;
     describe_parent(p, i, K0, D, S);
+    p.pdesc[i] = K0 | (D << 12) | (S << 24);       // pass B re-reads 4 coalesced bytes per parent
     const uint32_t ncls = __ldg(p.cls_count + S);
     const uint32_t* fm = p.cls_fm + (size_t)S * p.max_cls;
     const uint32_t* sz = p.cls_size + (size_t)S * p.max_cls;
@@ -411,6 +413,207 @@ box_rank_sweep_kernel(const BoxPrkParams p) {
   }
 }
 
+// ------------------------------------------------------------------ pass B (hash form)
+// One warp per segment, LANES = PARENTS, counter rows in global memory like the sweep form,
+// but every phase is record-parallel (lane loops over the classes of its own parent):
+//   1. insert : every (lane, class) record inserts its key into a per-warp shared-memory hash
+//               table and ORs its lane bit into the key's mask.  A parent contributes at most
+//               one record per key, so mask == the set of parents of this batch holding that key.
+//   2. leaders: the lowest lane of each mask owns the key: start = row[key]; row[key] += total
+//               size of the mask (one L2 read-modify-write per DISTINCT key); start -> table.
+//   3. ranks  : rank0 = start + sum of the class sizes of the lower lanes in the mask (popcounts:
+//               the class size is a per-lane power of two), then the selection test and hits.
+// Result is independent of hash placement.  The table has HT_SLOTS slots; a batch whose records
+// do not fit is re-run as sub-batches of fewer parents (earlier parents first).
+constexpr int HT_SLOTS = 128;
+
+constexpr int HQ_CAP = 64;   // deferred-hit queue entries per warp
+
+template <bool PRE_SMEM, bool MEM_SMEM>
+__global__ void __launch_bounds__(256, 4)
+box_rank_hash_kernel(const BoxPrkParams p) {
+  extern __shared__ uint32_t smem[];
+  const ExpandArgs& a = p.a;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* cursor = smem;
+  uint32_t* tkey = cursor + (size_t)warp * 3 * HT_SLOTS;
+  uint32_t* tmask = tkey + HT_SLOTS;
+  uint32_t* tstart = tmask + HT_SLOTS;
+  cursor += (size_t)p.warps_per_cta * 3 * HT_SLOTS;
+  uint4* hq = reinterpret_cast<uint4*>(cursor) + (size_t)warp * HQ_CAP;   // (rank0, owner|c<<5, first, n_hit)
+  cursor += (size_t)p.warps_per_cta * HQ_CAP * 4;
+  const uint32_t cls_pad = 1u << p.cls_pad_log2;
+  uint32_t* s_tab = cursor; cursor += p.n_sets * cls_pad;
+  uint32_t* s_cnt = cursor; cursor += p.n_sets;
+  for (uint32_t i = threadIdx.x; i < p.n_sets * cls_pad; i += blockDim.x) s_tab[i] = p.cls_packed[i];
+  for (uint32_t i = threadIdx.x; i < p.n_sets; i += blockDim.x) s_cnt[i] = p.cls_count[i];
+  // shared copy of the selection prefix as uint16 (out_per_part < 65536 when PRE_SMEM)
+  const uint2* sp = p.sp;
+  uint16_t* s_pre16 = nullptr;
+  if (PRE_SMEM) {
+    uint2* s_sp = reinterpret_cast<uint2*>(cursor);
+    cursor += 2u * p.out_per_part;
+    s_pre16 = reinterpret_cast<uint16_t*>(cursor);
+    cursor += ((p.in_per_part + 4u) & ~3u) / 2u;
+    for (uint32_t i = threadIdx.x; i <= p.in_per_part; i += blockDim.x) s_pre16[i] = (uint16_t)p.pre[i];
+    for (uint32_t i = threadIdx.x; i < p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
+    sp = s_sp;
+  }
+  auto PRE = [&](uint32_t i) -> uint32_t { return PRE_SMEM ? (uint32_t)s_pre16[i] : __ldg(p.pre + i); };
+  const uint16_t* members = p.members;
+  if (MEM_SMEM) {
+    uint16_t* s_mem = reinterpret_cast<uint16_t*>(cursor);
+    for (uint32_t i = threadIdx.x; i < p.n_sets * a.k; i += blockDim.x) s_mem[i] = p.members[i];
+    members = s_mem;
+  }
+  __syncthreads();
+  const uint32_t seg = blockIdx.x * p.warps_per_cta + warp;
+  if (seg >= p.n_segments) return;
+  uint32_t* row = p.table + (uint64_t)seg * p.n_keys;   // absolute start ranks of this segment
+
+  const uint64_t i0 = (uint64_t)seg * p.parents_per_seg;
+  const uint64_t i1 = min(a.n, i0 + p.parents_per_seg);
+  const uint32_t Pm = p.in_per_part, nm = p.out_per_part;
+  const int logk = __ffs(a.k) - 1;
+  // sub-batch count that always fits: (32 / n) parents * max_cls records <= HT_SLOTS
+  int nsub_safe = 1;
+  while ((32 / nsub_safe) * (int)p.max_cls > HT_SLOTS) nsub_safe <<= 1;
+
+  // resolve one deferred hit record (any lane may process any parent's record)
+  auto emit_hits = [&](uint32_t rank0, uint32_t S_o, uint32_t ent, uint32_t first, uint32_t n_hit, uint64_t child0) {
+    uint32_t part0, pos0;
+    if (p.in_shift != 0xFFFFFFFFu) { part0 = rank0 >> p.in_shift; pos0 = rank0 & (Pm - 1u); }
+    else { part0 = rank0 / Pm; pos0 = rank0 - part0 * Pm; }
+    const uint16_t* mem = members + (size_t)S_o * a.k + (ent >> 22);
+    for (uint32_t hh = 0; hh < n_hit; ++hh) {
+      uint32_t e = first + hh;
+      const bool wrap = e >= nm;
+      if (wrap) e -= nm;
+      const uint2 pl = sp[e];                      // (position, output slot l)
+      const uint32_t tt = wrap ? pl.x + Pm - pos0 : pl.x - pos0;
+      p.idx_out[(uint64_t)(part0 + (wrap ? 1u : 0u)) * nm + pl.y] = (uint32_t)(child0 + mem[tt]);
+    }
+  };
+
+  uint32_t ndesc = i0 + lane < i1 ? __ldcs(p.pdesc + i0 + lane) : 0u;
+  for (uint64_t base = i0; base < i1; base += 32) {
+    const uint32_t desc = ndesc;
+    const bool have = base + lane < i1;
+    if (base + 32 + lane < i1) ndesc = __ldcs(p.pdesc + base + 32 + lane);   // next batch (coalesced)
+    const uint32_t K0 = desc & 0xFFFu, D = (desc >> 12) & 0xFFFu, S = desc >> 24;
+    const uint32_t* trow = s_tab + (S << p.cls_pad_log2);
+    const uint32_t ncls = have ? s_cnt[S] : 0u;
+    // class size is the same for every class of one parent: k >> lsz, lsz = log2(ncls)
+    const uint32_t lsz = ncls ? (uint32_t)(__ffs(ncls) - 1) : 31u;
+    const uint32_t size = ncls ? (a.k >> lsz) : 0u;
+    uint32_t szmask[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) szmask[b] = __ballot_sync(0xffffffffu, lsz == (uint32_t)b);
+
+    int nsub = 1;
+    bool done = false;
+    while (!done) {
+      done = true;
+      const int per = 32 / nsub;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const bool mine = have && lane >= sub * per && lane < (sub + 1) * per;
+        const uint32_t my_ncls = mine ? ncls : 0u;
+        const uint32_t maxcls = __reduce_max_sync(0xffffffffu, my_ncls);
+        if (maxcls == 0u) continue;
+        // ---- clear
+#pragma unroll
+        for (int i = 0; i < HT_SLOTS / 32; ++i) { tkey[lane + 32 * i] = 0xFFFFFFFFu; tmask[lane + 32 * i] = 0u; }
+        __syncwarp();
+        // ---- 1. insert: key -> slot, OR the lane bit into the key's mask
+        bool overflow = false;
+        for (uint32_t c = 0; c < maxcls; ++c) {
+          if (c < my_ncls) {
+            const uint32_t key = K0 + (D & (trow[c] & 0xFFFu));
+            uint32_t h = (key * 0x9E3779B1u) >> 25;
+            int probes = 0;
+            while (true) {
+              const uint32_t old = atomicCAS(&tkey[h], 0xFFFFFFFFu, key);
+              if (old == 0xFFFFFFFFu || old == key) break;
+              h = (h + 1u) & (HT_SLOTS - 1u);
+              if (++probes >= HT_SLOTS) { overflow = true; break; }
+            }
+            if (!overflow) atomicOr(&tmask[h], 1u << lane);
+          }
+        }
+        if (__any_sync(0xffffffffu, overflow)) {   // nothing outside the table was touched yet
+          nsub = nsub_safe > nsub ? nsub_safe : nsub * 2;   // nsub_safe always fits
+          done = false;
+          break;
+        }
+        __syncwarp();
+        // ---- 2. leaders, slot-parallel: one L2 read-modify-write per distinct key, all in flight
+        {
+          uint32_t keyv[HT_SLOTS / 32], startv[HT_SLOTS / 32], totv[HT_SLOTS / 32];
+#pragma unroll
+          for (int i = 0; i < HT_SLOTS / 32; ++i) {
+            keyv[i] = tkey[lane + 32 * i];
+            const uint32_t m = tmask[lane + 32 * i];
+            uint32_t total = 0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+              if (szmask[b]) total += (uint32_t)__popc(m & szmask[b]) << (logk - b);   // warp-uniform skip
+            totv[i] = total;
+            startv[i] = keyv[i] != 0xFFFFFFFFu ? __ldcg(row + keyv[i]) : 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < HT_SLOTS / 32; ++i) {
+            if (keyv[i] != 0xFFFFFFFFu) {
+              __stcg(row + keyv[i], startv[i] + totv[i]);
+              tstart[lane + 32 * i] = startv[i];
+            }
+          }
+        }
+        __syncwarp();
+        // ---- 3. ranks + selection test; hits are queued and resolved with full lanes
+        uint32_t qn = 0;                            // warp-uniform queue length
+        for (uint32_t c = 0; c < maxcls; ++c) {
+          uint32_t n_hit = 0, rank0 = 0, first = 0;
+          if (c < my_ncls) {
+            const uint32_t key = K0 + (D & (trow[c] & 0xFFFu));
+            uint32_t h = (key * 0x9E3779B1u) >> 25;
+            while (tkey[h] != key) h = (h + 1u) & (HT_SLOTS - 1u);
+            const uint32_t m = tmask[h] & lt_mask;
+            uint32_t excl = 0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+              if (szmask[b]) excl += (uint32_t)__popc(m & szmask[b]) << (logk - b);      // warp-uniform skip
+            rank0 = tstart[h] + excl;
+            const uint32_t pos0 = p.in_shift != 0xFFFFFFFFu ? (rank0 & (Pm - 1u)) : (rank0 % Pm);
+            const uint32_t end = pos0 + size;      // size <= k <= Pm: wraps at most once
+            first = PRE(pos0);
+            n_hit = end <= Pm ? PRE(end) - first : (nm - first) + PRE(end - Pm);
+          }
+          const uint32_t hm = __ballot_sync(0xffffffffu, n_hit != 0u);
+          if (hm) {
+            const uint32_t at = qn + (uint32_t)__popc(hm & lt_mask);
+            if (n_hit) {
+              if (at < (uint32_t)HQ_CAP) hq[at] = make_uint4(rank0, (uint32_t)lane | (c << 5), first, n_hit);
+              else emit_hits(rank0, S, trow[c], first, n_hit, (base + lane) * (uint64_t)a.k);   // queue full
+            }
+            qn = min(qn + (uint32_t)__popc(hm), (uint32_t)HQ_CAP);
+          }
+        }
+        __syncwarp();
+        for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+          const bool on = q0 + lane < qn;
+          const uint4 e = on ? hq[q0 + lane] : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t owner = e.y & 31u, cc = e.y >> 5;
+          const uint32_t S_o = __shfl_sync(0xffffffffu, S, owner);
+          if (on) emit_hits(e.x, S_o, s_tab[(S_o << p.cls_pad_log2) + cc], e.z, e.w, (base + owner) * (uint64_t)a.k);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pass B (class-lane form)
 // smem layout: [warps][n_keys] counters | packed class table | pre[in_per_part+1] + sp (if PRE_SMEM)
 //              | members (if MEM_SMEM)
@@ -540,14 +743,15 @@ struct PrkPlan {
   int warps_per_cta, grid_b, pre_in_smem, mem_in_smem, mode;
   uint64_t parents_per_seg;
   size_t smem_b;
-  size_t off_table, off_pre, off_fill, off_sp, off_cnt, off_fm, off_size, off_off, off_packed, off_members, off_cid, off_idx, total;
+  size_t off_pdesc, off_table, off_pre, off_fill, off_sp, off_cnt, off_fm, off_size, off_off, off_packed, off_members, off_cid, off_idx, total;
 };
 
-// rank_mode 2 (default): sweep kernel, counter rows in global memory, 32 warps per SM.
+// rank_mode 3 (default): hash kernel, record-parallel, counter rows in global memory.
+// rank_mode 2: sweep kernel, counter rows in global memory, 32 warps per SM.
 // rank_mode 1: class-lane kernel, counter rows in shared memory (fewer warps).
 static int rank_mode() {
   const char* m = getenv("MCCB200_RANK_MODE");
-  return m ? atoi(m) : 2;
+  return m ? atoi(m) : 3;
 }
 
 static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
@@ -573,12 +777,15 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   pl.pre_in_smem = pre_bytes <= 72 * 1024 ? 1 : 0;
   pl.mem_in_smem = mem_bytes <= 16 * 1024 ? 1 : 0;
   pl.mode = rank_mode();
-  if (pl.mode == 2) pl.pre_in_smem = pre_bytes <= 40 * 1024 ? 1 : 0;   // 4 CTAs per SM share 227 KB
-  const size_t shared_part = tab_bytes + (pl.pre_in_smem ? pre_bytes : 0) + (pl.mem_in_smem ? mem_bytes : 0);
+  if (pl.mode == 2) pl.pre_in_smem = pre_bytes <= 36 * 1024 ? 1 : 0;   // 4 CTAs per SM share 227 KB
+  size_t pre_bytes3 = ((size_t)((in_per_part + 4) & ~3ull)) * 2 + (size_t)out_per_part_max * 8;
+  if (pl.mode == 3) pl.pre_in_smem = (pre_bytes3 <= 24 * 1024 && out_per_part_max < 65536) ? 1 : 0;
+  size_t shared_part = tab_bytes + (pl.pre_in_smem ? (pl.mode == 3 ? pre_bytes3 : pre_bytes) : 0) + (pl.mem_in_smem ? mem_bytes : 0);
+  if (pl.mode == 3) shared_part += (size_t)8 * 3 * HT_SLOTS * 4 + (size_t)8 * HQ_CAP * 16 + (size_t)pl.n_sets * 4;
   int w;
   uint64_t segs;
   const int sms = sm_count();
-  if (pl.mode == 2) {
+  if (pl.mode >= 2) {
     w = 8;
     segs = (uint64_t)sms * 32;
   } else {
@@ -592,10 +799,11 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   pl.parents_per_seg = (n + segs - 1) / segs;
   pl.n_segments = (uint32_t)((n + pl.parents_per_seg - 1) / pl.parents_per_seg);
   pl.grid_b = (int)((pl.n_segments + w - 1) / w);
-  pl.smem_b = (pl.mode == 2 ? 0 : (size_t)w * row) + shared_part;
+  pl.smem_b = (pl.mode >= 2 ? 0 : (size_t)w * row) + shared_part;
   const uint64_t n_out_max = total_children / in_per_part * out_per_part_max;
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t o = cur; cur += align_up(bytes, 256); return o; };
+  pl.off_pdesc = take((size_t)n * 4);
   pl.off_table = take(((size_t)pl.n_segments + 1) * row);
   pl.off_pre = take(((size_t)in_per_part + 2) * 4);
   pl.off_fill = take(((size_t)in_per_part + 2) * 4);
@@ -652,6 +860,7 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
 
   char* w = (char*)workspace;
   uint32_t* table = (uint32_t*)(w + pl.off_table);
+  p.pdesc = (uint32_t*)(w + pl.off_pdesc);
   uint32_t* pre = (uint32_t*)(w + pl.off_pre);
   uint32_t* fill = (uint32_t*)(w + pl.off_fill);
   uint2* sp = (uint2*)(w + pl.off_sp);
@@ -704,7 +913,17 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
     cudaFuncSetAttribute(box_rank_sweep_kernel<PS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
     box_rank_sweep_kernel<PS, MS><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
   } while (0)
-  if (pl.mode == 2) {
+#define MCCB_HASH(PS, MS)                                                                                          \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(box_rank_hash_kernel<PS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
+    box_rank_hash_kernel<PS, MS><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
+  } while (0)
+  if (pl.mode == 3) {
+    if (pl.pre_in_smem && pl.mem_in_smem) MCCB_HASH(true, true);
+    else if (pl.pre_in_smem) MCCB_HASH(true, false);
+    else if (pl.mem_in_smem) MCCB_HASH(false, true);
+    else MCCB_HASH(false, false);
+  } else if (pl.mode == 2) {
     if (pl.pre_in_smem && pl.mem_in_smem) MCCB_SWEEP(true, true);
     else if (pl.pre_in_smem) MCCB_SWEEP(true, false);
     else if (pl.mem_in_smem) MCCB_SWEEP(false, true);
@@ -717,6 +936,7 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
   }
 #undef MCCB_RANK
 #undef MCCB_SWEEP
+#undef MCCB_HASH
 
   // gather: the HBM-bound fused expand+select materialises the selected children
   ExpandArgs g = p.a;
