@@ -322,17 +322,30 @@ def main():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    dom_name = {"fused:box_prk_step": "box_prk.select", "fused:mc_indices+expand_select": "expand_select",
-                "fused:box_child_keys+sort+expand_select": "sort_pairs"}.get(path, None)
+    # algorithmic bytes per launch of every timed kernel group ("Kernels and rooflines")
+    nd = a.box_dims
+    alg = {
+        "expand_select": 2.0 * n * d * 4,              # read n selected parent rows + write n rows
+        "box_prk.rank": n * (4 + 4.0),                 # packed parent descriptor in, selected child id out
+        "box_prk.count": n * (nd * 4 + 4.0),           # key dims in, packed descriptor out
+        "box_child_bounds": n * nd * 4.0,              # key dims in
+    }
+    kernels = {k_: {"ms": v, "algorithmic_gbs": (alg[k_] / (v * 1e-3) / 1e9) if k_ in alg and v > 0 else None}
+               for k_, v in phase_ms.items()}
     roofline = None
-    if dom_name and dom_name in phase_ms:
-        alg_bytes = 2.0 * n * d * 4
-        dur_ms = phase_ms[dom_name]
-        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+    timed = {k_: v for k_, v in phase_ms.items() if k_ in alg}
+    if timed:
+        dom_name = max(timed, key=timed.get)
+        dur_ms = timed[dom_name]
+        achieved = alg[dom_name] / (dur_ms * 1e-3) / 1e9
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic_r1.json"   # dram__bytes_read+write per launch from `ncu --set full`
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get(dom_name)
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dur_ms,
-                    "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9)}
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg[dom_name], "kernel_ms": dur_ms,
+                    "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9), "all_kernels": kernels}
 
     cpu_baseline = None
     if not a.no_cpu_baseline:

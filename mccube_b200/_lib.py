@@ -200,8 +200,9 @@ _ws_cache: dict = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
-    key = (torch.device(device).index or 0)
+    """Grow-only scratch buffer per (device, stream): the C ABI never allocates, and two
+    streams must never share scratch."""
+    key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         _ws_cache[key] = buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

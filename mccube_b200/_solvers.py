@@ -43,6 +43,16 @@ from .diffrax_compat import (
 )
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index or 0
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class MCCSolver(AbstractWrappedSolver):
     """`MCCSolver(solver, recombination_kernel, n_substeps=1, weighted=False)`
     (_solvers.py:87-90).  `time_dtype` is the dtype diffrax carries `t` in (float32 unless
@@ -178,10 +188,18 @@ class MCCSolver(AbstractWrappedSolver):
         in_per_part = total // m
         out_per_part = mc.recombination_count
         dims = part.resolve_dims(d)
+        # the shared local index vector depends only on (key, t0): draw it on a side stream while the
+        # bounds / counting passes run
+        main = torch.cuda.current_stream()
+        side = _side_stream(y0c.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
         bounds = part.fixed_bounds(dims, y0c.device)
         if bounds is None:
             bounds = _lib.box_child_bounds(y0c, d, drift, dt, cub, dims, part.bits)
-        idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
+        main.wait_stream(side)
+        idx_local.record_stream(main)
         if getattr(self, "use_box_prk_kernel", True) and _lib.box_prk_supported(n, d, cub, dims, part.bits, in_per_part):
             out = _lib.box_prk_step(y0c, d, drift, dt, cub, dims, part.bits, bounds, idx_local, in_per_part)
             self.last_path = "fused:box_prk_step"

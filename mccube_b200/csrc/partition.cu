@@ -91,18 +91,25 @@ box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ parti
                    partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
 }
 
+// one warp per key dim: lanes stride over the CTA partials, shuffle-reduce
 __global__ void box_bounds_final_kernel(const float* __restrict__ partials, int n_ctas, BoxSpec spec,
                                         float* __restrict__ bounds) {
-  const int q = threadIdx.x;
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (q >= spec.n_dims) return;
   float lo = INFINITY, hi = -INFINITY;
-  for (int b = 0; b < n_ctas; ++b) {
+  for (int b = lane; b < n_ctas; b += 32) {
     lo = fminf(lo, partials[((size_t)b * spec.n_dims + q) * 2]);
     hi = fmaxf(hi, partials[((size_t)b * spec.n_dims + q) * 2 + 1]);
   }
-  float rng = __fsub_rn(hi, lo);
-  bounds[q] = lo;
-  bounds[spec.n_dims + q] = rng > 0.0f ? __fdiv_rn((float)(1 << spec.bits), rng) : 0.0f;
+  for (int o = 16; o; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) {
+    float rng = __fsub_rn(hi, lo);
+    bounds[q] = lo;
+    bounds[spec.n_dims + q] = rng > 0.0f ? __fdiv_rn((float)(1 << spec.bits), rng) : 0.0f;
+  }
 }
 
 __device__ __forceinline__ uint32_t box_cell(float x, float lo, float inv_h, int bits) {
@@ -183,7 +190,7 @@ extern "C" int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int3
   int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 4));
   cudaStream_t st = (cudaStream_t)stream;
   box_bounds_rows_kernel<<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
-  box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);
   count_launches(2);
   return check_launch("box_bounds");
 }
@@ -218,7 +225,7 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   cudaStream_t st = (cudaStream_t)stream;
   phase_mark("box_child_bounds", st);
   box_bounds_children_kernel<<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
-  box_bounds_final_kernel<<<1, 32, 0, st>>>((const float*)workspace, grid, s, bounds);
+  box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);
   phase_mark("end", st);
   count_launches(2);
   return check_launch("box_child_bounds");

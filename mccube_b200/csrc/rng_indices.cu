@@ -88,6 +88,59 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t count, uint32_t* __r
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = i;
 }
 
+// _shuffle for small inputs in ONE launch: a single CTA derives the keys, then per round draws
+// the 32-bit sort keys and sorts (key << 32 | position) with a shared-memory bitonic network --
+// positions are unique, so the unstable network reproduces the stable sort_key_val exactly.
+constexpr int SMALL_SHUFFLE_MAX = 8192;
+
+__global__ void __launch_bounds__(1024)
+small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t npad, uint32_t count, uint32_t* __restrict__ out) {
+  extern __shared__ unsigned long long s_comp[];        // [npad]
+  uint32_t* xa = reinterpret_cast<uint32_t*>(s_comp + npad);   // [npad]
+  uint32_t* xb = xa + npad;                                      // [npad]
+  __shared__ u32x2 s_sub[MAX_ROUNDS];
+  const bool part = rng.partitionable != 0;
+  if (threadIdx.x == 0) {
+    u32x2 key = {rng.key[0], rng.key[1]};
+    if (rng.key_dev) key = {rng.key_dev[0], rng.key_dev[1]};
+    if (rng.fold_time) {
+      float t = rng.t_dev ? *rng.t_dev : rng.t;
+      key = fold_in_key(key, __float_as_uint(t));
+      key = split_key(key, rng.n_leaves, rng.leaf, part);
+    }
+    for (int r = 0; r < rounds; ++r) {
+      u32x2 nk = split_key(key, 2, 0, part);
+      s_sub[r] = split_key(key, 2, 1, part);
+      key = nk;
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) xa[i] = i;
+  __syncthreads();
+  for (int r = 0; r < rounds; ++r) {
+    const u32x2 sub = s_sub[r];
+    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
+      s_comp[i] = i < n ? (((unsigned long long)random_bits32_at(sub, i, n, part) << 32) | i) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+          const uint32_t ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = s_comp[i], b = s_comp[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { s_comp[i] = b; s_comp[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) xb[q] = xa[(uint32_t)s_comp[q]];
+    __syncthreads();
+    uint32_t* t = xa; xa = xb; xb = t;
+  }
+  for (uint32_t q = threadIdx.x; q < count; q += blockDim.x) out[q] = xa[q];
+}
+
 static int shuffle_rounds(uint64_t size) {
   if (size < 1) size = 1;
   return (int)ceil(3.0 * log((double)size) / log(4294967295.0));
@@ -138,6 +191,21 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   if (workspace_bytes < p.total || workspace == nullptr)
     return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_indices: workspace %zu < %zu", workspace_bytes, p.total);
   if (count == 0) return MCCB200_OK;
+  if (!replace && p.rounds > 0 && n_inputs <= (uint64_t)SMALL_SHUFFLE_MAX) {
+    uint32_t npad = 2;
+    while (npad < n_inputs) npad <<= 1;
+    const size_t smem = (size_t)npad * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(small_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SHUFFLE_MAX * 16);
+      attr_set = true;
+    }
+    phase_mark("mc_indices", st);
+    small_shuffle_kernel<<<1, 1024, smem, st>>>(*rng, p.rounds, (uint32_t)n_inputs, npad, (uint32_t)count, idx_out);
+    phase_mark("end", st);
+    count_launches(1);
+    return check_launch("mc_indices(small shuffle)");
+  }
   char* w = (char*)workspace;
   DerivedKeys* dk = (DerivedKeys*)(w + p.off_dk);
   phase_mark("mc_indices", st);
