@@ -373,6 +373,19 @@ def column_means(p, d, weights=None):
     return sums[:d] / sums[d], sums[d]
 
 
+def second_moment(p, d, centre, weights=None):
+    """sum_r w_r (p_r - centre)(p_r - centre)^T as float64 [d, d] (accumulated on the GPU)."""
+    lib = load()
+    _require_cuda(p, weights, centre)
+    _f32c(p)
+    n, ld = p.shape
+    w_stride = 1 if weights is None else weights.stride(0)
+    m2 = torch.zeros((d, d), dtype=torch.float64, device=p.device)
+    _check(lib.mccb200_moments_m2(p.data_ptr(), n, d, ld, _ptr(weights), w_stride, centre.data_ptr(), m2.data_ptr(),
+                                  _stream()), "moments_m2")
+    return m2
+
+
 def moments(p, d, weights=None):
     """(sum[d], weight_total, m2[d, d]) in float64 about the weighted mean."""
     lib = load()
