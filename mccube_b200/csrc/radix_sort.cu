@@ -34,10 +34,16 @@ rs_histogram(const uint32_t* __restrict__ keys, uint64_t count, int shift, uint3
     hist[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)tile * RS_TILE;
+    uint32_t kv[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {   // all loads in flight before the first atomic
+      uint64_t g = base + (uint64_t)it * RS_THREADS + threadIdx.x;
+      kv[it] = g < count ? __ldcs(keys + g) : 0u;
+    }
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; ++it) {
       uint64_t g = base + (uint64_t)it * RS_THREADS + threadIdx.x;
-      if (g < count) atomicAdd(&hist[(keys[g] >> shift) & 0xFF], 1u);
+      if (g < count) atomicAdd(&hist[(kv[it] >> shift) & 0xFF], 1u);
     }
     __syncthreads();
     table[(uint64_t)threadIdx.x * num_tiles + tile] = hist[threadIdx.x];
@@ -133,7 +139,7 @@ rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __rest
 }
 
 template <bool IOTA_VALUES, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t count, int shift,
            uint32_t num_tiles, const uint32_t* __restrict__ table, uint32_t* __restrict__ keys_out,
            uint32_t* __restrict__ vals_out) {
@@ -153,28 +159,43 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
-    uint32_t key[RS_ITEMS], val[RS_ITEMS];
-    uint16_t rank[RS_ITEMS];
+    // Ranking without a serial read-modify-write chain: per item one MATCH.ANY, then the group
+    // leader issues a shared-memory atomicAdd that returns the running count of its digit in this
+    // warp.  Atomics of one warp execute in issue order, so the 16 of them pipeline; the returned
+    // values are only collected in the second loop.
+    uint32_t key[RS_ITEMS], old[RS_ITEMS];
+    uint32_t pl[RS_ITEMS / 2];   // (prefix within group | leader lane << 8), two per word
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; ++it) {
       uint64_t g = base + tile_elem(warp, it, lane);
-      bool ok = g < count;
-      key[it] = ok ? keys_in[g] : 0xFFFFFFFFu;
-      if (IOTA_VALUES) val[it] = (uint32_t)g;
-      else val[it] = ok ? vals_in[g] : 0u;
+      key[it] = g < count ? __ldcs(keys_in + g) : 0xFFFFFFFFu;
     }
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; ++it) {
       uint64_t g = base + tile_elem(warp, it, lane);
-      bool ok = g < count;
-      uint32_t dg = (key[it] >> shift) & 0xFF;
-      uint32_t mkey = ok ? dg : (256u + lane);  // invalid lanes form singleton groups
-      uint32_t m = __match_any_sync(0xffffffffu, mkey);
-      uint32_t c = ok ? warp_cnt[warp][dg] : 0u;
-      __syncwarp();
-      rank[it] = (uint16_t)(c + __popc(m & lt_mask));
-      if (ok && (m & lt_mask) == 0) warp_cnt[warp][dg] = c + __popc(m);
-      __syncwarp();
+      const bool ok = g < count;
+      const uint32_t dg = (key[it] >> shift) & 0xFF;
+      // peer mask of equal digits from 8 ballots (fixed cost; MATCH.ANY serialises over the ~30
+      // distinct digit values a warp of random keys holds)
+      uint32_t m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const uint32_t vote = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
+        m &= ((dg >> b) & 1u) ? vote : ~vote;
+      }
+      if (!ok) m = 1u << lane;
+      const uint32_t leader = __ffs(m) - 1;
+      old[it] = 0u;
+      if (ok && leader == (uint32_t)lane) old[it] = atomicAdd(&warp_cnt[warp][dg], (uint32_t)__popc(m));
+      const uint32_t v = (uint32_t)__popc(m & lt_mask) | (leader << 8);
+      if (it & 1) pl[it >> 1] |= v << 16; else pl[it >> 1] = v;
+    }
+    uint32_t rank2[RS_ITEMS / 2];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; ++it) {
+      const uint32_t v = (it & 1) ? (pl[it >> 1] >> 16) : (pl[it >> 1] & 0xFFFFu);
+      const uint32_t rk = __shfl_sync(0xffffffffu, old[it], v >> 8) + (v & 0xFFu);
+      if (it & 1) rank2[it >> 1] |= rk << 16; else rank2[it >> 1] = rk;
     }
     __syncthreads();
 
@@ -208,9 +229,10 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
       uint64_t g = base + tile_elem(warp, it, lane);
       if (g < count) {
         uint32_t dg = (key[it] >> shift) & 0xFF;
-        uint32_t pos = lstart[dg] + warp_cnt[warp][dg] + rank[it];
+        uint32_t rk = (it & 1) ? (rank2[it >> 1] >> 16) : (rank2[it >> 1] & 0xFFFFu);
+        uint32_t pos = lstart[dg] + warp_cnt[warp][dg] + rk;
         s_keys[pos] = key[it];
-        s_vals[pos] = val[it];
+        s_vals[pos] = IOTA_VALUES ? (uint32_t)g : __ldcs(vals_in + g);
       }
     }
     __syncthreads();

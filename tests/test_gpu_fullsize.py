@@ -1,0 +1,106 @@
+"""Parity evidence at BASELINE.json's FULL sizes, where the oracle cannot materialise the
+expansion (n*k*d = 512 GiB): size-independent properties plus bit-exact agreement between the
+two independent CUDA formulations (fused counting-sort vs child keys -> stable radix sort)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mccube_b200 as mccube
+from mccube_b200 import _lib
+from mccube_b200 import diffrax_compat as dfx
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n, d, dev, seed=0):
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    y0 = torch.randn((n, d), generator=gen, device=dev) * 1.5 + 1.0
+    drift = mccube.GaussianDiagDrift(np.full(d, 2.0), 3.0, device=dev)
+    terms = mccube.MCCTerm(
+        dfx.ODETerm(drift),
+        dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                      mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+    return y0, terms
+
+
+def test_config3_fused_step_full_size(dev):
+    """BASELINE config 3: n=2^24, d=64 (2^31 implicit children), Box + PRK + MonteCarloKernel."""
+    n, d, per = 1 << 24, 64, 64
+    dims, bits = (0, 1, 2, 3), 3
+    y0, terms = _problem(n, d, dev)
+    m = n // per
+    kernel = mccube.PartitioningRecombinationKernel(mccube.BoxPartitionKernel(m, dims=dims, bits=bits),
+                                                    mccube.MonteCarloKernel(per, key=42))
+    solver = mccube.MCCSolver(dfx.Euler(), kernel)
+    t0, t1 = np.float32(0.05), np.float32(0.1)
+    y1, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    assert solver.last_path == "fused:box_prk_step" and y1.shape == (n, d)
+    assert torch.isfinite(y1).all()
+    # (1) determinism: the step is a pure function of (key, t, y0)
+    y1b, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    assert torch.equal(y1, y1b)
+    del y1b
+    # (2) sortedness: partitions are consecutive chunks of the key-sorted children, so box keys of
+    #     the output are non-decreasing from one partition to the next
+    drift, cub, dt, k, dd = solver._describe(terms, y0, *solver.substep_times(t0, t1)[0], None)
+    bounds = _lib.box_child_bounds(y0, d, drift, dt, cub, dims, bits)
+    keys = _lib.box_keys(y1, dims, bits, bounds).view(m, per).to(torch.int64)
+    kmin, kmax = keys.min(dim=1).values, keys.max(dim=1).values
+    assert bool((kmax[:-1] <= kmin[1:]).all())
+    del keys
+    # (3) the independent formulation (child keys for all 2^31 children -> stable radix sort ->
+    #     permuted gather) gives the same state bit for bit
+    solver2 = mccube.MCCSolver(dfx.Euler(), kernel)
+    solver2.use_box_prk_kernel = False
+    y2, *_ = solver2.step(terms, t0, t1, y0, None, None, False)
+    assert solver2.last_path == "fused:box_child_keys+sort+expand_select"
+    assert torch.equal(y1, y2)
+    del y2
+    _lib.release_workspace()
+    # (4) one Langevin step contracts the mean towards the target by dt/var
+    mean0, _ = mccube.mean_and_cov(y0)
+    mean1, _ = mccube.mean_and_cov(y1)
+    expect = mean0 + float(dt) * (2.0 - mean0) / 3.0
+    assert float((mean1 - expect).abs().max()) < 0.02
+
+
+def test_config2_monte_carlo_full_size(dev):
+    """BASELINE config 2: n=2^20, d=10, MonteCarloKernel (default without replacement): replay is
+    bit-identical, selected children are distinct, and the fused step equals materialise +
+    gather with the (oracle-verified) index vector."""
+    n, d = 1 << 20, 10
+    y0, terms = _problem(n, d, dev, seed=1)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=42))
+    t0, t1 = np.float32(0.05), np.float32(0.1)
+    y1, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    y1b, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    assert torch.equal(y1, y1b)
+    k = 32
+    idx = _lib.mc_indices(_lib.make_rng((0, 42), t0), n * k, n, False, dev)  # bit-exact vs oracle: test_gpu_parity
+    assert torch.unique(idx).numel() == n
+    drift, cub, dt, kk, dd = solver._describe(terms, y0, *solver.substep_times(t0, t1)[0], None)
+    children = _lib.expand_all(y0, d, False, drift, dt, cub)      # 2^25 x 10 floats = 1.25 GiB, fits
+    want = _lib.gather_rows(children, idx)
+    assert torch.equal(y1, want)
+
+
+def test_monte_carlo_config3_size_with_replacement(dev):
+    """n=2^24, d=64, global MonteCarloKernel(with_replacement=True): every sampled output row is
+    its parent plus drift plus a +-scale noise vector (checked through the index vector)."""
+    n, d = 1 << 24, 64
+    y0, terms = _problem(n, d, dev, seed=2)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, True, key=42))
+    t0, t1 = np.float32(0.1), np.float32(0.15)
+    y1, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    idx = _lib.mc_indices(_lib.make_rng((0, 42), t0), n * 128, n, True, dev).to(torch.int64) & 0xFFFFFFFF
+    assert int(idx.max()) < n * 128
+    parent = idx // 128
+    drift, cub, dt, k, dd = solver._describe(terms, y0, *solver.substep_times(t0, t1)[0], None)
+    sample = torch.arange(0, n, 4099, device=dev)
+    yp = y0[parent[sample]]
+    centre = yp + (float(dt) * ((2.0 - yp) * (1.0 / 3.0)))
+    resid = (y1[sample] - centre).abs()
+    assert float((resid - float(cub.scale)).abs().max()) < 1e-5
