@@ -197,6 +197,22 @@ MCCB200_API int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, co
 MCCB200_API int mccb200_gaussian_full_drift(const float* y, uint64_t n, int d, int ld, const float* mean,
                                 const float* prec /*[d, d] row-major*/, float* f, void* stream);
 
+/* ------------------------------------------------------------------ sharded global resample
+ * Multi-GPU form of MonteCarloKernel (the reference is single-device).  Every rank
+ * holds n_loc consecutive parents and the SAME global index vector idx[n_tot] (a pure function
+ * of (key, t)).  owner(s) = parent(idx[s]) / n_loc can materialise slot s locally;
+ * dest(s) = s / n_loc stores it.
+ *   shard_owner_keys: keys[s] = owner(s); counts[owner * n_ranks + dest] = #slots (device, uint32)
+ *   (sort_pairs(keys, iota, log2 n_ranks) then groups the slots by owner, ascending slot inside)
+ *   shard_send_ids  : out[q] = idx[order[start + q]] - child_offset  (local child ids to expand)
+ *   scatter_rows    : out[slots[r] - slot_offset, :] = in[r, :]      (placement after the exchange) */
+MCCB200_API int mccb200_shard_owner_keys(const uint32_t* idx, uint64_t n_tot, uint64_t n_loc, int k, int n_ranks,
+                                         uint32_t* keys, uint32_t* counts, void* stream);
+MCCB200_API int mccb200_shard_send_ids(const uint32_t* idx, const uint32_t* order, uint64_t start, uint64_t count,
+                                       uint64_t child_offset, uint32_t* out, void* stream);
+MCCB200_API int mccb200_scatter_rows(const float* in, int ld, const uint32_t* slots, uint64_t slot_offset,
+                                     uint64_t n_rows, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

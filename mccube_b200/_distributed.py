@@ -62,3 +62,84 @@ def distributed_mean_and_cov(particles: torch.Tensor, weights=None, ddof: int = 
     m2 = _lib.second_moment(particles.contiguous(), d, centre, weights)
     cov = global_cov(m2, sums, centre, mean, wtot, ddof, group)
     return mean, cov
+
+
+# ------------------------------------------------------------------ sharded global resample
+def plan_blocks(counts, rank: int):
+    """Pure host arithmetic on the replicated counts matrix counts[owner, dest] (number of output
+    slots stored by `dest` whose selected parent lives on `owner`).  With the slots stably
+    grouped by owner (ascending slot inside a group, hence ascending dest):
+      send = (start, count) of the block this rank materialises, and its per-dest split sizes;
+      recv = per-source split sizes and, for each source o, the (start, count) of the sub-block
+             of o's group that is destined to this rank (arrival order == ascending slot)."""
+    import numpy as np
+
+    counts = np.asarray(counts, dtype=np.int64)
+    per_owner = counts.sum(axis=1)
+    owner_start = np.concatenate([[0], np.cumsum(per_owner)[:-1]])
+    send = dict(start=int(owner_start[rank]), count=int(per_owner[rank]), splits=[int(c) for c in counts[rank]])
+    recv_blocks = [(int(owner_start[o] + counts[o, :rank].sum()), int(counts[o, rank])) for o in range(counts.shape[0])]
+    recv = dict(splits=[int(c) for c in counts[:, rank]], blocks=recv_blocks, count=int(counts[:, rank].sum()))
+    return send, recv
+
+
+def exchange_rows(send_buf: torch.Tensor, send_splits, recv_splits, group=None) -> torch.Tensor:
+    """Variable-size all-to-all of rows (NCCL over NVLink on GPUs; gloo on CPU for the tests)."""
+    recv = send_buf.new_empty((sum(recv_splits),) + tuple(send_buf.shape[1:]))
+    dist.all_to_all_single(recv, send_buf.contiguous(), output_split_sizes=list(recv_splits),
+                           input_split_sizes=list(send_splits), group=group)
+    return recv
+
+
+class ShardedMonteCarloStep:
+    """One MCCSolver step with a GLOBAL MonteCarloKernel resample over row-sharded particles.
+
+    Every rank draws the same global index vector (bit-exact with the single-GPU / reference
+    one), materialises the selected children of ITS OWN parents with the fused expand+select
+    kernel (no parent row ever crosses the link), and one variable-size all-to-all moves each
+    child row to the rank that stores its output slot.  The concatenation of the per-rank results
+    is bit-identical to the single-device step on the concatenated state.
+    """
+
+    def __init__(self, solver, terms, n_ranks: int):
+        from ._kernels import MonteCarloKernel
+
+        if type(solver.recombination_kernel) is not MonteCarloKernel or solver.weighted or solver.n_substeps != 1:
+            raise NotImplementedError("sharded step: unweighted MonteCarloKernel with n_substeps=1 only")
+        self.solver, self.terms, self.n_ranks = solver, terms, n_ranks
+
+    def prepare(self, t0, t1, y_shard: torch.Tensor, rank: int):
+        """Local work before the exchange: (send_buf, send_splits, recv_splits, placement)."""
+        import math
+
+        from . import _lib
+
+        solver, kernel = self.solver, self.solver.recombination_kernel
+        n_loc, d = y_shard.shape
+        n_tot = n_loc * self.n_ranks
+        if kernel.recombination_count != n_tot:
+            raise ValueError(f"MonteCarloKernel.recombination_count must be the GLOBAL particle count {n_tot}")
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        idx = kernel.indices(t0, n_tot * k, n_tot, y_shard.device)            # replicated, deterministic
+        keys, counts_dev = _lib.shard_owner_keys(idx, n_loc, k, self.n_ranks)
+        order = _lib.sort_pairs(keys, None, max(1, math.ceil(math.log2(self.n_ranks))))
+        counts = counts_dev.cpu().numpy()                                     # host split sizes for the collective
+        send, recv = plan_blocks(counts, rank)
+        ids = _lib.shard_send_ids(idx, order, send["start"], send["count"], rank * n_loc * k)
+        send_buf = _lib.expand_select(y_shard, d, False, drift, dt, cub, ids, n_out=send["count"])
+        slots = torch.cat([order[s:s + c] for (s, c) in recv["blocks"]]) if recv["count"] else order[:0]
+        return send_buf, send["splits"], recv["splits"], (slots.contiguous(), rank * n_loc, n_loc, d)
+
+    @staticmethod
+    def place(recv_buf: torch.Tensor, placement) -> torch.Tensor:
+        from . import _lib
+
+        slots, slot_offset, n_loc, d = placement
+        y1 = torch.empty((n_loc, d), dtype=torch.float32, device=recv_buf.device)
+        return _lib.scatter_rows_(y1, recv_buf.contiguous(), slots, slot_offset)
+
+    def step(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None) -> torch.Tensor:
+        send_buf, send_splits, recv_splits, placement = self.prepare(t0, t1, y_shard.contiguous(), rank)
+        if self.n_ranks == 1:
+            return self.place(send_buf, placement)
+        return self.place(exchange_rows(send_buf, send_splits, recv_splits, group), placement)

@@ -88,6 +88,12 @@ _SIGNATURES = {
                                       C.c_void_p]),
     "mccb200_moments_m2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "mccb200_shard_owner_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
+    "mccb200_shard_send_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                         C.c_void_p]),
+    "mccb200_scatter_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p,
+                                       C.c_void_p]),
     "mccb200_gaussian_full_drift": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
 }
@@ -415,3 +421,33 @@ def gaussian_full_drift(y, d, mean, prec):
     _check(lib.mccb200_gaussian_full_drift(y.data_ptr(), y.shape[0], d, y.shape[1], mean.data_ptr(), prec.data_ptr(),
                                            f.data_ptr(), _stream()), "gaussian_full_drift")
     return f
+
+
+def shard_owner_keys(idx, n_loc, k, n_ranks):
+    """(keys[n_tot] = owner rank of every output slot, counts[n_ranks, n_ranks] = slots per (owner, dest))."""
+    lib = load()
+    _require_cuda(idx)
+    keys = torch.empty(idx.numel(), dtype=torch.int32, device=idx.device)
+    counts = torch.empty((n_ranks, n_ranks), dtype=torch.int32, device=idx.device)
+    _check(lib.mccb200_shard_owner_keys(idx.data_ptr(), idx.numel(), n_loc, k, n_ranks, keys.data_ptr(),
+                                        counts.data_ptr(), _stream()), "shard_owner_keys")
+    return keys, counts
+
+
+def shard_send_ids(idx, order, start, count, child_offset):
+    lib = load()
+    _require_cuda(idx, order)
+    out = torch.empty(count, dtype=torch.int32, device=idx.device)
+    _check(lib.mccb200_shard_send_ids(idx.data_ptr(), order.data_ptr(), start, count, child_offset, out.data_ptr(),
+                                      _stream()), "shard_send_ids")
+    return out
+
+
+def scatter_rows_(out, rows, slots, slot_offset=0):
+    """out[slots[r] - slot_offset, :] = rows[r, :]"""
+    lib = load()
+    _require_cuda(out, rows, slots)
+    _f32c(rows); _f32c(out)
+    _check(lib.mccb200_scatter_rows(rows.data_ptr(), rows.shape[1], slots.data_ptr(), slot_offset, rows.shape[0],
+                                    out.data_ptr(), _stream()), "scatter_rows")
+    return out

@@ -60,3 +60,64 @@ def test_global_moments_two_ranks_gloo():
         mp.spawn(_worker, args=(world, _free_port(), n, d, out), nprocs=world, join=True)
         np.testing.assert_allclose(out["mean"], out["want_mean"], rtol=1e-12)
         np.testing.assert_allclose(out["cov"], out["want_cov"], rtol=1e-9, atol=1e-12)
+
+
+def test_plan_blocks_matches_bruteforce():
+    from mccube_b200._distributed import plan_blocks
+
+    rs = np.random.default_rng(3)
+    G, n_loc, k = 4, 50, 8
+    n_tot = G * n_loc
+    idx = rs.integers(0, n_tot * k, size=n_tot)
+    owner = idx // (n_loc * k)
+    dest = np.arange(n_tot) // n_loc
+    counts = np.zeros((G, G), np.int64)
+    np.add.at(counts, (owner, dest), 1)
+    order = np.argsort(owner, kind="stable")
+    for r in range(G):
+        send, recv = plan_blocks(counts, r)
+        mine = order[send["start"]:send["start"] + send["count"]]
+        assert np.array_equal(mine, np.nonzero(owner == r)[0])
+        assert send["splits"] == [int(((owner == r) & (dest == q)).sum()) for q in range(G)]
+        got = np.concatenate([order[s:s + c] for s, c in recv["blocks"]])
+        want = np.concatenate([np.nonzero((owner == o) & (dest == r))[0] for o in range(G)])
+        assert np.array_equal(got, want) and sorted(got) == list(range(r * n_loc, (r + 1) * n_loc))
+
+
+def _exchange_worker(rank, world, port, out):
+    from mccube_b200._distributed import exchange_rows, plan_blocks
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.default_rng(5)
+        n_loc, k, d = 64, 4, 3
+        n_tot = world * n_loc
+        idx = rs.integers(0, n_tot * k, size=n_tot)
+        children = rs.normal(size=(n_tot * k, d)).astype(np.float32)     # stand-in for the expansion
+        owner, dest = idx // (n_loc * k), np.arange(n_tot) // n_loc
+        counts = np.zeros((world, world), np.int64)
+        np.add.at(counts, (owner, dest), 1)
+        order = np.argsort(owner, kind="stable")
+        send, recv = plan_blocks(counts, rank)
+        mine = order[send["start"]:send["start"] + send["count"]]
+        send_buf = torch.tensor(children[idx[mine]])                       # what expand_select produces locally
+        recv_buf = exchange_rows(send_buf, send["splits"], recv["splits"])
+        slots = np.concatenate([order[s:s + c] for s, c in recv["blocks"]])
+        y1 = np.empty((n_loc, d), np.float32)
+        y1[slots - rank * n_loc] = recv_buf.numpy()
+        out[rank] = (y1, children[idx[rank * n_loc:(rank + 1) * n_loc]])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_resample_exchange_two_ranks_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        for r in range(world):
+            got, want = out[r]
+            assert np.array_equal(got, want)

@@ -411,3 +411,35 @@ def test_box_prk_step_matches_sort_path_and_oracle(dev, n, d, dims, bits, m, rep
             ref.MonteCarloKernel(out_per, replace, key=jr.prng_key(42)))
         oracle = ref.mcc_step(y0, t0, t1, fn, ref.hadamard_points(d), ref.hadamard_weights(d), SQRT2, kern)
         assert np.array_equal(got, oracle)
+
+
+# ------------------------------------------------------------------ sharded global resample
+@pytest.mark.parametrize("replace", [False, True])
+def test_sharded_monte_carlo_step_emulated_ranks(dev, replace):
+    """The multi-GPU global resample, with the ranks emulated one after another on this GPU and
+    the NCCL all-to-all replaced by an in-memory exchange: the concatenated result must be
+    bit-identical to the single-device step on the concatenated state."""
+    from mccube_b200._distributed import ShardedMonteCarloStep
+
+    G, n_loc, d = 4, 250, 10
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=21)
+    terms = _terms(d, mean, inv_var, dev)
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    yt = cuda(y, dev)
+    single = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, replace, key=42))
+    want, *_ = single.step(terms, t0, t1, yt, None, None, False)
+    sharded = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, replace, key=42)),
+                                    terms, G)
+    prepared = [sharded.prepare(t0, t1, yt[r * n_loc:(r + 1) * n_loc].contiguous(), r) for r in range(G)]
+    outs = []
+    for r in range(G):
+        parts = []
+        for src in range(G):
+            send_buf, send_splits, _, _ = prepared[src]
+            off = sum(send_splits[:r])
+            parts.append(send_buf[off:off + send_splits[r]])
+        recv = torch.cat(parts)
+        assert [p.shape[0] for p in parts] == prepared[r][2]
+        outs.append(ShardedMonteCarloStep.place(recv, prepared[r][3]))
+    assert torch.equal(torch.cat(outs), want)
