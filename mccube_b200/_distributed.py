@@ -83,6 +83,37 @@ def plan_blocks(counts, rank: int):
     return send, recv
 
 
+def plan_rebalance(per_owner, n_loc: int):
+    """Deterministic rebalancing of owner-computed rows (pure host arithmetic, identical on every
+    rank).  per_owner[r] = rows rank r materialises from its own parents (sums to G * n_loc).
+    Every rank keeps its first min(per_owner[r], n_loc) rows; ranks with a surplus give their
+    LAST rows, in rank order, to the ranks with a deficit, in rank order.
+    Returns transfers[src][dst] = row count, and for every src the offset (within its surplus
+    rows) at which the rows for dst begin."""
+    import numpy as np
+
+    per_owner = np.asarray(per_owner, dtype=np.int64)
+    G = per_owner.shape[0]
+    surplus = np.maximum(per_owner - n_loc, 0)
+    deficit = np.maximum(n_loc - per_owner, 0)
+    assert surplus.sum() == deficit.sum()
+    transfers = np.zeros((G, G), dtype=np.int64)
+    src, dst = 0, 0
+    s_left, d_left = surplus.copy(), deficit.copy()
+    while True:
+        while src < G and s_left[src] == 0:
+            src += 1
+        while dst < G and d_left[dst] == 0:
+            dst += 1
+        if src >= G or dst >= G:
+            break
+        c = min(s_left[src], d_left[dst])
+        transfers[src, dst] += c
+        s_left[src] -= c
+        d_left[dst] -= c
+    return transfers
+
+
 def exchange_rows(send_buf: torch.Tensor, send_splits, recv_splits, group=None) -> torch.Tensor:
     """Variable-size all-to-all of rows (NCCL over NVLink on GPUs; gloo on CPU for the tests)."""
     recv = send_buf.new_empty((sum(recv_splits),) + tuple(send_buf.shape[1:]))
@@ -143,3 +174,57 @@ class ShardedMonteCarloStep:
         if self.n_ranks == 1:
             return self.place(send_buf, placement)
         return self.place(exchange_rows(send_buf, send_splits, recv_splits, group), placement)
+
+    # ---- owner-computes variant: no row leaves its rank except the binomial imbalance
+    def prepare_owner(self, t0, t1, y_shard: torch.Tensor, rank: int):
+        """Every rank materialises the selected children of its own parents in place (slot order)
+        and only the surplus over n_loc rows is exchanged, so the collective moves O(sqrt(n_loc))
+        rows instead of (G-1)/G of the state.  The global multiset of particles equals the
+        reference's; the row ORDER differs by a known permutation, returned as `slot_map`
+        (global output slot of every local row) so parity can be checked exactly.
+        Returns (y1 with the kept rows filled, send_buf, send_splits, recv_splits, keep, slot_map_parts)."""
+        import math
+
+        from . import _lib
+
+        solver, kernel = self.solver, self.solver.recombination_kernel
+        n_loc, d = y_shard.shape
+        G = self.n_ranks
+        n_tot = n_loc * G
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        idx = kernel.indices(t0, n_tot * k, n_tot, y_shard.device)
+        keys, counts_dev = _lib.shard_owner_keys(idx, n_loc, k, G)
+        order = _lib.sort_pairs(keys, None, max(1, math.ceil(math.log2(G))))
+        counts = counts_dev.cpu().numpy()
+        per_owner = counts.sum(axis=1)
+        starts = [int(x) for x in ([0] + list(per_owner.cumsum()[:-1]))]
+        transfers = plan_rebalance(per_owner, n_loc)
+        keep = int(min(per_owner[rank], n_loc))
+        y1 = torch.empty((n_loc, d), dtype=torch.float32, device=y_shard.device)
+        base = rank * n_loc * k
+        if keep:
+            ids = _lib.shard_send_ids(idx, order, starts[rank], keep, base)
+            _lib.expand_select(y_shard, d, False, drift, dt, cub, ids, n_out=keep, out=y1[:keep])
+        n_give = int(transfers[rank].sum())
+        ids = _lib.shard_send_ids(idx, order, starts[rank] + n_loc, n_give, base)
+        send_buf = (_lib.expand_select(y_shard, d, False, drift, dt, cub, ids, n_out=n_give) if n_give
+                    else y1.new_empty((0, d)))
+        # slot map: kept rows, then received rows in giver order (the giver's surplus rows are
+        # order[starts[g] + n_loc + offset ...], offset = rows it gave to lower-ranked takers)
+        parts = [order[starts[rank]:starts[rank] + keep]]
+        for g in range(G):
+            c = int(transfers[g, rank])
+            if c:
+                off = int(transfers[g, :rank].sum())
+                parts.append(order[starts[g] + n_loc + off: starts[g] + n_loc + off + c])
+        return (y1, send_buf, [int(c) for c in transfers[rank]], [int(c) for c in transfers[:, rank]], keep,
+                torch.cat(parts))
+
+    def step_owner(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None):
+        """Returns (y1_shard, slot_map): y1_shard[q] is the reference's output row slot_map[q]."""
+        y1, send_buf, send_splits, recv_splits, keep, slot_map = self.prepare_owner(t0, t1, y_shard.contiguous(), rank)
+        if self.n_ranks > 1:
+            recv = exchange_rows(send_buf, send_splits, recv_splits, group)
+            if recv.shape[0]:
+                y1[keep:keep + recv.shape[0]] = recv
+        return y1, slot_map

@@ -52,6 +52,12 @@ def main():
         sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, rep, key=42)), terms, world)
         got = sh.step(t0, t1, y[rank * n_loc:(rank + 1) * n_loc].contiguous(), rank)
         assert torch.equal(got, want[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: sharded != single (replace={rep})"
+    # owner-computes variant: rows equal the single-device result through the exported slot map
+    want, *_ = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)).step(
+        terms, t0, t1, y, None, None, False)
+    sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)), terms, world)
+    got, slot_map = sh.step_owner(t0, t1, y[rank * n_loc:(rank + 1) * n_loc].contiguous(), rank)
+    assert torch.equal(got, want[slot_map.to(torch.int64) & 0xFFFFFFFF]), f"rank {rank}: owner-computes mismatch"
     dist.barrier()
 
     # ---- timing at n_loc = 2^n_log2 per rank
@@ -73,7 +79,23 @@ def main():
     torch.cuda.synchronize(); dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # owner-computes timing
+    gen.manual_seed(11 + rank)
+    yo = torch.randn((n_loc, d), generator=gen, device=dev)
+    for i in range(3):
+        yo, _ = sh.step_owner(times[i][0], times[i][1], yo, rank)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for i in range(3, 3 + a.steps):
+        yo, _ = sh.step_owner(times[i][0], times[i][1], yo, rank)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms_o = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms_o, op=dist.ReduceOp.MAX)
     if rank == 0:
+        print(json.dumps({"variant": "owner-computes (imbalance exchange only)", "n_gpus": world, "n_per_gpu": n_loc, "d": d,
+                          "ms_per_step": float(ms_o) / a.steps,
+                          "particle_steps_per_sec": n_tot * a.steps / (float(ms_o) * 1e-3)}))
         print(json.dumps({"check": "sharded == single-device, bit-exact (replace False and True)", "n_gpus": world,
                           "n_per_gpu": n_loc, "d": d, "replace": replace, "ms_per_step": float(ms) / a.steps,
                           "particle_steps_per_sec": n_tot * a.steps / (float(ms) * 1e-3),

@@ -121,3 +121,16 @@ def test_sharded_resample_exchange_two_ranks_gloo():
         for r in range(world):
             got, want = out[r]
             assert np.array_equal(got, want)
+
+
+def test_plan_rebalance_is_consistent():
+    from mccube_b200._distributed import plan_rebalance
+
+    rs = np.random.default_rng(9)
+    for G, n_loc in [(2, 100), (8, 1000), (5, 7)]:
+        for _ in range(20):
+            per = rs.multinomial(G * n_loc, np.ones(G) / G)
+            tr = plan_rebalance(per, n_loc)
+            assert np.array_equal(per - tr.sum(1) + tr.sum(0), np.full(G, n_loc))   # everybody ends with n_loc
+            assert np.array_equal(tr.sum(1), np.maximum(per - n_loc, 0))            # only the surplus moves
+            assert (np.diag(tr) == 0).all()

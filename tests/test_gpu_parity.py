@@ -443,3 +443,38 @@ def test_sharded_monte_carlo_step_emulated_ranks(dev, replace):
         assert [p.shape[0] for p in parts] == prepared[r][2]
         outs.append(ShardedMonteCarloStep.place(recv, prepared[r][3]))
     assert torch.equal(torch.cat(outs), want)
+
+
+def test_sharded_owner_computes_emulated_ranks(dev):
+    """Owner-computes variant: only the imbalance is exchanged; rows equal the single-device
+    result after applying the exported slot map (a permutation of all output slots)."""
+    from mccube_b200._distributed import ShardedMonteCarloStep
+
+    G, n_loc, d = 4, 500, 10
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=33)
+    terms = _terms(d, mean, inv_var, dev)
+    t0, t1 = np.float32(0.4), np.float32(0.45)
+    yt = cuda(y, dev)
+    want, *_ = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)).step(
+        terms, t0, t1, yt, None, None, False)
+    sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)), terms, G)
+    prep = [sh.prepare_owner(t0, t1, yt[r * n_loc:(r + 1) * n_loc].contiguous(), r) for r in range(G)]
+    all_slots = []
+    moved = 0
+    for r in range(G):
+        y1, _, _, recv_splits, keep, slot_map = prep[r]
+        parts = []
+        for src in range(G):
+            _, send_buf, send_splits, _, _, _ = prep[src]
+            off = sum(send_splits[:r])
+            parts.append(send_buf[off:off + send_splits[r]])
+        recv = torch.cat(parts)
+        assert [p.shape[0] for p in parts] == recv_splits and keep + recv.shape[0] == n_loc
+        y1[keep:] = recv
+        moved += recv.shape[0]
+        sm = slot_map.to(torch.int64) & 0xFFFFFFFF
+        assert torch.equal(y1, want[sm])
+        all_slots.append(sm)
+    assert torch.equal(torch.sort(torch.cat(all_slots)).values, torch.arange(n_tot, device=dev))
+    assert moved < n_tot // 4          # only the imbalance crosses ranks
