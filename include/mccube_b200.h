@@ -82,6 +82,20 @@ MCCB200_API size_t mccb200_mc_indices_workspace_bytes(uint64_t n_inputs, uint64_
 MCCB200_API int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, int replace,
                        uint32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weighted branches of jr.choice (random.py:60-65 with a real `weighting_function`):
+ *   gumbel_keys: keys_out[i] = order-preserving uint32 of g_i = -gumbel(key)_i - log(p_i); the
+ *     caller sorts them (sort_pairs, 32 bits) and keeps the first `count`  (Gumbel top-k).
+ *   weighted_choice_replace: c = cumsum(p) (fp64 accumulate), r = c[-1] * (1 - uniform(key)),
+ *     idx = searchsorted(c, r).
+ * p may be strided (the weight column of packed particles).  Random bits are jax.random's; the
+ * float arithmetic is not promised bit-identical to XLA. */
+MCCB200_API size_t mccb200_weighted_workspace_bytes(uint64_t n_inputs);
+MCCB200_API int mccb200_gumbel_keys(const mccb200_rng* rng, const float* p, int p_stride, uint64_t n_inputs,
+                                    uint32_t* keys_out, void* workspace, size_t workspace_bytes, void* stream);
+MCCB200_API int mccb200_weighted_choice_replace(const mccb200_rng* rng, const float* p, int p_stride,
+                                                uint64_t n_inputs, uint64_t count, uint32_t* idx_out,
+                                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stable LSD radix sort of (uint32 key, uint32 value) pairs on bits [0, key_bits)
  * == lax.sort_key_val(keys, values, is_stable=True) (jax _shuffle) / jnp.argsort
  * (stratified.py:43).  values_in == NULL sorts an implicit iota (argsort).

@@ -4,9 +4,9 @@
 The index vector `jr.choice` would gather with is produced on the GPU by
 `mccb200_mc_indices` (in-kernel threefry2x32 + stable radix-sort shuffle), bit-exact
 with jax.random on the integer branches (p = None).  Weighted sampling with a real
-`weighting_function` (Gumbel top-k / inverse-CDF, random.py:62-65) is float arithmetic
-that cannot be promised bit-exact across XLA-CPU and CUDA libm and is not part of this
-round: it raises NotImplementedError.
+`weighting_function` (Gumbel top-k / inverse-CDF, random.py:62-65) uses the same random
+bits but float arithmetic (log, cumsum) that cannot be promised bit-exact across XLA-CPU and
+CUDA libm: `mccb200_gumbel_keys` / `mccb200_weighted_choice_replace`.
 """
 from __future__ import annotations
 
@@ -50,21 +50,29 @@ class MonteCarloKernel(AbstractRecombinationKernel):
         return _lib.mc_indices(rng, n_inputs, math.prod(shape), self.with_replacement, device)
 
     def _probabilities(self, p, weighted):
+        """`weights = self.weighting_function(weights)` (random.py:60-63); None = uniform."""
         if not weighted:
             return None
         _, w = unpack_particles(p, True)
         w = self.weighting_function(w)
-        if w is not None:
-            raise NotImplementedError(
-                "MonteCarloKernel with a non-trivial weighting_function (Gumbel top-k / inverse-CDF sampling, "
-                "random.py:62-65) is not implemented on the CUDA path yet")
-        return None
+        if w is None:
+            return None
+        return torch.as_tensor(w, dtype=torch.float32, device=p.device)
+
+    def weighted_indices(self, t, probs, count, leaf: int = 0, n_leaves: int = 1) -> torch.Tensor:
+        """Gumbel top-k (without replacement) / inverse-CDF (with) indices (random.py:65 with p)."""
+        shape = tuple(count) if isinstance(count, (tuple, list)) else (count,)
+        rng = _lib.make_rng(self.key, t, leaf=leaf, n_leaves=n_leaves, partitionable=self.threefry_partitionable)
+        return _lib.weighted_indices(rng, probs, math.prod(shape), self.with_replacement)
 
     def __call__(self, t, particles, args, weighted: bool = False):
         def _choice(i, n_leaves, p, count):
-            self._probabilities(p, weighted)
+            probs = self._probabilities(p, weighted)
             shape = tuple(count) if isinstance(count, (tuple, list)) else (count,)
-            idx = self.indices(t, p.shape[0], shape, p.device, i, n_leaves)
+            if probs is None:
+                idx = self.indices(t, p.shape[0], shape, p.device, i, n_leaves)
+            else:
+                idx = self.weighted_indices(t, probs, shape, i, n_leaves)
             out = _lib.gather_rows(p.contiguous(), idx)
             return out.reshape(*shape, p.shape[-1])
 
@@ -73,7 +81,15 @@ class MonteCarloKernel(AbstractRecombinationKernel):
     # -- all partitions at once with the shared local index vector (quirk Q4)
     def call_batched(self, t, part, args, weighted, count):
         m, per, ld = part.shape
-        self._probabilities(part[0], weighted)
+        if self._probabilities(part[0], weighted) is not None:
+            # probabilities differ per partition (same key, same Gumbel noise): one draw per partition
+            flat = part.reshape(m * per, ld).contiguous()
+            rows = []
+            for b in range(m):
+                probs = self._probabilities(part[b], weighted)
+                rows.append(self.weighted_indices(t, probs, count).to(torch.int64) + b * per)
+            idx = torch.cat(rows).to(torch.int32)
+            return _lib.gather_rows(flat, idx).reshape(m, -1, ld)
         idx_local = self.indices(t, per, count, part.device)
         idx = (torch.arange(m, device=part.device, dtype=torch.int64)[:, None] * per
                + idx_local.to(torch.int64)[None, :]).reshape(-1).to(torch.int32)

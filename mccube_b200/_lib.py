@@ -56,6 +56,11 @@ _SIGNATURES = {
     "mccb200_mc_indices_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64, C.c_int]),
     "mccb200_mc_indices": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),
+    "mccb200_weighted_workspace_bytes": (C.c_size_t, [C.c_uint64]),
+    "mccb200_gumbel_keys": (C.c_int, [C.POINTER(Rng), C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
+    "mccb200_weighted_choice_replace": (C.c_int, [C.POINTER(Rng), C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
+                                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_sort_pairs_workspace_bytes": (C.c_size_t, [C.c_uint64]),
     "mccb200_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -451,3 +456,23 @@ def scatter_rows_(out, rows, slots, slot_offset=0):
     _check(lib.mccb200_scatter_rows(rows.data_ptr(), rows.shape[1], slots.data_ptr(), slot_offset, rows.shape[0],
                                     out.data_ptr(), _stream()), "scatter_rows")
     return out
+
+
+def weighted_indices(rng: Rng, p: torch.Tensor, count: int, replace: bool) -> torch.Tensor:
+    """Index vector of jr.choice(key, a, (count,), replace, p) for a probability vector p
+    (float32, possibly a strided column view)."""
+    lib = load()
+    _require_cuda(p)
+    if p.dtype != torch.float32 or p.dim() != 1:
+        raise MccubeB200Error("weighted_indices: p must be a 1-D float32 tensor")
+    n = p.numel()
+    ws = workspace(lib.mccb200_weighted_workspace_bytes(n), p.device)
+    if replace:
+        out = torch.empty(count, dtype=torch.int32, device=p.device)
+        _check(lib.mccb200_weighted_choice_replace(C.byref(rng), p.data_ptr(), p.stride(0), n, count, out.data_ptr(),
+                                                   ws.data_ptr(), ws.numel(), _stream()), "weighted_choice_replace")
+        return out
+    keys = torch.empty(n, dtype=torch.int32, device=p.device)
+    _check(lib.mccb200_gumbel_keys(C.byref(rng), p.data_ptr(), p.stride(0), n, keys.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream()), "gumbel_keys")
+    return sort_pairs(keys, None, 32)[:count].contiguous()

@@ -7,21 +7,13 @@
 // jax_threefry_partitionable are implemented.  The oracle restatement is
 // oracle/jax_random.py; SURVEY.md Appendix A states the algorithm.
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace mccb {
 
 int sort_pairs_impl(const uint32_t*, const uint32_t*, uint64_t, int, uint32_t*, uint32_t*, void*, size_t,
                     cudaStream_t);
 size_t sort_pairs_ws(uint64_t);
-
-constexpr int MAX_ROUNDS = 8;
-
-// Derived keys, produced on the device so key / t may live in device memory.
-struct DerivedKeys {
-  u32x2 step_key;               // key handed to jr.choice
-  u32x2 round_sub[MAX_ROUNDS];  // sort-key generator of each _shuffle round
-  u32x2 randint_hi, randint_lo; // k1, k2 of randint
-};
 
 __global__ void derive_keys_kernel(mccb200_rng rng, int rounds, DerivedKeys* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -42,6 +34,10 @@ __global__ void derive_keys_kernel(mccb200_rng rng, int rounds, DerivedKeys* out
     out->round_sub[r] = split_key(k, 2, 1, part);
     k = nk;
   }
+}
+
+void launch_derive_keys(const mccb200_rng& rng, int rounds, DerivedKeys* out, cudaStream_t st) {
+  derive_keys_kernel<<<1, 32, 0, st>>>(rng, rounds, out);
 }
 
 // random_bits(sub, 32, (n,)).  Original mode: one threefry block yields elements i and

@@ -478,3 +478,58 @@ def test_sharded_owner_computes_emulated_ranks(dev):
         all_slots.append(sm)
     assert torch.equal(torch.sort(torch.cat(all_slots)).values, torch.arange(n_tot, device=dev))
     assert moved < n_tot // 4          # only the imbalance crosses ranks
+
+
+# ------------------------------------------------------------------ weighted sampling (float branches)
+def test_weighted_monte_carlo_reference_expectation(dev):
+    # /root/reference/tests/test_kernels.py:83-92: identity weighting, key 42, t=0 -> rows by descending weight
+    y0 = torch.tensor([[1.0, 0.01], [2.0, 1.0], [3.0, 100.0], [4.0, 10000.0]], device=dev)
+    for part in (False, True):
+        mc = mccube.MonteCarloKernel(None, weighting_function=lambda w: w, key=42, threefry_partitionable=part)
+        v = mccube.MonteCarloPartitioningKernel(4, mc)(0.0, y0, ..., weighted=True)
+        assert v.shape == (4, 1, 2)
+        order = torch.argsort(y0[:, -1], descending=True)
+        assert torch.equal(v[:, 0, :], y0[order])
+
+
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_weighted_indices_vs_oracle(dev, replace, partitionable):
+    """Same random bits as jax.random; float scores may round differently from NumPy's libm, so
+    allow a tiny fraction of index differences (ties within one ulp)."""
+    rs = np.random.default_rng(4)
+    P, n, t = 20000, 2500, 0.35
+    p = rs.uniform(0.05, 1.0, size=P).astype(np.float32)
+    key = jr.mc_step_key(jr.prng_key(42), t, partitionable=partitionable)
+    if replace:
+        c = np.cumsum(p.astype(np.float64)).astype(np.float32)     # the CUDA path accumulates in fp64
+        u = jr.uniform(key, n, np.float32, partitionable=partitionable)
+        want = np.searchsorted(c, c[-1] * (np.float32(1) - u))
+    else:
+        want = jr.choice_indices(key, P, n, False, p, partitionable=partitionable)
+    rng = _lib.make_rng(KEY, t, partitionable=partitionable)
+    got = u32(_lib.weighted_indices(rng, cuda(p, dev), n, replace))
+    assert got.shape == want.shape
+    mismatch = float((got != want).mean())
+    assert mismatch < 2e-3, mismatch
+    if not replace:
+        assert len(np.unique(got)) == n
+
+
+def test_weighted_solver_step_with_weighting_function(dev):
+    """MCCSolver(weighted=True) + MonteCarloKernel(weighting_function=identity): weights are
+    used as sampling probabilities and renormalised (generic path)."""
+    n, d = 64, 3
+    yy, mean, inv_var = _setup(n, d, seed=12)
+    w0 = np.random.default_rng(3).uniform(0.5, 1.5, size=n).astype(np.float32)
+    yw = ref.pack_particles(yy, w0)
+    t0, t1 = np.float32(0.1), np.float32(0.15)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, weighting_function=lambda w: w, key=7), weighted=True)
+    got, *_ = solver.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(yw, dev), None, None, False)
+    got = got.cpu().numpy()
+    want = ref.mcc_step(yw, t0, t1, lambda y: ref.gaussian_diag_drift(y, mean, inv_var), ref.hadamard_points(d),
+                        ref.hadamard_weights(d), SQRT2,
+                        ref.MonteCarloKernel(n, weighting_function=lambda w: w, key=jr.prng_key(7)), weighted=True)
+    assert got.shape == want.shape and abs(got[:, -1].sum() - 1.0) < 1e-5
+    same_rows = (got[:, :-1] == want[:, :-1]).all(axis=1).mean()
+    assert same_rows > 0.95
