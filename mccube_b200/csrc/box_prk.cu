@@ -67,6 +67,7 @@ struct BoxPrkParams {
   const uint2* sp;             // [out_per_part]     (position, l) sorted by position
   uint32_t* pdesc;             // [n] per-parent K0 | D << 12 | S << 24 (written by pass A)
   uint32_t* table;             // [n_segments + 1][n_keys]
+  const uint32_t* key_start;   // [n_keys] children with a smaller key (flat form: rows stay relative)
   uint32_t* idx_out;           // [n_out] selected child ids
   int warps_per_cta;
   int pre_in_smem, tab_in_smem;
@@ -103,8 +104,8 @@ __device__ __forceinline__ void describe_parent(const BoxPrkParams& p, uint64_t 
   for (int q = 0; q < p.spec.n_dims; ++q) {
     const int col = p.spec.dims[q];
     const float lo = __ldg(p.bounds + q), ih = __ldg(p.bounds + p.spec.n_dims + q);
-    const float y = __ldg(a.y0 + i * a.ld + col);
-    const float fv = drift_value(a, i, col, y);
+    const float y = ld_strided(a.y0 + i * a.ld + col);
+    const float fv = a.drift_kind == 1 ? ld_strided(a.f + i * a.d + col) : drift_value(a, i, col, y);
     const uint32_t cm = box_cell_u(child_value(a, y, fv, -a.scale), lo, ih, p.spec.bits);
     const uint32_t cp = box_cell_u(child_value(a, y, fv, a.scale), lo, ih, p.spec.bits);
     K0 = (K0 << p.spec.bits) | cm;
@@ -614,6 +615,233 @@ box_rank_hash_kernel(const BoxPrkParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------ flat record machinery
+// A batch = 32 consecutive parents, one per lane, parent `lane` holding ncls class records.
+// The records of the batch are numbered parent-major (excl = exclusive scan of ncls) and
+// processed 32 per ROUND with every lane busy: record r0 + lane belongs to parent
+// `owner` = (#parents whose first record is <= r) - 1.  Inside a round, __match_any_sync on the
+// key gives each record its peers; records of one key are in parent order both inside a round
+// (lane order) and across rounds (earlier rounds hold earlier parents), and one parent never
+// holds a key twice, so "start of the key + sizes of the lower peers" is the stable rank.
+struct FlatBatch {
+  uint32_t desc;   // K0 | D << 12 | S << 24 of this lane's parent
+  uint32_t pk;     // excl | log2(ncls) << 16
+  uint32_t ncls, excl, R;
+};
+
+__device__ __forceinline__ FlatBatch flat_batch(uint32_t desc, uint32_t ncls, int lane) {
+  FlatBatch b;
+  uint32_t incl = ncls;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  b.desc = desc; b.ncls = ncls; b.excl = incl - ncls;
+  b.R = __shfl_sync(0xffffffffu, incl, 31);
+  b.pk = b.excl | ((ncls ? (uint32_t)(__ffs(ncls) - 1) : 0u) << 16);
+  return b;
+}
+
+struct FlatRecord {
+  bool valid;
+  int owner;        // lane holding the record's parent
+  uint32_t S, ent, key, lsz;   // split set, packed class entry, box key, log2(k / class size)
+};
+
+__device__ __forceinline__ FlatRecord flat_record(const FlatBatch& b, uint32_t r0, int lane, const uint32_t* s_tab,
+                                                  uint32_t cls_pad_log2) {
+  FlatRecord rec;
+  const uint32_t r = r0 + (uint32_t)lane;
+  rec.valid = r < b.R;
+  const uint32_t rel = b.excl - r0;                     // wraps (>= 32) when the parent starts earlier
+  const uint32_t starts = __reduce_or_sync(0xffffffffu, (b.ncls && rel < 32u) ? (1u << rel) : 0u);
+  const uint32_t before = (uint32_t)__popc(__ballot_sync(0xffffffffu, b.ncls && b.excl < r0));
+  const uint32_t le_mask = 0xffffffffu >> (31 - lane);
+  rec.owner = rec.valid ? (int)(before + (uint32_t)__popc(starts & le_mask)) - 1 : 0;
+  const uint32_t od = __shfl_sync(0xffffffffu, b.desc, rec.owner);
+  const uint32_t opk = __shfl_sync(0xffffffffu, b.pk, rec.owner);
+  rec.S = od >> 24;
+  rec.ent = rec.valid ? s_tab[(rec.S << cls_pad_log2) + (r - (opk & 0xFFFFu))] : 0u;
+  rec.key = rec.valid ? (od & 0xFFFu) + ((od >> 12) & rec.ent & 0xFFFu) : 0xFFFFFFFFu;
+  rec.lsz = rec.valid ? (opk >> 16) : 31u;
+  return rec;
+}
+
+// Sum of the class sizes k >> lsz over the peers (tot) and over the peers in lower lanes (ex).
+__device__ __forceinline__ void peer_sizes(uint32_t peers, uint32_t lsz, int logk, int nb, uint32_t lt_mask,
+                                           uint32_t& ex, uint32_t& tot) {
+  ex = 0; tot = 0;
+  for (int b = 0; b < nb; ++b) {
+    const uint32_t m = __ballot_sync(0xffffffffu, lsz == (uint32_t)b);
+    if (m) {                                             // warp-uniform
+      const uint32_t mb = peers & m;
+      ex += (uint32_t)__popc(mb & lt_mask) << (logk - b);
+      tot += (uint32_t)__popc(mb) << (logk - b);
+    }
+  }
+}
+
+// (K0, D, S) from the two candidate child coordinates in 4 vectorised key dims
+__device__ __forceinline__ uint32_t describe_parent4(const BoxPrkParams& p, uint64_t i, const float (&lo)[4],
+                                                     const float (&ih)[4]) {
+  float vm[4], vp[4];
+  key_children4(p.a, p.spec, i, vm, vp);
+  uint32_t K0 = 0, D = 0, S = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t cm = box_cell_u(vm[q], lo[q], ih[q], p.spec.bits);
+    const uint32_t cp = box_cell_u(vp[q], lo[q], ih[q], p.spec.bits);
+    K0 = (K0 << p.spec.bits) | cm;
+    D = (D << p.spec.bits) | (cp - cm);
+    if (cp != cm) S |= 1u << q;
+  }
+  return K0 | (D << 12) | (S << 24);
+}
+
+// ------------------------------------------------------------------ pass A (flat form)
+// CTA per segment, warps interleave its batches; one aggregated shared-memory atomic per
+// (round, distinct key) instead of one per class record (box-ordered input makes most lanes
+// of a batch share their keys, which serialises plain atomics 32-way).
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+box_count_flat_kernel(const BoxPrkParams p) {
+  extern __shared__ uint32_t smem[];
+  const ExpandArgs& a = p.a;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* hist = smem;
+  const uint32_t cls_pad = 1u << p.cls_pad_log2;
+  uint32_t* s_tab = hist + p.n_keys;
+  uint32_t* s_cnt = s_tab + p.n_sets * cls_pad;
+  for (uint32_t i = threadIdx.x; i < p.n_keys; i += blockDim.x) hist[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < p.n_sets * cls_pad; i += blockDim.x) s_tab[i] = p.cls_packed[i];
+  for (uint32_t i = threadIdx.x; i < p.n_sets; i += blockDim.x) s_cnt[i] = p.cls_count[i];
+  __syncthreads();
+  float lo[4] = {0.f, 0.f, 0.f, 0.f}, ih[4] = {0.f, 0.f, 0.f, 0.f};
+  if (VEC4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { lo[q] = __ldg(p.bounds + q); ih[q] = __ldg(p.bounds + 4 + q); }
+  }
+  const int logk = __ffs(a.k) - 1;
+  const int nb = (int)p.cls_pad_log2 + 1;
+  const uint32_t seg = blockIdx.x;
+  const uint64_t i0 = (uint64_t)seg * p.parents_per_seg;
+  const uint64_t i1 = min(a.n, i0 + p.parents_per_seg);
+  for (uint64_t base = i0 + (threadIdx.x & ~31u); base < i1; base += blockDim.x) {
+    const uint64_t i = base + lane;
+    const bool have = i < i1;
+    uint32_t desc = 0;
+    if (have) {
+      if (VEC4) desc = describe_parent4(p, i, lo, ih);
+      else { uint32_t K0, D, S; describe_parent(p, i, K0, D, S); desc = K0 | (D << 12) | (S << 24); }
+      p.pdesc[i] = desc;                                 // pass B re-reads 4 coalesced bytes per parent
+    }
+    const FlatBatch b = flat_batch(desc, have ? s_cnt[desc >> 24] : 0u, lane);
+    for (uint32_t r0 = 0; r0 < b.R; r0 += 32) {
+      const FlatRecord rec = flat_record(b, r0, lane, s_tab, p.cls_pad_log2);
+      const uint32_t peers = __match_any_sync(0xffffffffu, rec.key);
+      uint32_t ex, tot;
+      peer_sizes(peers, rec.lsz, logk, nb, lt_mask, ex, tot);
+      if (rec.valid && (peers & lt_mask) == 0u) atomicAdd(&hist[rec.key], tot);
+    }
+  }
+  __syncthreads();
+  uint32_t* row = p.table + (uint64_t)seg * p.n_keys;
+  for (uint32_t i = threadIdx.x; i < p.n_keys; i += blockDim.x) row[i] = hist[i];
+}
+
+// ------------------------------------------------------------------ pass B (flat form)
+// One warp per segment walks its batches in order.  Per round: one L2 atomicAdd per distinct
+// key on the segment's (relative) counter row hands the key's records their rank run; the
+// selection test and the rare hits follow with every lane holding a record.
+template <bool PRE_SMEM, bool MEM_SMEM>
+__global__ void __launch_bounds__(256, 4)
+box_rank_flat_kernel(const BoxPrkParams p) {
+  extern __shared__ uint32_t smem[];
+  const ExpandArgs& a = p.a;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t* cursor = smem;
+  const uint32_t cls_pad = 1u << p.cls_pad_log2;
+  uint32_t* s_tab = cursor; cursor += p.n_sets * cls_pad;
+  uint32_t* s_cnt = cursor; cursor += p.n_sets;
+  for (uint32_t i = threadIdx.x; i < p.n_sets * cls_pad; i += blockDim.x) s_tab[i] = p.cls_packed[i];
+  for (uint32_t i = threadIdx.x; i < p.n_sets; i += blockDim.x) s_cnt[i] = p.cls_count[i];
+  const uint2* sp = p.sp;
+  uint16_t* s_pre16 = nullptr;
+  if (PRE_SMEM) {
+    cursor += ((cursor - smem) & 1u);                    // 8-byte alignment for sp
+    uint2* s_sp = reinterpret_cast<uint2*>(cursor);
+    cursor += 2u * p.out_per_part;
+    s_pre16 = reinterpret_cast<uint16_t*>(cursor);
+    cursor += ((p.in_per_part + 4u) & ~3u) / 2u;
+    for (uint32_t i = threadIdx.x; i <= p.in_per_part; i += blockDim.x) s_pre16[i] = (uint16_t)p.pre[i];
+    for (uint32_t i = threadIdx.x; i < p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
+    sp = s_sp;
+  }
+  auto PRE = [&](uint32_t i) -> uint32_t { return PRE_SMEM ? (uint32_t)s_pre16[i] : __ldg(p.pre + i); };
+  const uint16_t* members = p.members;
+  if (MEM_SMEM) {
+    uint16_t* s_mem = reinterpret_cast<uint16_t*>(cursor);
+    for (uint32_t i = threadIdx.x; i < p.n_sets * a.k; i += blockDim.x) s_mem[i] = p.members[i];
+    members = s_mem;
+  }
+  __syncthreads();
+  const uint32_t seg = blockIdx.x * p.warps_per_cta + warp;
+  if (seg >= p.n_segments) return;
+  uint32_t* row = p.table + (uint64_t)seg * p.n_keys;    // same key, earlier segments (relative ranks)
+
+  const uint64_t i0 = (uint64_t)seg * p.parents_per_seg;
+  const uint64_t i1 = min(a.n, i0 + p.parents_per_seg);
+  const uint32_t Pm = p.in_per_part, nm = p.out_per_part;
+  const int logk = __ffs(a.k) - 1;
+  const int nb = (int)p.cls_pad_log2 + 1;
+
+  uint32_t ndesc = i0 + lane < i1 ? __ldcs(p.pdesc + i0 + lane) : 0u;
+  for (uint64_t base = i0; base < i1; base += 32) {
+    const uint32_t desc = ndesc;
+    const bool have = base + lane < i1;
+    if (base + 32 + lane < i1) ndesc = __ldcs(p.pdesc + base + 32 + lane);   // next batch (coalesced)
+    const FlatBatch b = flat_batch(desc, have ? s_cnt[desc >> 24] : 0u, lane);
+    for (uint32_t r0 = 0; r0 < b.R; r0 += 32) {
+      const FlatRecord rec = flat_record(b, r0, lane, s_tab, p.cls_pad_log2);
+      const uint32_t peers = __match_any_sync(0xffffffffu, rec.key);
+      uint32_t ex, tot;
+      peer_sizes(peers, rec.lsz, logk, nb, lt_mask, ex, tot);
+      const int leader = __ffs(peers) - 1;
+      uint32_t st = 0;
+      if (rec.valid && lane == leader) st = atomicAdd(row + rec.key, tot);
+      st = __shfl_sync(0xffffffffu, st, leader);
+      if (rec.valid) {
+        const uint32_t rank0 = st + __ldg(p.key_start + rec.key) + ex;
+        const uint32_t size = a.k >> rec.lsz;
+        uint32_t part0, pos0;
+        if (p.in_shift != 0xFFFFFFFFu) { part0 = rank0 >> p.in_shift; pos0 = rank0 & (Pm - 1u); }
+        else { part0 = rank0 / Pm; pos0 = rank0 - part0 * Pm; }
+        const uint32_t end = pos0 + size;                // size <= k <= Pm: wraps at most once
+        const uint32_t first = PRE(pos0);
+        const uint32_t n_hit = end <= Pm ? PRE(end) - first : (nm - first) + PRE(end - Pm);
+        if (n_hit) {
+          const uint16_t* mem = members + (size_t)rec.S * a.k + (rec.ent >> 22);
+          const uint64_t child0 = (base + (uint64_t)rec.owner) * (uint64_t)a.k;
+          for (uint32_t hh = 0; hh < n_hit; ++hh) {
+            uint32_t e = first + hh;
+            const bool wrap = e >= nm;
+            if (wrap) e -= nm;
+            const uint2 pl = sp[e];                      // (position, output slot l)
+            const uint32_t tt = wrap ? pl.x + Pm - pos0 : pl.x - pos0;
+            p.idx_out[(uint64_t)(part0 + (wrap ? 1u : 0u)) * nm + pl.y] = (uint32_t)(child0 + mem[tt]);
+          }
+        }
+      }
+      __syncwarp();   // this round's atomics are ordered before the next round's (same-key runs)
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pass B (class-lane form)
 // smem layout: [warps][n_keys] counters | packed class table | pre[in_per_part+1] + sp (if PRE_SMEM)
 //              | members (if MEM_SMEM)
@@ -746,12 +974,14 @@ struct PrkPlan {
   size_t off_pdesc, off_table, off_pre, off_fill, off_sp, off_cnt, off_fm, off_size, off_off, off_packed, off_members, off_cid, off_idx, total;
 };
 
-// rank_mode 3 (default): hash kernel, record-parallel, counter rows in global memory.
+// rank_mode 4 (default): flat kernels (records of a batch spread over all lanes, match_any ranking,
+//              one L2 atomic per distinct key and round); rows stay relative, no fold pass.
+// rank_mode 3: hash kernel, record-parallel, counter rows in global memory.
 // rank_mode 2: sweep kernel, counter rows in global memory, 32 warps per SM.
 // rank_mode 1: class-lane kernel, counter rows in shared memory (fewer warps).
 static int rank_mode() {
   const char* m = getenv("MCCB200_RANK_MODE");
-  return m ? atoi(m) : 3;
+  return m ? atoi(m) : 4;
 }
 
 static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
@@ -779,9 +1009,10 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   pl.mode = rank_mode();
   if (pl.mode == 2) pl.pre_in_smem = pre_bytes <= 36 * 1024 ? 1 : 0;   // 4 CTAs per SM share 227 KB
   size_t pre_bytes3 = ((size_t)((in_per_part + 4) & ~3ull)) * 2 + (size_t)out_per_part_max * 8;
-  if (pl.mode == 3) pl.pre_in_smem = (pre_bytes3 <= 24 * 1024 && out_per_part_max < 65536) ? 1 : 0;
-  size_t shared_part = tab_bytes + (pl.pre_in_smem ? (pl.mode == 3 ? pre_bytes3 : pre_bytes) : 0) + (pl.mem_in_smem ? mem_bytes : 0);
+  if (pl.mode >= 3) pl.pre_in_smem = (pre_bytes3 <= 24 * 1024 && out_per_part_max < 65536) ? 1 : 0;
+  size_t shared_part = tab_bytes + (pl.pre_in_smem ? (pl.mode >= 3 ? pre_bytes3 : pre_bytes) : 0) + (pl.mem_in_smem ? mem_bytes : 0);
   if (pl.mode == 3) shared_part += (size_t)8 * 3 * HT_SLOTS * 4 + (size_t)8 * HQ_CAP * 16 + (size_t)pl.n_sets * 4;
+  if (pl.mode == 4) shared_part += (size_t)pl.n_sets * 4 + 8;
   int w;
   uint64_t segs;
   const int sms = sm_count();
@@ -894,13 +1125,21 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
   box_selection_kernel<<<1, 1024, 0, st>>>(idx_local, p.out_per_part, p.in_per_part, pre, fill, sp);
 
   phase_mark("box_prk.count", st);
-  box_count_kernel<<<pl.n_segments, 256, (size_t)pl.n_keys * 4, st>>>(p);
-  phase_mark("box_prk.scan", st);
   uint32_t* key_tot = table + (uint64_t)pl.n_segments * pl.n_keys;
+  p.key_start = key_tot;
+  if (pl.mode == 4) {
+    const size_t smem_a = ((size_t)pl.n_keys + (size_t)pl.n_sets * (1u << pl.cls_pad_log2) + pl.n_sets) * 4;
+    if (box_dims_vec4(p.spec, p.a)) box_count_flat_kernel<true><<<pl.n_segments, 256, smem_a, st>>>(p);
+    else box_count_flat_kernel<false><<<pl.n_segments, 256, smem_a, st>>>(p);
+  } else {
+    box_count_kernel<<<pl.n_segments, 256, (size_t)pl.n_keys * 4, st>>>(p);
+  }
+  phase_mark("box_prk.scan", st);
   box_scan_columns_kernel<<<(pl.n_keys + 31) / 32, 1024, 0, st>>>(table, pl.n_segments, pl.n_keys, key_tot);
   box_scan_keys_kernel<<<1, 1024, 0, st>>>(key_tot, pl.n_keys);
-  box_scan_fold_kernel<<<(int)min((uint64_t)sm_count() * 8, ((uint64_t)pl.n_segments * pl.n_keys + 255) / 256), 256, 0, st>>>(
-      table, pl.n_segments, pl.n_keys, key_tot);
+  if (pl.mode != 4)   // the flat rank kernel adds key_start itself
+    box_scan_fold_kernel<<<(int)min((uint64_t)sm_count() * 8, ((uint64_t)pl.n_segments * pl.n_keys + 255) / 256), 256, 0, st>>>(
+        table, pl.n_segments, pl.n_keys, key_tot);
 
   phase_mark("box_prk.rank", st);
 #define MCCB_RANK(PS, MS)                                                                                     \
@@ -918,7 +1157,17 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
     cudaFuncSetAttribute(box_rank_hash_kernel<PS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
     box_rank_hash_kernel<PS, MS><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
   } while (0)
-  if (pl.mode == 3) {
+#define MCCB_FLAT(PS, MS)                                                                                          \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(box_rank_flat_kernel<PS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
+    box_rank_flat_kernel<PS, MS><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
+  } while (0)
+  if (pl.mode == 4) {
+    if (pl.pre_in_smem && pl.mem_in_smem) MCCB_FLAT(true, true);
+    else if (pl.pre_in_smem) MCCB_FLAT(true, false);
+    else if (pl.mem_in_smem) MCCB_FLAT(false, true);
+    else MCCB_FLAT(false, false);
+  } else if (pl.mode == 3) {
     if (pl.pre_in_smem && pl.mem_in_smem) MCCB_HASH(true, true);
     else if (pl.pre_in_smem) MCCB_HASH(true, false);
     else if (pl.mem_in_smem) MCCB_HASH(false, true);
@@ -937,6 +1186,7 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
 #undef MCCB_RANK
 #undef MCCB_SWEEP
 #undef MCCB_HASH
+#undef MCCB_FLAT
 
   // gather: the HBM-bound fused expand+select materialises the selected children
   ExpandArgs g = p.a;

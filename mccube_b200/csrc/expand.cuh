@@ -30,6 +30,23 @@ struct ExpandArgs {
 int fill_expand_args(ExpandArgs& a, const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
                      float dt, const mccb200_cubature* cub);
 
+// Loads of a few columns out of every (long) row: only one 64-byte line per row is wanted, so
+// ask L2 for a 64-byte fill instead of its default 128-byte one.  Measured on B200 (2^24 rows of
+// 256 B, 16 B used per row; experiments/strided_read.cu): 0.175 ms with the hint, 0.30 ms without;
+// cudaLimitMaxL2FetchGranularity has no effect.
+__device__ __forceinline__ float ld_strided(const float* p) {
+  float v;
+  asm("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_strided4(const float* p) {  // p 16-byte aligned
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p));
+  return v;
+}
+
 // Drift value f_col(y0[i, :]) of parent i (evaluated on PARENTS only, _term.py:58-63).
 __device__ __forceinline__ float drift_value(const ExpandArgs& a, uint64_t i, int col, float y) {
   if (a.drift_kind == 2) return __fmul_rn(__fsub_rn(__ldg(a.mean + col), y), __ldg(a.inv_var + col));
@@ -54,5 +71,37 @@ struct BoxSpec {
   int dims[MCCB200_BOX_MAX_DIMS];
 };
 int make_box_spec(BoxSpec& s, const int32_t* dims_host, int n_dims, int bits, int d);
+
+// Key dims are 4 consecutive, 16-byte aligned columns (the default dims 0..3): one 128-bit load
+// per parent instead of four scalar ones.
+inline bool box_dims_vec4(const BoxSpec& s, const ExpandArgs& a) {
+  if (s.n_dims != 4 || (s.dims[0] & 3) || (a.ld & 3)) return false;
+  for (int q = 1; q < 4; ++q)
+    if (s.dims[q] != s.dims[0] + q) return false;
+  if (((uintptr_t)a.y0) & 15) return false;
+  if (a.drift_kind == 1 && ((a.d & 3) || (((uintptr_t)a.f) & 15))) return false;
+  return true;
+}
+
+// The two candidate child coordinates (- and + noise) of parent i in its 4 vectorised key dims.
+__device__ __forceinline__ void key_children4(const ExpandArgs& a, const BoxSpec& s, uint64_t i, float (&vm)[4],
+                                              float (&vp)[4]) {
+  const int c0 = s.dims[0];
+  const float4 y4 = ld_strided4(a.y0 + i * a.ld + c0);
+  const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.drift_kind == 1) {
+    const float4 f4 = ld_strided4(a.f + i * a.d + c0);
+    f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
+  } else if (a.drift_kind == 2) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = __fmul_rn(__fsub_rn(__ldg(a.mean + c0 + q), y[q]), __ldg(a.inv_var + c0 + q));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    vm[q] = child_value(a, y[q], f[q], -a.scale);
+    vp[q] = child_value(a, y[q], f[q], a.scale);
+  }
+}
 
 }  // namespace mccb

@@ -58,28 +58,46 @@ box_bounds_rows_kernel(const float* __restrict__ p, uint64_t n, int ld, BoxSpec 
   }
 }
 
+template <bool VEC4>
 __global__ void __launch_bounds__(BB_THREADS)
 box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ partials) {
   // one pass: every thread keeps the running min/max of all key dims of its parents
   float lo[MCCB200_BOX_MAX_DIMS], hi[MCCB200_BOX_MAX_DIMS];
 #pragma unroll
   for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  if (VEC4) {
+    // 4 consecutive aligned key columns and the Hadamard cubature: one 128-bit load (64-byte L2
+    // fill) per parent, two parents in flight per thread
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += 2 * stride) {
+      float vm0[4], vp0[4], vm1[4], vp1[4];
+      const bool two = i + stride < a.n;
+      key_children4(a, spec, i, vm0, vp0);
+      key_children4(a, spec, two ? i + stride : i, vm1, vp1);
 #pragma unroll
-    for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) {
-      if (q < spec.n_dims) {
-        const int c = spec.dims[q];
-        const float y = __ldg(a.y0 + i * a.ld + c);
-        const float fv = drift_value(a, i, c, y);
-        if (a.points) {
-          for (uint32_t j = 0; j < a.k; ++j) {
-            const float v = child_value(a, y, fv, noise_value(a, j, c));
-            lo[q] = fminf(lo[q], v); hi[q] = fmaxf(hi[q], v);
+      for (int q = 0; q < 4; ++q) {
+        lo[q] = fminf(lo[q], fminf(fminf(vm0[q], vp0[q]), fminf(vm1[q], vp1[q])));
+        hi[q] = fmaxf(hi[q], fmaxf(fmaxf(vm0[q], vp0[q]), fmaxf(vm1[q], vp1[q])));
+      }
+    }
+  } else {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+#pragma unroll
+      for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) {
+        if (q < spec.n_dims) {
+          const int c = spec.dims[q];
+          const float y = ld_strided(a.y0 + i * a.ld + c);
+          const float fv = a.drift_kind == 1 ? ld_strided(a.f + i * a.d + c) : drift_value(a, i, c, y);
+          if (a.points) {
+            for (uint32_t j = 0; j < a.k; ++j) {
+              const float v = child_value(a, y, fv, noise_value(a, j, c));
+              lo[q] = fminf(lo[q], v); hi[q] = fmaxf(hi[q], v);
+            }
+          } else {
+            // every Hadamard column takes both signs over the k rows (rows j and j + k/2 negate)
+            const float v0 = child_value(a, y, fv, -a.scale), v1 = child_value(a, y, fv, a.scale);
+            lo[q] = fminf(lo[q], fminf(v0, v1)); hi[q] = fmaxf(hi[q], fmaxf(v0, v1));
           }
-        } else {
-          // every Hadamard column takes both signs over the k rows (rows j and j + k/2 negate)
-          const float v0 = child_value(a, y, fv, -a.scale), v1 = child_value(a, y, fv, a.scale);
-          lo[q] = fminf(lo[q], fminf(v0, v1)); hi[q] = fmaxf(hi[q], fmaxf(v0, v1));
         }
       }
     }
@@ -224,7 +242,8 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 6));
   cudaStream_t st = (cudaStream_t)stream;
   phase_mark("box_child_bounds", st);
-  box_bounds_children_kernel<<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
+  if (!a.points && box_dims_vec4(s, a)) box_bounds_children_kernel<true><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
+  else box_bounds_children_kernel<false><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
   box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);
   phase_mark("end", st);
   count_launches(2);
