@@ -187,13 +187,39 @@ MCCB200_API int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int l
  * children by box key (stable in child id) without storing keys or ids, then selection of
  * local positions idx_local[0..out_per_part) in every partition of in_per_part children,
  * then the fused Euler update of the selected children.  Result == expand_all ->
- * box_keys -> sort_pairs -> expand_select(perm) bit for bit.  n_dims*bits <= 12. */
+ * box_keys -> sort_pairs -> expand_select(perm) bit for bit.  n_dims*bits <= 12.
+ * Replaces PartitioningRecombinationKernel.__call__ (mccube/_kernels/base.py:152-177) applied to
+ * the expansion of MCCSolver.step (mccube/_solvers.py:132-144). */
 MCCB200_API size_t mccb200_box_prk_step_workspace_bytes(uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part);
 MCCB200_API int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                          const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
                          const float* bounds, const uint32_t* idx_local, uint64_t out_per_part,
                          uint64_t in_per_part, float* y1, void* workspace, size_t workspace_bytes,
                          void* stream);
+
+/* The same step as four calls, so that a caller can (a) keep the class tables, which depend on
+ * (k, dims, bits) only, across steps and (b) draw idx_local and build its selection tables on a
+ * second stream while the counting pass runs:
+ *     tables    (once)          -> `tables`  (mccb200_box_prk_tables_bytes)
+ *     selection (idx_local)     -> `sel`     (mccb200_box_prk_selection_bytes)
+ *     count     (y0, bounds, tables)         -> workspace (same size as for box_prk_step)
+ *     rank_gather (tables, sel, workspace of count) -> y1
+ * box_prk_step == tables; selection; count; rank_gather on one stream. */
+MCCB200_API size_t mccb200_box_prk_tables_bytes(int k, int n_dims, int bits);
+MCCB200_API int mccb200_box_prk_tables(int k, const int32_t* dims_host, int n_dims, int bits, void* tables,
+                                       size_t tables_bytes, void* stream);
+MCCB200_API size_t mccb200_box_prk_selection_bytes(uint64_t in_per_part, uint64_t out_per_part);
+MCCB200_API int mccb200_box_prk_selection(const uint32_t* idx_local, uint64_t out_per_part, uint64_t in_per_part,
+                                          void* sel, size_t sel_bytes, void* stream);
+MCCB200_API int mccb200_box_prk_count(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                      const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                                      const float* bounds, uint64_t in_per_part, const void* tables, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+MCCB200_API int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                            const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                                            uint64_t out_per_part, uint64_t in_per_part, const void* tables,
+                                            const void* sel, float* y1, void* workspace, size_t workspace_bytes,
+                                            void* stream);
 
 /* ------------------------------------------------------------------ A11: moments
  * One pass each: sums[d] (+ weight sum) and centred second moments [d, d] in fp64:

@@ -89,6 +89,18 @@ _SIGNATURES = {
                                        C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_void_p]),
+    "mccb200_box_prk_tables_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mccb200_box_prk_tables": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]),
+    "mccb200_box_prk_selection_bytes": (C.c_size_t, [C.c_uint64, C.c_uint64]),
+    "mccb200_box_prk_selection": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_box_prk_count": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                        C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_box_prk_rank_gather": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                              C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_uint64,
+                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_void_p]),
     "mccb200_moments_sum": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "mccb200_moments_m2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
@@ -368,6 +380,67 @@ def box_prk_step(y0, d, drift, dt, cub, dims, bits, bounds, idx_local, in_per_pa
                                     _dims_array(dims), len(dims), bits, bounds.data_ptr(), idx_local.data_ptr(),
                                     idx_local.numel(), in_per_part, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                     _stream()), "box_prk_step")
+    return out
+
+
+_prk_tables_cache: dict = {}
+
+
+def box_prk_tables(k, dims, bits, device):
+    """Class tables of the fused Box step: a function of (k, dims, bits) only, built once per
+    device and kept (the cubature and the partitioner do not change during a solve)."""
+    lib = load()
+    key = (torch.device(device).index or 0, int(k), tuple(dims), int(bits))
+    hit = _prk_tables_cache.get(key)
+    if hit is not None:
+        return hit
+    nbytes = lib.mccb200_box_prk_tables_bytes(int(k), len(dims), int(bits))
+    if nbytes == 0:
+        raise MccubeB200Error(f"box_prk_tables: unsupported shape k={k} dims={dims} bits={bits}")
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _check(lib.mccb200_box_prk_tables(int(k), _dims_array(dims), len(dims), int(bits), buf.data_ptr(), nbytes,
+                                      _stream()), "box_prk_tables")
+    _prk_tables_cache[key] = buf
+    return buf
+
+
+def box_prk_selection(idx_local, in_per_part):
+    """Prefix-count tables of the shared local index vector (runs on the current stream)."""
+    lib = load()
+    _require_cuda(idx_local)
+    nbytes = lib.mccb200_box_prk_selection_bytes(int(in_per_part), idx_local.numel())
+    if nbytes == 0:
+        raise MccubeB200Error("box_prk_selection: partition sizes out of range")
+    sel = torch.empty(nbytes, dtype=torch.uint8, device=idx_local.device)
+    _check(lib.mccb200_box_prk_selection(idx_local.data_ptr(), idx_local.numel(), int(in_per_part), sel.data_ptr(),
+                                         nbytes, _stream()), "box_prk_selection")
+    return sel
+
+
+def box_prk_count(y0, d, drift, dt, cub, dims, bits, bounds, in_per_part, tables):
+    """Counting pass + scan; returns the workspace that box_prk_rank_gather consumes."""
+    lib = load()
+    _require_cuda(y0, bounds, tables)
+    _f32c(y0)
+    n = y0.shape[0]
+    nbytes = lib.mccb200_box_prk_step_workspace_bytes(n, cub.k, len(dims), bits, in_per_part)
+    ws = workspace(nbytes, y0.device)
+    _check(lib.mccb200_box_prk_count(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                     _dims_array(dims), len(dims), bits, bounds.data_ptr(), in_per_part,
+                                     tables.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "box_prk_count")
+    return ws
+
+
+def box_prk_rank_gather(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_part, tables, sel, ws, out=None):
+    lib = load()
+    _require_cuda(y0, tables, sel, ws)
+    n = y0.shape[0]
+    n_out = n * cub.k // in_per_part * out_per_part
+    out = torch.empty((n_out, y0.shape[1]), dtype=torch.float32, device=y0.device) if out is None else out
+    _check(lib.mccb200_box_prk_rank_gather(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                           _dims_array(dims), len(dims), bits, out_per_part, in_per_part,
+                                           tables.data_ptr(), sel.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), _stream()), "box_prk_rank_gather")
     return out
 
 

@@ -188,22 +188,32 @@ class MCCSolver(AbstractWrappedSolver):
         in_per_part = total // m
         out_per_part = mc.recombination_count
         dims = part.resolve_dims(d)
-        # the shared local index vector depends only on (key, t0): draw it on a side stream while the
-        # bounds / counting passes run
+        use_kernel = (getattr(self, "use_box_prk_kernel", True)
+                      and _lib.box_prk_supported(n, d, cub, dims, part.bits, in_per_part))
+        # The shared local index vector depends only on (key, t0): it is drawn, and its selection
+        # tables are built, on a side stream while the bounds / counting passes run on the main one.
         main = torch.cuda.current_stream()
         side = _side_stream(y0c.device)
-        side.wait_stream(main)
+        tables = _lib.box_prk_tables(k, dims, part.bits, y0c.device) if use_kernel else None
+        # (no side.wait_stream(main): the draw reads nothing the main stream produces, so it may
+        # also overlap the previous step's gather)
         with torch.cuda.stream(side):
             idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
+            sel = _lib.box_prk_selection(idx_local, in_per_part) if use_kernel else None
         bounds = part.fixed_bounds(dims, y0c.device)
         if bounds is None:
             bounds = _lib.box_child_bounds(y0c, d, drift, dt, cub, dims, part.bits)
-        main.wait_stream(side)
-        idx_local.record_stream(main)
-        if getattr(self, "use_box_prk_kernel", True) and _lib.box_prk_supported(n, d, cub, dims, part.bits, in_per_part):
-            out = _lib.box_prk_step(y0c, d, drift, dt, cub, dims, part.bits, bounds, idx_local, in_per_part)
+        if use_kernel:
+            ws = _lib.box_prk_count(y0c, d, drift, dt, cub, dims, part.bits, bounds, in_per_part, tables)
+            main.wait_stream(side)
+            idx_local.record_stream(main)
+            sel.record_stream(main)
+            out = _lib.box_prk_rank_gather(y0c, d, drift, dt, cub, dims, part.bits, out_per_part, in_per_part,
+                                           tables, sel, ws)
             self.last_path = "fused:box_prk_step"
             return out
+        main.wait_stream(side)
+        idx_local.record_stream(main)
         keys = _lib.box_child_keys(y0c, d, drift, dt, cub, dims, part.bits, bounds)
         perm = _lib.sort_pairs(keys, None, len(dims) * part.bits)
         out = _lib.expand_select(y0c, d, False, drift, dt, cub, idx_local, perm=perm, out_per_part=out_per_part,
