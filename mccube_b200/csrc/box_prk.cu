@@ -68,8 +68,9 @@ struct BoxPrkParams {
   const uint32_t* cls_packed;  // [n_sets][cls_pad]   fm | (size-1) << 12 | off << 22, or BP_INVALID
   const uint16_t* members;     // [n_sets][k]         points j sorted by (class, j)
   // selection tables
-  const uint32_t* pre;         // [in_per_part + 1]  #selected entries with position < pos
-  const uint2* sp;             // [out_per_part]     (position, l) sorted by position
+  const uint32_t* pre;         // [in_per_part + sel_ext + 1]  #selected entries with position < pos (extended)
+  const uint2* sp;             // [2 * out_per_part]  (position, l) sorted by position (extended)
+  uint32_t sel_ext;
   uint32_t* pdesc;             // [n] per-parent K0 | D << 12 | S << 24 (written by pass A)
   uint32_t* table;             // [n_segments + 1][n_keys]
   const uint32_t* key_start;   // [n_keys] children with a smaller key (rows stay relative to it)
@@ -161,11 +162,14 @@ __global__ void box_tables_kernel(const TableSpec p, uint32_t* cls_count, uint32
     cls_packed[(size_t)S * cls_pad + c] = c < count ? (fm[c] | ((size[c] - 1u) << 12) | (off[c] << 22)) : BP_INVALID;
 }
 
-// pre[pos] = #l with idx_local[l] < pos (pos in [0, in_per_part]); sp = (pos, l) sorted by pos.
+// pre[pos] = #l with idx_local[l] < pos for pos in [0, in_per_part]; sp = (pos, l) sorted by pos.
+// Both are EXTENDED by one wrap so that a class run crossing a partition boundary needs no special
+// case: pre[in_per_part + x] = out_per_part + pre[x] for x in (0, ext], and
+// sp[out_per_part + e] = (sp[e].pos + in_per_part, sp[e].l + out_per_part).
 // Single CTA (the selection vector is tiny next to the state).
 __global__ void __launch_bounds__(1024)
 box_selection_kernel(const uint32_t* __restrict__ idx_local, uint32_t out_per_part, uint32_t in_per_part,
-                     uint32_t* __restrict__ pre, uint32_t* __restrict__ fill, uint2* __restrict__ sp) {
+                     uint32_t ext, uint32_t* __restrict__ pre, uint32_t* __restrict__ fill, uint2* __restrict__ sp) {
   __shared__ uint32_t wtot[32];
   __shared__ uint32_t carry_s;
   const uint32_t len = in_per_part + 1;
@@ -185,12 +189,12 @@ box_selection_kernel(const uint32_t* __restrict__ idx_local, uint32_t out_per_pa
     if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = x;
     __syncthreads();
     if (threadIdx.x < 32) {
-      uint32_t t = wtot[threadIdx.x], s = t;
+      uint32_t t = wtot[threadIdx.x], sc = t;
       for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-        if (threadIdx.x >= o) s += y;
+        uint32_t y = __shfl_up_sync(0xffffffffu, sc, o);
+        if (threadIdx.x >= o) sc += y;
       }
-      wtot[threadIdx.x] = s - t;
+      wtot[threadIdx.x] = sc - t;
     }
     __syncthreads();
     const uint32_t carry = carry_s;
@@ -204,7 +208,9 @@ box_selection_kernel(const uint32_t* __restrict__ idx_local, uint32_t out_per_pa
     const uint32_t pos = idx_local[l];
     const uint32_t slot = pre[pos] + atomicAdd(&fill[pos], 1u);  // duplicates: any order (same child)
     sp[slot] = make_uint2(pos, l);
+    sp[out_per_part + slot] = make_uint2(pos + in_per_part, l + out_per_part);
   }
+  for (uint32_t x = 1 + threadIdx.x; x <= ext; x += 1024) pre[in_per_part + x] = out_per_part + pre[x];
 }
 
 // ------------------------------------------------------------------ scan
@@ -377,10 +383,12 @@ __device__ __forceinline__ FlatRecord flat_record(const FlatBatch& b, uint32_t r
   const uint32_t r = r0 + (uint32_t)lane;
   rec.valid = r < b.R;
   const uint32_t rel = b.excl - r0;                     // wraps (>= 32) when the parent starts earlier
-  const uint32_t starts = __reduce_or_sync(0xffffffffu, (b.ncls && rel < 32u) ? (1u << rel) : 0u);
-  const uint32_t before = (uint32_t)__popc(__ballot_sync(0xffffffffu, b.ncls && b.excl < r0));
+  // (parents without records are the lanes past the end of the segment; their excl == R marks a
+  // bit above every valid record of the last round and is never < r0, so they need no guard)
+  const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+  const uint32_t before = (uint32_t)__popc(__ballot_sync(0xffffffffu, b.excl < r0));
   const uint32_t le_mask = 0xffffffffu >> (31 - lane);
-  rec.owner = rec.valid ? (int)(before + (uint32_t)__popc(starts & le_mask)) - 1 : 0;
+  rec.owner = (int)(before + (uint32_t)__popc(starts & le_mask)) - 1;   // shuffles take it mod 32
   const uint32_t od = __shfl_sync(0xffffffffu, b.desc, rec.owner);
   const uint32_t opk = __shfl_sync(0xffffffffu, b.pk, rec.owner);
   rec.S = od >> 24;
@@ -506,11 +514,11 @@ box_rank_flat_kernel(const BoxPrkParams p) {
   if (PRE_SMEM) {
     cursor += ((cursor - smem) & 1u);                    // 8-byte alignment for sp
     uint2* s_sp = reinterpret_cast<uint2*>(cursor);
-    cursor += 2u * p.out_per_part;
+    cursor += 4u * p.out_per_part;
     s_pre16 = reinterpret_cast<uint16_t*>(cursor);
-    cursor += ((p.in_per_part + 4u) & ~3u) / 2u;
-    for (uint32_t i = threadIdx.x; i <= p.in_per_part; i += blockDim.x) s_pre16[i] = (uint16_t)p.pre[i];
-    for (uint32_t i = threadIdx.x; i < p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
+    cursor += ((p.in_per_part + p.sel_ext + 4u) & ~3u) / 2u;
+    for (uint32_t i = threadIdx.x; i <= p.in_per_part + p.sel_ext; i += blockDim.x) s_pre16[i] = (uint16_t)p.pre[i];
+    for (uint32_t i = threadIdx.x; i < 2u * p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
     sp = s_sp;
   }
   auto PRE = [&](uint32_t i) -> uint32_t { return PRE_SMEM ? (uint32_t)s_pre16[i] : __ldg(p.pre + i); };
@@ -541,15 +549,11 @@ box_rank_flat_kernel(const BoxPrkParams p) {
       uint32_t part0, pos0;
       if (p.in_shift != 0xFFFFFFFFu) { part0 = rank0 >> p.in_shift; pos0 = rank0 & (Pm - 1u); }
       else { part0 = rank0 / Pm; pos0 = rank0 - part0 * Pm; }
-      const uint16_t* mem = members + (e4.z >> 11);
+      const uint16_t* mem = members + (e4.z >> 11) - pos0;
       uint32_t* out0 = p.idx_out + (uint64_t)part0 * nm;
-      for (uint32_t hh = 0; hh < n_hit; ++hh) {
-        uint32_t e = first + hh;
-        const bool wrap = e >= nm;
-        if (wrap) e -= nm;
-        const uint2 pl = sp[e];                          // (position, output slot l)
-        const uint32_t tt = wrap ? pl.x + Pm - pos0 : pl.x - pos0;
-        out0[(wrap ? nm : 0u) + pl.y] = e4.w + mem[tt];
+      for (uint32_t e = first; e < first + n_hit; ++e) {
+        const uint2 pl = sp[e];                          // (position, output slot l), extended past one wrap
+        out0[pl.y] = e4.w + mem[pl.x];
       }
     }
     q_head = (q_head + cnt) & (FQ_CAP - 1);
@@ -567,7 +571,7 @@ box_rank_flat_kernel(const BoxPrkParams p) {
     o.st = 0;
     if (rec.valid && lane == o.leader) o.st = atomicAdd(row + rec.key, totu << ushift);
     o.valid = rec.valid; o.key = rec.key; o.exu = exu; o.e = rec.e;
-    o.child0 = (uint32_t)(base + (uint64_t)rec.owner) * a.k;   // child ids are uint32 (n * k <= 2^32)
+    o.child0 = ((uint32_t)base + (uint32_t)(rec.owner & 31)) << logk;   // child ids are uint32 (n * k <= 2^32)
     o.moff = (rec.S << logk) + (rec.ent >> 22);
   };
   // back half: rank, selection test, queue the hit records
@@ -577,9 +581,8 @@ box_rank_flat_kernel(const BoxPrkParams p) {
     if (o.valid) {
       rank0 = st + __ldg(p.key_start + o.key) + (o.exu << ushift);
       const uint32_t pos0 = p.in_shift != 0xFFFFFFFFu ? (rank0 & (Pm - 1u)) : (rank0 % Pm);
-      const uint32_t end = pos0 + ((1u << o.e) << ushift);   // size <= k <= Pm: wraps at most once
       first = PRE(pos0);
-      n_hit = end <= Pm ? PRE(end) - first : (nm - first) + PRE(end - Pm);
+      n_hit = PRE(pos0 + ((1u << o.e) << ushift)) - first;   // size <= k <= Pm: the extended table covers the wrap
     }
     const uint32_t hm = __ballot_sync(0xffffffffu, n_hit != 0u);
     if (hm) {
@@ -642,15 +645,17 @@ static bool make_tables_layout(TablesLayout& L, int k, int n_dims, int bits) {
   return true;
 }
 
-struct SelLayout { size_t off_pre, off_fill, off_sp, total; };
+// pre is extended by min(in_per_part, BP_MAX_K) positions (a class run holds at most k <= in_per_part children)
+struct SelLayout { size_t off_pre, off_fill, off_sp, total; uint32_t ext; };
 
 static bool make_sel_layout(SelLayout& L, uint64_t in_per_part, uint64_t out_per_part) {
-  if (in_per_part >= 0x80000000ull || out_per_part >= 0x80000000ull || in_per_part < 1 || out_per_part < 1) return false;
+  if (in_per_part >= 0x40000000ull || out_per_part >= 0x40000000ull || in_per_part < 1 || out_per_part < 1) return false;
+  L.ext = (uint32_t)(in_per_part < (uint64_t)BP_MAX_K ? in_per_part : (uint64_t)BP_MAX_K);
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t o = cur; cur += align_up(bytes, 256); return o; };
-  L.off_pre = take(((size_t)in_per_part + 2) * 4);
+  L.off_pre = take(((size_t)in_per_part + L.ext + 2) * 4);
   L.off_fill = take(((size_t)in_per_part + 2) * 4);
-  L.off_sp = take((size_t)out_per_part * 8);
+  L.off_sp = take((size_t)out_per_part * 2 * 8);
   L.total = cur;
   return true;
 }
@@ -658,7 +663,7 @@ static bool make_sel_layout(SelLayout& L, uint64_t in_per_part, uint64_t out_per
 struct PrkPlan {
   TablesLayout tl;
   uint32_t n_keys, n_segments;
-  int warps_per_cta, grid_b, pre_in_smem, mem_in_smem;
+  int warps_per_cta, ctas_per_sm, grid_b, pre_in_smem, mem_in_smem;
   uint64_t parents_per_seg;
   size_t smem_a, smem_b;
   size_t off_pdesc, off_table, off_idx, off_tables, off_sel, total;
@@ -669,8 +674,8 @@ struct PrkPlan {
 static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
                           uint64_t out_per_part_max) {
   if (!make_tables_layout(pl.tl, k, n_dims, bits)) return false;
-  if (in_per_part >= 0x80000000ull || in_per_part < (uint64_t)k) return false;  // a class run wraps at most once
-  if (out_per_part_max >= 0x80000000ull || out_per_part_max < 1) return false;
+  if (in_per_part >= 0x40000000ull || in_per_part < (uint64_t)k) return false;  // a class run wraps at most once
+  if (out_per_part_max >= 0x40000000ull || out_per_part_max < 1) return false;
   const uint64_t total_children = n * (uint64_t)k;
   if (total_children > 0x100000000ull) return false;
   const TableSpec& t = pl.tl.t;
@@ -678,11 +683,14 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   const size_t row = (size_t)pl.n_keys * 4;
   const size_t tab_bytes = (size_t)t.n_sets * (1u << t.cls_pad_log2) * 4 + (size_t)t.n_sets * 4 + 8;
   const size_t mem_bytes = (size_t)t.n_sets * k * 2 + 8;
-  const size_t pre_bytes = ((size_t)((in_per_part + 4) & ~3ull)) * 2 + (size_t)out_per_part_max * 8;
-  pl.pre_in_smem = (pre_bytes <= 24 * 1024 && out_per_part_max < 65536) ? 1 : 0;
+  const size_t pre_bytes = ((size_t)((in_per_part + BP_MAX_K + 4) & ~3ull)) * 2 + (size_t)out_per_part_max * 16;
+  pl.pre_in_smem = (pre_bytes <= 28 * 1024 && out_per_part_max < 32768) ? 1 : 0;   // 2 * out_per_part fits uint16
   pl.mem_in_smem = mem_bytes <= 16 * 1024 ? 1 : 0;
   pl.warps_per_cta = 8;
-  uint64_t segs = (uint64_t)sm_count() * 32;            // 4 CTAs of 8 warps per SM, one warp per segment
+  // 4 resident pass-B CTAs per SM.  Measured: 5 / 6 CTAs (48 / 40 registers) leave pass B at 0.75 / 0.83 ms
+  // (it is issue-bound, not latency-bound) and push the counter table past L2 (scan 0.09 -> 0.20 / 0.28 ms).
+  pl.ctas_per_sm = 4;
+  uint64_t segs = (uint64_t)sm_count() * pl.warps_per_cta * pl.ctas_per_sm;   // one warp per segment
   if (segs > n) segs = n ? n : 1;
   pl.parents_per_seg = (n + segs - 1) / segs;
   pl.n_segments = (uint32_t)((n + pl.parents_per_seg - 1) / pl.parents_per_seg);
@@ -728,7 +736,7 @@ static int launch_tables(const TablesLayout& L, const int32_t* dims_host, int n_
 static int launch_selection(const SelLayout& L, const uint32_t* idx_local, uint64_t out_per_part, uint64_t in_per_part,
                             void* sel, cudaStream_t st) {
   char* w = (char*)sel;
-  box_selection_kernel<<<1, 1024, 0, st>>>(idx_local, (uint32_t)out_per_part, (uint32_t)in_per_part,
+  box_selection_kernel<<<1, 1024, 0, st>>>(idx_local, (uint32_t)out_per_part, (uint32_t)in_per_part, L.ext,
                                            (uint32_t*)(w + L.off_pre), (uint32_t*)(w + L.off_fill), (uint2*)(w + L.off_sp));
   count_launches(1);
   return MCCB200_OK;
@@ -886,6 +894,7 @@ extern "C" int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, c
   bind_tables(p, pl.tl, tables);
   p.pre = (const uint32_t*)((const char*)sel + sl.off_pre);
   p.sp = (const uint2*)((const char*)sel + sl.off_sp);
+  p.sel_ext = sl.ext;
   return launch_rank_gather(p, pl, y1, (cudaStream_t)stream);
 }
 
@@ -913,6 +922,7 @@ extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mc
   bind_tables(p, pl.tl, w + pl.off_tables);
   p.pre = (const uint32_t*)(w + pl.off_sel + sl.off_pre);
   p.sp = (const uint2*)(w + pl.off_sel + sl.off_sp);
+  p.sel_ext = sl.ext;
   rc = launch_count(p, pl, st);
   if (rc) return rc;
   return launch_rank_gather(p, pl, y1, st);
