@@ -237,6 +237,16 @@ MCCB200_API int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, co
 MCCB200_API int mccb200_gaussian_full_drift(const float* y, uint64_t n, int d, int ld, const float* mean,
                                 const float* prec /*[d, d] row-major*/, float* f, void* stream);
 
+/* The same drift on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM) with
+ * the 3xTF32 operand split, |error| ~ 1e-6 relative (csrc/gemm_drift.cu).  prepare splits prec
+ * once into prec_split [2][d][d] (mccb200_gaussian_full_drift_tc_prepare_bytes).  Shapes:
+ * d % 32 == 0, 32 <= d <= 1024, ld % 4 == 0, 16-byte aligned pointers; f is [n, d] contiguous. */
+MCCB200_API int mccb200_gaussian_full_drift_tc_supported(uint64_t n, int d, int ld);
+MCCB200_API size_t mccb200_gaussian_full_drift_tc_prepare_bytes(int d);
+MCCB200_API int mccb200_gaussian_full_drift_tc_prepare(const float* prec, int d, float* prec_split, void* stream);
+MCCB200_API int mccb200_gaussian_full_drift_tc(const float* y, uint64_t n, int d, int ld, const float* mean,
+                                   const float* prec_split, float* f, void* stream);
+
 /* ------------------------------------------------------------------ sharded global resample
  * Multi-GPU form of MonteCarloKernel (the reference is single-device).  Every rank
  * holds n_loc consecutive parents and the SAME global index vector idx[n_tot] (a pure function

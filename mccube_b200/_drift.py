@@ -30,13 +30,26 @@ class GaussianDiagDrift:
 
 class GaussianFullDrift:
     """grad log N(y; mean, cov) = -(y - mean) @ cov^-1 for a full covariance (config 4).
-    Evaluated by the library's GEMM kernel into an [n, d] array (drift kind 1)."""
+    Evaluated into an [n, d] array (drift kind 1): on the tensor cores (tcgen05 kind::tf32 with
+    the 3xTF32 split, csrc/gemm_drift.cu) when d % 32 == 0, otherwise by the fp32 SIMT tiles.
+    `tensor_cores=False` forces the SIMT kernel."""
 
-    def __init__(self, mean, cov, device="cuda"):
+    def __init__(self, mean, cov, device="cuda", tensor_cores: bool = True):
         cov = np.asarray(cov, dtype=np.float64)
         self.mean = torch.tensor(np.asarray(mean), dtype=torch.float32, device=device)
         self.prec = torch.tensor(np.linalg.inv(cov).astype(np.float32), dtype=torch.float32, device=device)
+        self.tensor_cores = tensor_cores
+        self._prec_split = None
+        self.last_path = None
 
     def __call__(self, t, y, args=None):
         d = self.mean.numel()
-        return _lib.gaussian_full_drift(y.contiguous(), d, self.mean, self.prec)
+        y = y.contiguous()
+        if self.tensor_cores and _lib.gaussian_full_drift_tc_supported(y.shape[0], d, y.shape[1]) \
+                and y.data_ptr() % 16 == 0:
+            if self._prec_split is None:
+                self._prec_split = _lib.gaussian_full_drift_tc_prepare(self.prec)
+            self.last_path = "tcgen05:3xtf32"
+            return _lib.gaussian_full_drift_tc(y, d, self.mean, self._prec_split)
+        self.last_path = "simt:fp32"
+        return _lib.gaussian_full_drift(y, d, self.mean, self.prec)

@@ -113,6 +113,11 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "mccb200_gaussian_full_drift": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
+    "mccb200_gaussian_full_drift_tc_supported": (C.c_int, [C.c_uint64, C.c_int, C.c_int]),
+    "mccb200_gaussian_full_drift_tc_prepare_bytes": (C.c_size_t, [C.c_int]),
+    "mccb200_gaussian_full_drift_tc_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mccb200_gaussian_full_drift_tc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -498,6 +503,32 @@ def gaussian_full_drift(y, d, mean, prec):
     f = torch.empty((y.shape[0], d), dtype=torch.float32, device=y.device)
     _check(lib.mccb200_gaussian_full_drift(y.data_ptr(), y.shape[0], d, y.shape[1], mean.data_ptr(), prec.data_ptr(),
                                            f.data_ptr(), _stream()), "gaussian_full_drift")
+    return f
+
+
+def gaussian_full_drift_tc_supported(n, d, ld) -> bool:
+    return bool(load().mccb200_gaussian_full_drift_tc_supported(int(n), int(d), int(ld)))
+
+
+def gaussian_full_drift_tc_prepare(prec):
+    """3xTF32 split of the precision matrix, [2, d, d] (hi / lo of prec^T); done once per target."""
+    lib = load()
+    _require_cuda(prec)
+    d = prec.shape[0]
+    split = torch.empty((2, d, d), dtype=torch.float32, device=prec.device)
+    _check(lib.mccb200_gaussian_full_drift_tc_prepare(prec.contiguous().data_ptr(), d, split.data_ptr(), _stream()),
+           "gaussian_full_drift_tc_prepare")
+    return split
+
+
+def gaussian_full_drift_tc(y, d, mean, prec_split):
+    """-(y - mean) @ prec on the tensor cores (tcgen05, 3xTF32, fp32 accumulation)."""
+    lib = load()
+    _require_cuda(y, mean, prec_split)
+    _f32c(y)
+    f = torch.empty((y.shape[0], d), dtype=torch.float32, device=y.device)
+    _check(lib.mccb200_gaussian_full_drift_tc(y.data_ptr(), y.shape[0], d, y.shape[1], mean.data_ptr(),
+                                              prec_split.data_ptr(), f.data_ptr(), _stream()), "gaussian_full_drift_tc")
     return f
 
 

@@ -1,0 +1,408 @@
+// Full-covariance Gaussian drift on the 5th-generation tensor cores (sm_100a):
+//     F = -(Y - mean) @ prec            Y [n, d] fp32, prec = cov^-1 [d, d] fp32
+// the drift of BASELINE config 4 (n = 2^20, d = 512).  In the reference this is
+// vmap(grad(multivariate_normal.logpdf)) evaluated on the parents (README.md:72-76 via
+// mccube/_term.py:58-63): two batched triangular solves, i.e. a dense n x d x d contraction.
+//
+// Precision recipe: "3xTF32" -- both operands are split into a TF32-representable high part and
+// the fp32 remainder, and three tcgen05.mma.kind::tf32 products are accumulated in fp32 in TMEM:
+//     A B  ~=  A_hi B_hi + A_lo B_hi + A_hi B_lo          (A_lo B_lo ~ 2^-22 |A||B| is dropped)
+// which keeps the result within ~1e-6 of the fp32/fp64 value (one-pass TF32 would be ~1e-3; the
+// parity bar is 1e-5).  prec is split once (mccb200_gaussian_full_drift_tc_prepare), the
+// particle tile is centred and split in shared memory by converter warps.
+//
+// Kernel anatomy (persistent, one CTA per SM, 10 warps, warp-specialised).  A CTA tile is
+// 256 particles (two M = 128 accumulators sharing every prec tile: the prec traffic from L2 per
+// flop is half that of an M = 128 tile) x NT <= 256 output columns; the k-step is 16 fp32 (one
+// 64-byte swizzle row), 64 KB per stage, 3 stages:
+//   warp 0      TMA producer : Y tile [256 x 16] + prec_hi / prec_lo tiles [NT x 16] per k-step,
+//                              64-byte swizzle, mbarrier complete_tx
+//   warps 2-5   converter    : a = y - mean; hi = rn_tf32(a); lo = rn_tf32(a - hi), written back
+//                              to the (swizzled) stage buffers; fence.proxy.async; arrive
+//   warp 1      MMA issuer   : one thread issues 12 tcgen05.mma (M128 x N256 x K8, a_negate) per
+//                              k-step into the two TMEM accumulators, tcgen05.commit frees the stage
+//   warps 6-9   epilogue     : tcgen05.ld 32x32b.x32 -> 128-byte row segments of F; TMA / converter
+//                              keep filling stages meanwhile, and the second accumulator drains
+//                              while the next tile's first MMAs run on the first
+// Roofline: 3 * 2 n d^2 flop on the TF32 pipe (128 cycles per M128 N256 K8 instruction, 1536 per
+// k-step) against 48 KB per k-step through L2 (~31 B/cycle/SM, under the ~42 B/cycle/SM L2 cap).
+// First version of this kernel (M = 128 tile, 32-float k-step, 2 stages of 96 KB) measured 3.29 ms
+// at n = 2^20, d = 512: bound by its 53 B/cycle/SM of L2 traffic and the 2-deep ring.
+// Accuracy: the tensor core truncates (round-toward-zero) at every accumulation, a bias of
+// ~2^-24 per K = 8 instruction: measured max error 7.6e-6 (d = 512) / 1.3e-5 (d = 1024) of max|F|.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mccb {
+
+constexpr int TC_BM = 128;            // rows per accumulator (UMMA M)
+constexpr int TC_RB = 2;              // accumulators (row blocks) per CTA tile
+constexpr int TC_BK = 16;             // fp32 per k-step = one 64-byte swizzle row
+constexpr int TC_UK = 8;              // K of one tcgen05.mma.kind::tf32
+constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_NT = 256;        // UMMA N
+constexpr int TC_MAX_D = 1024;
+constexpr int TC_THREADS = 320;
+constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 64
+constexpr uint32_t TC_A_BYTES = TC_RB * TC_BM * TC_ROW_BYTES;          // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_MAX_NT * TC_ROW_BYTES;              // 16 KB
+constexpr uint32_t TC_OFF_AHI = 0, TC_OFF_ALO = TC_A_BYTES, TC_OFF_BHI = 2 * TC_A_BYTES,
+                   TC_OFF_BLO = 2 * TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4 + 256 + 1024;  // + mean, barriers, align
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spins on the phase parity; traps instead of hanging the GPU if a phase is never completed.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (spin & 1023u) == 1023u) {                 // ~2 s at 2 GHz: a protocol bug, not a slow tile
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile stored as rows of 64 bytes with the 64-byte swizzle (what TMA
+// SWIZZLE_64B writes: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)): 8-row groups are
+// 512 bytes apart (SBO), descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B.  Advancing
+// along K inside the swizzle row = adding the byte offset to the start address.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(8 * TC_ROW_BYTES >> 4) << 32;  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// round-to-nearest TF32 (10 explicit mantissa bits) of an fp32 value, as fp32 bits
+__device__ __forceinline__ float rn_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+struct TcDriftParams {
+  uint64_t n;
+  int d, nt, n_tiles, k_tiles;
+  uint32_t n_m_tiles;
+  const float* mean;
+  float* f;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_bhi,
+                              const __grid_constant__ CUtensorMap map_blo, const TcDriftParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // swizzled tiles want (at least) 512-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_mean = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4);
+  // barrier ring: full[s] (TMA landed), conv[s] (converter done), empty[s] (MMA consumed),
+  //               tmem_full (both accumulators ready), tmem_empty[r] (accumulator r drained)
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + TC_STAGES), bar_empty = smem_u32(bars + 2 * TC_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1 + TC_RB);
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.d; i += TC_THREADS) s_mean[i] = p.mean[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    for (int r = 0; r < TC_RB; ++r) mbar_init(bar_tempty + 8 * r, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: TC_RB accumulators of up to 256 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const uint32_t stage_tx = TC_A_BYTES + 2u * (uint32_t)p.nt * TC_ROW_BYTES;
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          for (int kt = 0; kt < p.k_tiles; ++kt) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
+            mbar_expect_tx(bar_full + 8 * stage, stage_tx);
+            tma_load_2d(sb + TC_OFF_AHI, &map_y, bar_full + 8 * stage, kt * TC_BK, (int)(mt * (TC_RB * TC_BM)));
+            tma_load_2d(sb + TC_OFF_BHI, &map_bhi, bar_full + 8 * stage, kt * TC_BK, nt * p.nt);
+            tma_load_2d(sb + TC_OFF_BLO, &map_blo, bar_full + 8 * stage, kt * TC_BK, nt * p.nt);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, A negated, N = nt, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((uint32_t)(p.nt >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          for (int kt = 0; kt < p.k_tiles; ++kt) {
+            mbar_wait(bar_full + 8 * stage, phase);          // the prec tiles (TMA) ...
+            mbar_wait(bar_conv + 8 * stage, phase);          // ... and the split particle tile (converter warps)
+            tc_fence_after();
+            const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
+            const uint64_t b_hi = tc_smem_desc(sb + TC_OFF_BHI), b_lo = tc_smem_desc(sb + TC_OFF_BLO);
+#pragma unroll
+            for (int r = 0; r < TC_RB; ++r) {
+              if (kt == 0) {                                  // accumulator r drained by the epilogue?
+                mbar_wait(bar_tempty + 8 * r, tphase ^ 1u);
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + (uint32_t)r * (uint32_t)p.nt;
+              const uint64_t a_hi = tc_smem_desc(sb + TC_OFF_AHI + r * TC_BM * TC_ROW_BYTES);
+              const uint64_t a_lo = tc_smem_desc(sb + TC_OFF_ALO + r * TC_BM * TC_ROW_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {   // descriptor start address advances in 16-byte units
+                const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
+                tc_mma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (kt | ks) != 0);
+              }
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
+                const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
+                tc_mma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              }
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
+                const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
+                tc_mma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
+            }
+            tc_commit(bar_empty + 8 * stage);               // stage reusable once these MMAs have read it
+            if (kt == p.k_tiles - 1) tc_commit(bar_tfull);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+          }
+          tphase ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converter: centre and split the particle tile in place (swizzle aware) =====
+    const int tc = threadIdx.x - 64;                       // 0..127
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        for (int kt = 0; kt < p.k_tiles; ++kt) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < (int)(TC_A_BYTES / 16) / 128; ++i) {
+            const int q = tc + 128 * i;                    // physical 16-byte chunk of the tile
+            const int r = q >> 2, pc = q & 3;
+            const int col = kt * TC_BK + ((pc ^ ((r >> 1) & 3)) << 2);   // logical column of the chunk
+            float4 v = *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16);
+            const float4 m = *reinterpret_cast<const float4*>(s_mean + col);
+            float4 hi, lo;
+            v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+            hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
+            lo.x = rn_tf32(v.x - hi.x); lo.y = rn_tf32(v.y - hi.y); lo.z = rn_tf32(v.z - hi.z); lo.w = rn_tf32(v.w - hi.w);
+            *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16) = hi;
+            *reinterpret_cast<float4*>(sa + TC_OFF_ALO + q * 16) = lo;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
+          mbar_arrive(bar_conv + 8 * stage);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> F =====
+    const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31 belong to this warp
+    uint32_t tphase = 0;
+    for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        mbar_wait(bar_tfull, tphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int r = 0; r < TC_RB; ++r) {
+          const uint64_t row = (uint64_t)mt * (TC_RB * TC_BM) + (uint64_t)(r * TC_BM + quad * 32 + lane);
+          for (int c0 = 0; c0 < p.nt; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * (uint32_t)p.nt + (uint32_t)c0, v);
+            if (row < p.n) {
+              float4* dst = reinterpret_cast<float4*>(p.f + row * (uint64_t)p.d + (uint64_t)(nt * p.nt + c0));
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                __stcs(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * r);
+        }
+        tphase ^= 1u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// prec [k][n] -> split[0][n][k] = rn_tf32(prec), split[1][n][k] = rn_tf32(prec - hi)   (B operand, K-major)
+__global__ void __launch_bounds__(256)
+prec_split_kernel(const float* __restrict__ prec, int d, float* __restrict__ split) {
+  const size_t total = (size_t)d * d;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t nn = e / d, kk = e % d;
+    const float v = prec[kk * d + nn];
+    const float hi = rn_tf32(v);
+    split[e] = hi;
+    split[total + e] = rn_tf32(v - hi);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// fp32 matrix [rows][cols] with row pitch ld floats; box = [box_rows][TC_BK floats], 64-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MCCB200_ERR_CUDA, "gaussian_full_drift_tc: cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MCCB200_ERR_CUDA, "gaussian_full_drift_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MCCB200_OK;
+}
+
+static bool tc_shape_ok(uint64_t n, int d, int ld, const void* y) {
+  return d >= 32 && d <= TC_MAX_D && d % 32 == 0 && ld % 4 == 0 && ((uintptr_t)y & 15) == 0 && n >= 1 &&
+         n < 0x7FFFFFFFull;
+}
+
+}  // namespace mccb
+
+using namespace mccb;
+
+extern "C" int mccb200_gaussian_full_drift_tc_supported(uint64_t n, int d, int ld) {
+  return tc_shape_ok(n, d, ld, nullptr) ? 1 : 0;
+}
+
+extern "C" size_t mccb200_gaussian_full_drift_tc_prepare_bytes(int d) { return (size_t)2 * d * d * sizeof(float); }
+
+extern "C" int mccb200_gaussian_full_drift_tc_prepare(const float* prec, int d, float* prec_split, void* stream) {
+  MCCB_REQUIRE(prec && prec_split && d >= 1, "gaussian_full_drift_tc_prepare: bad argument");
+  const size_t total = (size_t)d * d;
+  prec_split_kernel<<<(int)min((total + 255) / 256, (size_t)sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(prec, d, prec_split);
+  count_launches(1);
+  return check_launch("gaussian_full_drift_tc_prepare");
+}
+
+extern "C" int mccb200_gaussian_full_drift_tc(const float* y, uint64_t n, int d, int ld, const float* mean,
+                                              const float* prec_split, float* f, void* stream) {
+  MCCB_REQUIRE(y && mean && prec_split && f, "gaussian_full_drift_tc: NULL argument");
+  if (n == 0) return MCCB200_OK;
+  if (!tc_shape_ok(n, d, ld, y) || ((uintptr_t)f & 15) || ((uintptr_t)prec_split & 15))
+    return fail(MCCB200_ERR_UNSUPPORTED, "gaussian_full_drift_tc: needs d %% 32 == 0, 32 <= d <= %d, 16-byte aligned rows (d=%d ld=%d)",
+                TC_MAX_D, d, ld);
+  TcDriftParams p{};
+  p.n = n; p.d = d;
+  p.nt = d % 256 == 0 ? 256 : d % 128 == 0 ? 128 : d % 64 == 0 ? 64 : 32;
+  p.n_tiles = d / p.nt;
+  p.k_tiles = d / TC_BK;
+  p.n_m_tiles = (uint32_t)((n + TC_RB * TC_BM - 1) / (TC_RB * TC_BM));
+  p.mean = mean; p.f = f;
+  CUtensorMap map_y, map_bhi, map_blo;
+  int rc = make_map(&map_y, y, n, (uint64_t)d, (uint64_t)ld, TC_RB * TC_BM);
+  if (rc) return rc;
+  rc = make_map(&map_bhi, prec_split, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt);
+  if (rc) return rc;
+  rc = make_map(&map_blo, prec_split + (size_t)d * d, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt);
+  if (rc) return rc;
+  cudaFuncSetAttribute(gaussian_full_drift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+  const int grid = (int)min((uint32_t)sm_count(), p.n_m_tiles);
+  phase_mark("gemm_drift_tc", (cudaStream_t)stream);
+  gaussian_full_drift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(map_y, map_bhi, map_blo, p);
+  phase_mark("end", (cudaStream_t)stream);
+  count_launches(1);
+  return check_launch("gaussian_full_drift_tc");
+}

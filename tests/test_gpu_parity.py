@@ -356,6 +356,37 @@ def test_full_covariance_drift(dev):
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("n,d", [(1000, 96), (128, 32), (4096, 128), (777, 512), (2048, 1024)])
+def test_full_covariance_drift_tensor_cores(dev, n, d):
+    """tcgen05 3xTF32 drift (config 4's dense contraction) vs float64, and vs the fp32 SIMT kernel."""
+    rs = np.random.default_rng(d)
+    a = rs.normal(size=(d, d))
+    cov = a @ a.T / d + np.eye(d)
+    mean = rs.normal(size=d) * 2.0
+    y = (rs.normal(size=(n, d)) * 1.5 + mean).astype(np.float32)
+    f = mccube.GaussianFullDrift(mean, cov, device=dev)
+    yt = cuda(y, dev)
+    got = f(0.0, yt).cpu().numpy()
+    assert f.last_path == "tcgen05:3xtf32"
+    prec32 = f.prec.cpu().numpy().astype(np.float64)
+    want = -(y.astype(np.float64) - f.mean.cpu().numpy().astype(np.float64)) @ prec32
+    scale = np.abs(want).max()
+    # tensor-core accumulation truncates: the bias grows with d / 8 accumulation steps (measured
+    # 7.6e-6 at d = 512, 1.3e-5 at d = 1024, relative to max |F|)
+    tol = 1e-5 if d <= 512 else 2e-5
+    assert np.abs(got - want).max() <= tol * scale
+    # the north-star bar is on the particle STATES (y + dt f + noise within 1e-5 relative)
+    dt = 0.05
+    y1_got, y1_want = y + np.float32(dt) * got, y.astype(np.float64) + dt * want
+    assert np.abs(y1_got - y1_want).max() <= 1e-5 * np.abs(y1_want).max()
+    simt = mccube.GaussianFullDrift(mean, cov, device=dev, tensor_cores=False)
+    ref = simt(0.0, yt).cpu().numpy()
+    assert simt.last_path == "simt:fp32"
+    assert np.abs(got - ref).max() <= tol * scale
+    # a second call reuses the split precision matrix and is deterministic
+    assert np.array_equal(got, f(0.0, yt).cpu().numpy())
+
+
 # ------------------------------------------------------------------ fused Box + PRK kernel
 @pytest.mark.parametrize("n,d,dims,bits,m,replace,kind", [
     (96, 6, (0, 2, 5), 2, 32, False, 2),
