@@ -31,6 +31,7 @@
 // Accuracy: the tensor core truncates (round-toward-zero) at every accumulation, a bias of
 // ~2^-24 per K = 8 instruction: measured max error 7.6e-6 (d = 512) / 1.3e-5 (d = 1024) of max|F|.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -38,13 +39,16 @@ namespace mccb {
 
 constexpr int TC_BM = 128;            // rows per accumulator (UMMA M)
 constexpr int TC_RB = 2;              // accumulators (row blocks) per CTA tile
-constexpr int TC_BK = 16;             // fp32 per k-step = one 64-byte swizzle row
+constexpr int TC_BK = 16;             // fp32 per k-step = one swizzle row (8 / 16 / 32 floats <-> 32 / 64 / 128-byte swizzle)
 constexpr int TC_UK = 8;              // K of one tcgen05.mma.kind::tf32
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 192 / (TC_BK * 4);   // 192 KB of stages: 6 x 32 KB (or 3 x 64 KB at TC_BK = 16)
 constexpr int TC_MAX_NT = 256;        // UMMA N
 constexpr int TC_MAX_D = 1024;
 constexpr int TC_THREADS = 320;
-constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 64
+constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 32
+constexpr int TC_CHUNKS = TC_ROW_BYTES / 16;                           // 16-byte chunks per row
+constexpr int TC_SWZ_SHIFT = TC_ROW_BYTES == 128 ? 0 : TC_ROW_BYTES == 64 ? 1 : 2;   // row bits that feed the XOR
+constexpr uint64_t TC_LAYOUT_TYPE = TC_ROW_BYTES == 128 ? 2 : TC_ROW_BYTES == 64 ? 4 : 6;   // UMMA SWIZZLE_128B/64B/32B
 constexpr uint32_t TC_A_BYTES = TC_RB * TC_BM * TC_ROW_BYTES;          // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_MAX_NT * TC_ROW_BYTES;              // 16 KB
 constexpr uint32_t TC_OFF_AHI = 0, TC_OFF_ALO = TC_A_BYTES, TC_OFF_BHI = 2 * TC_A_BYTES,
@@ -103,9 +107,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major operand tile stored as rows of 64 bytes with the 64-byte swizzle (what TMA
-// SWIZZLE_64B writes: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)): 8-row groups are
-// 512 bytes apart (SBO), descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B.  Advancing
+// K-major operand tile stored as rows of TC_ROW_BYTES with the matching TMA swizzle (16-byte chunk
+// c of row r sits at chunk c ^ ((r >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1)): address bits [4,7) ^= bits
+// [7,10)); 8-row groups are 8 * TC_ROW_BYTES apart (SBO), descriptor version 1 (sm_100).  Advancing
 // along K inside the swizzle row = adding the byte offset to the start address.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -113,7 +117,7 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)(8 * TC_ROW_BYTES >> 4) << 32;  // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+  d |= TC_LAYOUT_TYPE << 61;                     // swizzle mode
   return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -137,6 +141,7 @@ struct TcDriftParams {
   uint64_t n;
   int d, nt, n_tiles, k_tiles;
   uint32_t n_m_tiles;
+  int debug;   // MCCB200_DEBUG_GEMM (timing experiments only, results are wrong): 1 = converter idle, 2 = one product
   const float* mean;
   float* f;
 };
@@ -220,15 +225,17 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
               const uint32_t d_tmem = tmem_base + (uint32_t)r * (uint32_t)p.nt;
               const uint64_t a_hi = tc_smem_desc(sb + TC_OFF_AHI + r * TC_BM * TC_ROW_BYTES);
               const uint64_t a_lo = tc_smem_desc(sb + TC_OFF_ALO + r * TC_BM * TC_ROW_BYTES);
+              if (!(p.debug & 2)) {
 #pragma unroll
-              for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {   // descriptor start address advances in 16-byte units
-                const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
-                tc_mma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (kt | ks) != 0);
-              }
+                for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {   // descriptor start address advances in 16-byte units
+                  const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
+                  tc_mma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (kt | ks) != 0);
+                }
 #pragma unroll
-              for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
-                const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
-                tc_mma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
+                  const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
+                  tc_mma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                }
               }
 #pragma unroll
               for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
@@ -254,10 +261,10 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
           mbar_wait(bar_full + 8 * stage, phase);
           uint8_t* sa = smem + stage * TC_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < (int)(TC_A_BYTES / 16) / 128; ++i) {
+          for (int i = 0; i < ((p.debug & 1) ? 0 : (int)(TC_A_BYTES / 16) / 128); ++i) {
             const int q = tc + 128 * i;                    // physical 16-byte chunk of the tile
-            const int r = q >> 2, pc = q & 3;
-            const int col = kt * TC_BK + ((pc ^ ((r >> 1) & 3)) << 2);   // logical column of the chunk
+            const int r = q / TC_CHUNKS, pc = q % TC_CHUNKS;
+            const int col = kt * TC_BK + ((pc ^ ((r >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 2);   // logical column of the chunk
             float4 v = *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16);
             const float4 m = *reinterpret_cast<const float4*>(s_mean + col);
             float4 hi, lo;
@@ -339,7 +346,7 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// fp32 matrix [rows][cols] with row pitch ld floats; box = [box_rows][TC_BK floats], 64-byte swizzle
+// fp32 matrix [rows][cols] with row pitch ld floats; box = [box_rows][TC_BK floats], swizzle = row bytes
 static int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(MCCB200_ERR_CUDA, "gaussian_full_drift_tc: cuTensorMapEncodeTiled unavailable");
@@ -348,7 +355,9 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   TC_ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : TC_ROW_BYTES == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MCCB200_ERR_CUDA, "gaussian_full_drift_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return MCCB200_OK;
@@ -391,6 +400,7 @@ extern "C" int mccb200_gaussian_full_drift_tc(const float* y, uint64_t n, int d,
   p.k_tiles = d / TC_BK;
   p.n_m_tiles = (uint32_t)((n + TC_RB * TC_BM - 1) / (TC_RB * TC_BM));
   p.mean = mean; p.f = f;
+  { const char* dbg = getenv("MCCB200_DEBUG_GEMM"); p.debug = dbg ? atoi(dbg) : 0; }
   CUtensorMap map_y, map_bhi, map_blo;
   int rc = make_map(&map_y, y, n, (uint64_t)d, (uint64_t)ld, TC_RB * TC_BM);
   if (rc) return rc;
