@@ -44,7 +44,9 @@ constexpr int TC_UK = 8;              // K of one tcgen05.mma.kind::tf32
 constexpr int TC_STAGES = 192 / (TC_BK * 4);   // 192 KB of stages: 6 x 32 KB (or 3 x 64 KB at TC_BK = 16)
 constexpr int TC_MAX_NT = 256;        // UMMA N
 constexpr int TC_MAX_D = 1024;
-constexpr int TC_THREADS = 320;
+constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = 32 * (2 + TC_CONV_WARPS + TC_EPI_WARPS);   // producer, MMA, converters, epilogue
+constexpr int TC_CLUSTER = 2;         // CTAs (SM pair) sharing every prec tile through TMA multicast
 constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 32
 constexpr int TC_CHUNKS = TC_ROW_BYTES / 16;                           // 16-byte chunks per row
 constexpr int TC_SWZ_SHIFT = TC_ROW_BYTES == 128 ? 0 : TC_ROW_BYTES == 64 ? 1 : 2;   // row bits that feed the XOR
@@ -54,7 +56,8 @@ constexpr uint32_t TC_B_BYTES = TC_MAX_NT * TC_ROW_BYTES;              // 16 KB
 constexpr uint32_t TC_OFF_AHI = 0, TC_OFF_ALO = TC_A_BYTES, TC_OFF_BHI = 2 * TC_A_BYTES,
                    TC_OFF_BLO = 2 * TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4 + 256 + 1024;  // + mean, barriers, align
+constexpr uint32_t TC_EPI_BYTES = 0;                                   // the epilogue does not stage through shared memory
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4 + 256 + TC_EPI_BYTES + 1024;  // + mean, barriers, align
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,10 +95,37 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// the same box written to the same shared-memory offset of every CTA in cta_mask (each CTA's own
+// mbarrier at that offset receives the complete_tx)
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+// pull a tile into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of cta_mask once the MMAs issued so far are done
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -120,6 +150,29 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   d |= TC_LAYOUT_TYPE << 61;                     // swizzle mode
   return d;
 }
+// 16 TMEM lanes x 64 columns: thread t holds rows t/4 (v[4i], v[4i+1]) and t/4 + 8 (v[4i+2], v[4i+3]),
+// columns 8i + 2(t%4), +1  -- the accumulator-fragment layout: a warp-wide 8-byte store then writes
+// 8 rows x one full 32-byte sector
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -141,12 +194,13 @@ struct TcDriftParams {
   uint64_t n;
   int d, nt, n_tiles, k_tiles;
   uint32_t n_m_tiles;
+  long long* trace;   // debug: [256 stages][5] clock64 stamps of CTA 0 (producer issue, full seen, converted, MMA start, MMA issued)
   int debug;   // MCCB200_DEBUG_GEMM (timing experiments only, results are wrong): 1 = converter idle, 2 = one product
   const float* mean;
   float* f;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_bhi,
                               const __grid_constant__ CUtensorMap map_blo, const TcDriftParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -159,6 +213,7 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
   const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + TC_STAGES), bar_empty = smem_u32(bars + 2 * TC_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + 1);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1 + TC_RB);
+  uint8_t* s_epi = smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4 + 256;
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -166,11 +221,11 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 128);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 32 * TC_CONV_WARPS);
+      mbar_init(bar_empty + 8 * s, TC_CLUSTER);          // one commit from every CTA of the cluster
     }
     mbar_init(bar_tfull, 1);
-    for (int r = 0; r < TC_RB; ++r) mbar_init(bar_tempty + 8 * r, 128);
+    for (int r = 0; r < TC_RB; ++r) mbar_init(bar_tempty + 8 * r, 32 * TC_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: TC_RB accumulators of up to 256 fp32 columns
@@ -178,24 +233,42 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();            // barrier inits visible cluster-wide before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const uint32_t cta_rank = cluster_ctarank();
+  const uint16_t cta_all = (uint16_t)((1u << TC_CLUSTER) - 1u);
+  // Both CTAs of a cluster run the same number of tiles (their stage rings are coupled); a CTA
+  // past the end recomputes the last tile and stores nothing.
+  const uint32_t n_iter = (p.n_m_tiles + gridDim.x - 1) / gridDim.x;
 
   const uint32_t stage_tx = TC_A_BYTES + 2u * (uint32_t)p.nt * TC_ROW_BYTES;
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+      uint32_t g = 0;
+      const int b_rows = p.nt / TC_CLUSTER;                // this CTA's slice of every prec tile
+      const uint32_t b_off = cta_rank * (uint32_t)b_rows * TC_ROW_BYTES;
+      for (uint32_t it = 0; it < n_iter; ++it) {
+        const uint32_t mt = min(blockIdx.x + it * gridDim.x, p.n_m_tiles - 1u);
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);   // stage free in EVERY CTA of the cluster
+            if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 0] = clock64();
+            ++g;
             const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
             mbar_expect_tx(bar_full + 8 * stage, stage_tx);
             tma_load_2d(sb + TC_OFF_AHI, &map_y, bar_full + 8 * stage, kt * TC_BK, (int)(mt * (TC_RB * TC_BM)));
-            tma_load_2d(sb + TC_OFF_BHI, &map_bhi, bar_full + 8 * stage, kt * TC_BK, nt * p.nt);
-            tma_load_2d(sb + TC_OFF_BLO, &map_blo, bar_full + 8 * stage, kt * TC_BK, nt * p.nt);
+            // the particle tile is read from HBM once per m-tile (first n-tile); take that latency
+            // off the stage ring by pulling the NEXT m-tile's slice into L2 during the last n-tile
+            if (nt == p.n_tiles - 1 && it + 1 < n_iter && (p.debug & 4) == 0)
+              tma_prefetch_l2_2d(&map_y, kt * TC_BK,
+                                 (int)(min(blockIdx.x + (it + 1) * gridDim.x, p.n_m_tiles - 1u) * (TC_RB * TC_BM)));
+            tma_load_2d_mcast(sb + TC_OFF_BHI + b_off, &map_bhi, bar_full + 8 * stage, kt * TC_BK,
+                              nt * p.nt + (int)cta_rank * b_rows, cta_all);
+            tma_load_2d_mcast(sb + TC_OFF_BLO + b_off, &map_blo, bar_full + 8 * stage, kt * TC_BK,
+                              nt * p.nt + (int)cta_rank * b_rows, cta_all);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -207,13 +280,15 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
       // instruction descriptor: D fp32, A/B tf32, both K-major, A negated, N = nt, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((uint32_t)(p.nt >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t stage = 0, phase = 0, tphase = 0;
-      for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+      uint32_t stage = 0, phase = 0, tphase = 0, g = 0;
+      for (uint32_t it = 0; it < n_iter; ++it) {
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait(bar_full + 8 * stage, phase);          // the prec tiles (TMA) ...
-            mbar_wait(bar_conv + 8 * stage, phase);          // ... and the split particle tile (converter warps)
+            // conv[stage] completes only after every converter thread has seen full[stage] (all TMA
+            // bytes of the stage, from both CTAs, landed) and fenced its own writes
+            mbar_wait(bar_conv + 8 * stage, phase);
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 3] = clock64();
             const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
             const uint64_t b_hi = tc_smem_desc(sb + TC_OFF_BHI), b_lo = tc_smem_desc(sb + TC_OFF_BLO);
 #pragma unroll
@@ -243,26 +318,29 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
                 tc_mma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
               }
             }
-            tc_commit(bar_empty + 8 * stage);               // stage reusable once these MMAs have read it
+            tc_commit_mcast(bar_empty + 8 * stage, cta_all);  // tell every producer of the cluster: this CTA is done with the stage
             if (kt == p.k_tiles - 1) tc_commit(bar_tfull);
+            if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 4] = clock64();
+            ++g;
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
           tphase ^= 1u;
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + TC_CONV_WARPS) {
     // ===== converter: centre and split the particle tile in place (swizzle aware) =====
-    const int tc = threadIdx.x - 64;                       // 0..127
-    uint32_t stage = 0, phase = 0;
-    for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+    const int tc = threadIdx.x - 64;                       // 0 .. 32 * TC_CONV_WARPS - 1
+    uint32_t stage = 0, phase = 0, g = 0;
+    for (uint32_t it = 0; it < n_iter; ++it) {
       for (int nt = 0; nt < p.n_tiles; ++nt) {
         for (int kt = 0; kt < p.k_tiles; ++kt) {
           mbar_wait(bar_full + 8 * stage, phase);
+          if (p.trace && blockIdx.x == 0 && tc == 0 && g < 256) p.trace[g * 5 + 1] = clock64();
           uint8_t* sa = smem + stage * TC_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < ((p.debug & 1) ? 0 : (int)(TC_A_BYTES / 16) / 128); ++i) {
-            const int q = tc + 128 * i;                    // physical 16-byte chunk of the tile
+          for (int i = 0; i < ((p.debug & 1) ? 0 : (int)(TC_A_BYTES / 16) / (32 * TC_CONV_WARPS)); ++i) {
+            const int q = tc + 32 * TC_CONV_WARPS * i;     // physical 16-byte chunk of the tile
             const int r = q / TC_CHUNKS, pc = q % TC_CHUNKS;
             const int col = kt * TC_BK + ((pc ^ ((r >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 2);   // logical column of the chunk
             float4 v = *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16);
@@ -276,30 +354,46 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
           mbar_arrive(bar_conv + 8 * stage);
+          if (p.trace && blockIdx.x == 0 && tc == 0 && g < 256) p.trace[g * 5 + 2] = clock64();
+          ++g;
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> F =====
+    // Shared memory is the scarce resource of this kernel (tensor-core operand reads + converter +
+    // TMA fills ~ 128 B/cycle), so the accumulator goes straight from registers to global memory.
+    // The 32x32b load shape (thread = row) would scatter 16-byte pieces over 32 rows per store
+    // (measured 21k cycles per tile); the 16x256b fragment shape lets a warp-wide 8-byte store write
+    // 8 rows x one full 32-byte sector.
     const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31 belong to this warp
     uint32_t tphase = 0;
-    for (uint32_t mt = blockIdx.x; mt < p.n_m_tiles; mt += gridDim.x) {
+    for (uint32_t it = 0; it < n_iter; ++it) {
+      const uint32_t mt = blockIdx.x + it * gridDim.x;
+      const bool live = mt < p.n_m_tiles;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
         mbar_wait(bar_tfull, tphase);
         tc_fence_after();
 #pragma unroll 1
         for (int r = 0; r < TC_RB; ++r) {
-          const uint64_t row = (uint64_t)mt * (TC_RB * TC_BM) + (uint64_t)(r * TC_BM + quad * 32 + lane);
-          for (int c0 = 0; c0 < p.nt; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * (uint32_t)p.nt + (uint32_t)c0, v);
-            if (row < p.n) {
-              float4* dst = reinterpret_cast<float4*>(p.f + row * (uint64_t)p.d + (uint64_t)(nt * p.nt + c0));
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {                    // lanes 0-15 / 16-31 of the quadrant
+            const uint64_t row_a = (uint64_t)mt * (TC_RB * TC_BM) + (uint64_t)(r * TC_BM + quad * 32 + h * 16 + (lane >> 2));
+            float* dst_a = p.f + row_a * (uint64_t)p.d + (uint64_t)(nt * p.nt + 2 * (lane & 3));
+            float* dst_b = dst_a + 8 * (uint64_t)p.d;
+            const bool ok_a = live && row_a < p.n, ok_b = live && row_a + 8 < p.n;
+            for (int c0 = 0; c0 < p.nt; c0 += 64) {
+              uint32_t v[32];
+              const int ncol = min(64, p.nt - c0);         // nt = 32: half of the 64-column load is another tile's columns
+              tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)r * (uint32_t)p.nt + (uint32_t)c0, v);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                __stcs(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+              for (int i = 0; i < 8; ++i) {
+                if (8 * i < ncol) {
+                  if (ok_a) __stcs(reinterpret_cast<float2*>(dst_a + c0 + 8 * i), make_float2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])));
+                  if (ok_b) __stcs(reinterpret_cast<float2*>(dst_b + c0 + 8 * i), make_float2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                }
+              }
             }
           }
           tc_fence_before();
@@ -310,7 +404,7 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();            // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -363,6 +457,8 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t
   return MCCB200_OK;
 }
 
+static long long* g_tc_trace = nullptr;   // debug only (mccb200_debug_gemm_trace)
+
 static bool tc_shape_ok(uint64_t n, int d, int ld, const void* y) {
   return d >= 32 && d <= TC_MAX_D && d % 32 == 0 && ld % 4 == 0 && ((uintptr_t)y & 15) == 0 && n >= 1 &&
          n < 0x7FFFFFFFull;
@@ -371,6 +467,9 @@ static bool tc_shape_ok(uint64_t n, int d, int ld, const void* y) {
 }  // namespace mccb
 
 using namespace mccb;
+
+// Debug hook (not part of the C ABI of include/mccube_b200.h): device buffer of 256 * 5 int64 clock stamps.
+extern "C" __attribute__((visibility("default"))) void mccb200_debug_gemm_trace(long long* buf) { g_tc_trace = buf; }
 
 extern "C" int mccb200_gaussian_full_drift_tc_supported(uint64_t n, int d, int ld) {
   return tc_shape_ok(n, d, ld, nullptr) ? 1 : 0;
@@ -401,15 +500,19 @@ extern "C" int mccb200_gaussian_full_drift_tc(const float* y, uint64_t n, int d,
   p.n_m_tiles = (uint32_t)((n + TC_RB * TC_BM - 1) / (TC_RB * TC_BM));
   p.mean = mean; p.f = f;
   { const char* dbg = getenv("MCCB200_DEBUG_GEMM"); p.debug = dbg ? atoi(dbg) : 0; }
+  p.trace = g_tc_trace;
   CUtensorMap map_y, map_bhi, map_blo;
   int rc = make_map(&map_y, y, n, (uint64_t)d, (uint64_t)ld, TC_RB * TC_BM);
   if (rc) return rc;
-  rc = make_map(&map_bhi, prec_split, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt);
+  rc = make_map(&map_bhi, prec_split, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt / TC_CLUSTER);
   if (rc) return rc;
-  rc = make_map(&map_blo, prec_split + (size_t)d * d, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt);
+  rc = make_map(&map_blo, prec_split + (size_t)d * d, (uint64_t)d, (uint64_t)d, (uint64_t)d, (uint32_t)p.nt / TC_CLUSTER);
   if (rc) return rc;
   cudaFuncSetAttribute(gaussian_full_drift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-  const int grid = (int)min((uint32_t)sm_count(), p.n_m_tiles);
+  int grid = (int)min((uint32_t)sm_count(), p.n_m_tiles);
+  grid = (grid + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // whole clusters
+  if (grid > sm_count()) grid -= TC_CLUSTER;
+  if (grid < TC_CLUSTER) grid = TC_CLUSTER;
   phase_mark("gemm_drift_tc", (cudaStream_t)stream);
   gaussian_full_drift_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(map_y, map_bhi, map_blo, p);
   phase_mark("end", (cudaStream_t)stream);
