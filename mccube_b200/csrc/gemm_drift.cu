@@ -38,21 +38,25 @@
 namespace mccb {
 
 constexpr int TC_BM = 128;            // rows per accumulator (UMMA M)
-constexpr int TC_RB = 2;              // accumulators (row blocks) per CTA tile
-constexpr int TC_BK = 16;             // fp32 per k-step = one swizzle row (8 / 16 / 32 floats <-> 32 / 64 / 128-byte swizzle)
+constexpr int TC_RB = 1;              // accumulators (row blocks) per CTA tile
+constexpr int TC_ACC = 2;             // TMEM accumulator stages (epilogue of tile i overlaps the main loop of tile i+1)
+constexpr int TC_BK = 32;             // fp32 per k-step = one swizzle row (8 / 16 / 32 floats <-> 32 / 64 / 128-byte swizzle)
 constexpr int TC_UK = 8;              // K of one tcgen05.mma.kind::tf32
-constexpr int TC_STAGES = 192 / (TC_BK * 4);   // 192 KB of stages: 6 x 32 KB (or 3 x 64 KB at TC_BK = 16)
+constexpr int TC_STAGES = 3;          // 3 x 64 KB
 constexpr int TC_MAX_NT = 256;        // UMMA N
 constexpr int TC_MAX_D = 1024;
 constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 4;
-constexpr int TC_THREADS = 32 * (2 + TC_CONV_WARPS + TC_EPI_WARPS);   // producer, MMA, converters, epilogue
-constexpr int TC_CLUSTER = 2;         // CTAs (SM pair) sharing every prec tile through TMA multicast
-constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 32
+constexpr int TC_CONV_GROUPS = 2;     // converter groups taking alternate stages: the fence / barrier / remote-arrive tail of one
+                                      // stage overlaps the conversion of the next
+constexpr int TC_THREADS = 32 * (2 + TC_CONV_GROUPS * TC_CONV_WARPS + TC_EPI_WARPS);   // producer, MMA, converters, epilogue
+constexpr int TC_CLUSTER = 2;         // CTA pair (cta_group::2): one UMMA spans both SMs, each holds half of every prec tile
+constexpr uint32_t TC_ROW_BYTES = TC_BK * 4;                           // 128: TMA moves a box row by row at ~2.5-4 cycles per row,
+                                                                       // so short rows starve the ring (measured: 64-byte rows 15-25 B/cycle/SM)
 constexpr int TC_CHUNKS = TC_ROW_BYTES / 16;                           // 16-byte chunks per row
 constexpr int TC_SWZ_SHIFT = TC_ROW_BYTES == 128 ? 0 : TC_ROW_BYTES == 64 ? 1 : 2;   // row bits that feed the XOR
 constexpr uint64_t TC_LAYOUT_TYPE = TC_ROW_BYTES == 128 ? 2 : TC_ROW_BYTES == 64 ? 4 : 6;   // UMMA SWIZZLE_128B/64B/32B
 constexpr uint32_t TC_A_BYTES = TC_RB * TC_BM * TC_ROW_BYTES;          // 16 KB
-constexpr uint32_t TC_B_BYTES = TC_MAX_NT * TC_ROW_BYTES;              // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_MAX_NT / 2 * TC_ROW_BYTES;          // 16 KB: each CTA of the pair holds half of the N rows
 constexpr uint32_t TC_OFF_AHI = 0, TC_OFF_ALO = TC_A_BYTES, TC_OFF_BHI = 2 * TC_A_BYTES,
                    TC_OFF_BLO = 2 * TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 64 KB
@@ -117,14 +121,40 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {   // same offset in another CTA of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// wait that also acquires what remote CTAs released before arriving
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at this offset in every CTA of cta_mask once the MMAs issued so far are done
+// arrive on the barrier at this offset in every CTA of cta_mask once the pair's MMAs issued so far are done
 __device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
@@ -133,7 +163,7 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -204,100 +234,97 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
 gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_bhi,
                               const __grid_constant__ CUtensorMap map_blo, const TcDriftParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // swizzled tiles want (at least) 512-byte alignment
+  // swizzled tiles want (at least) 512-byte alignment; both CTAs of the pair use identical offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* s_mean = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4);
-  // barrier ring: full[s] (TMA landed), conv[s] (converter done), empty[s] (MMA consumed),
-  //               tmem_full (both accumulators ready), tmem_empty[r] (accumulator r drained)
+  // barrier ring: full[s]   (this CTA's TMA landed)                        local, 1 arrival + tx bytes
+  //               conv[s]   (both CTAs' particle tiles split)              LEADER's, 1 arrival per CTA
+  //               empty[s]  (the pair's MMAs consumed the stage)           each CTA, 1 multicast commit
+  //               tmem_full (accumulators ready)                           each CTA, 1 multicast commit
+  //               tmem_empty[r] (accumulator r drained in both CTAs)       LEADER's, 1 arrival per CTA
   const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + TC_STAGES), bar_empty = smem_u32(bars + 2 * TC_STAGES);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + 1);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1 + TC_RB);
-  uint8_t* s_epi = smem + TC_STAGES * TC_STAGE_BYTES + TC_MAX_D * 4 + 256;
+  const uint32_t bar_tfull = smem_u32(bars + 3 * TC_STAGES), bar_tempty = smem_u32(bars + 3 * TC_STAGES + TC_ACC);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2 * TC_ACC);
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const uint16_t cta_all = (uint16_t)((1u << TC_CLUSTER) - 1u);
   for (int i = threadIdx.x; i < p.d; i += TC_THREADS) s_mean[i] = p.mean[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 32 * TC_CONV_WARPS);
-      mbar_init(bar_empty + 8 * s, TC_CLUSTER);          // one commit from every CTA of the cluster
+      mbar_init(bar_conv + 8 * s, TC_CLUSTER);            // one arrival per CTA (its converter warps sync first)
+      mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tfull, 1);
-    for (int r = 0; r < TC_RB; ++r) mbar_init(bar_tempty + 8 * r, 32 * TC_EPI_WARPS);
+    for (int a = 0; a < TC_ACC; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, TC_CLUSTER);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: TC_RB accumulators of up to 256 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // TMEM: TC_RB accumulators of up to 256 fp32 columns, allocated in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  cluster_sync_all();            // barrier inits visible cluster-wide before any remote arrive / multicast
+  cluster_sync_all();            // barrier inits visible cluster-wide before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t cta_rank = cluster_ctarank();
-  const uint16_t cta_all = (uint16_t)((1u << TC_CLUSTER) - 1u);
-  // Both CTAs of a cluster run the same number of tiles (their stage rings are coupled); a CTA
-  // past the end recomputes the last tile and stores nothing.
-  const uint32_t n_iter = (p.n_m_tiles + gridDim.x - 1) / gridDim.x;
+  // The pair walks the same sequence of (pair tile, n-tile, k-step); a CTA whose 256 rows lie past the
+  // end recomputes the last tile and stores nothing.
+  const uint32_t n_pairs = (p.n_m_tiles + 1u) / 2u, pairs_in_grid = gridDim.x / 2u;
+  const uint32_t n_iter = (n_pairs + pairs_in_grid - 1u) / pairs_in_grid;
+  const uint32_t pair0 = blockIdx.x / 2u;
+  const uint32_t b_rows = (uint32_t)p.nt / TC_CLUSTER;     // this CTA's rows of every prec tile
 
-  const uint32_t stage_tx = TC_A_BYTES + 2u * (uint32_t)p.nt * TC_ROW_BYTES;
+  const uint32_t stage_tx = TC_A_BYTES + 2u * b_rows * TC_ROW_BYTES;
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (each CTA: its 256 particles, its half of the prec tile) =====
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t g = 0;
-      const int b_rows = p.nt / TC_CLUSTER;                // this CTA's slice of every prec tile
-      const uint32_t b_off = cta_rank * (uint32_t)b_rows * TC_ROW_BYTES;
+      uint32_t stage = 0, phase = 0, g = 0;
       for (uint32_t it = 0; it < n_iter; ++it) {
-        const uint32_t mt = min(blockIdx.x + it * gridDim.x, p.n_m_tiles - 1u);
+        const uint32_t mt = min((pair0 + it * pairs_in_grid) * 2u + cta_rank, p.n_m_tiles - 1u);
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kt = 0; kt < p.k_tiles; ++kt) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);   // stage free in EVERY CTA of the cluster
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 0] = clock64();
             ++g;
             const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
             mbar_expect_tx(bar_full + 8 * stage, stage_tx);
             tma_load_2d(sb + TC_OFF_AHI, &map_y, bar_full + 8 * stage, kt * TC_BK, (int)(mt * (TC_RB * TC_BM)));
-            // the particle tile is read from HBM once per m-tile (first n-tile); take that latency
-            // off the stage ring by pulling the NEXT m-tile's slice into L2 during the last n-tile
-            if (nt == p.n_tiles - 1 && it + 1 < n_iter && (p.debug & 4) == 0)
-              tma_prefetch_l2_2d(&map_y, kt * TC_BK,
-                                 (int)(min(blockIdx.x + (it + 1) * gridDim.x, p.n_m_tiles - 1u) * (TC_RB * TC_BM)));
-            tma_load_2d_mcast(sb + TC_OFF_BHI + b_off, &map_bhi, bar_full + 8 * stage, kt * TC_BK,
-                              nt * p.nt + (int)cta_rank * b_rows, cta_all);
-            tma_load_2d_mcast(sb + TC_OFF_BLO + b_off, &map_blo, bar_full + 8 * stage, kt * TC_BK,
-                              nt * p.nt + (int)cta_rank * b_rows, cta_all);
+            tma_load_2d(sb + TC_OFF_BHI, &map_bhi, bar_full + 8 * stage, kt * TC_BK, nt * p.nt + (int)(cta_rank * b_rows));
+            tma_load_2d(sb + TC_OFF_BLO, &map_blo, bar_full + 8 * stage, kt * TC_BK, nt * p.nt + (int)(cta_rank * b_rows));
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, A negated, N = nt, M = 128
+    // ===== MMA issuer: one thread of the LEADER CTA drives both SMs' tensor cores =====
+    if (lane == 0 && cta_rank == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, A negated, N = nt, M = 256 (128 rows per CTA)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((uint32_t)(p.nt >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t stage = 0, phase = 0, tphase = 0, g = 0;
+                             ((uint32_t)(TC_CLUSTER * TC_BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, g = 0;
       for (uint32_t it = 0; it < n_iter; ++it) {
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kt = 0; kt < p.k_tiles; ++kt) {
-            // conv[stage] completes only after every converter thread has seen full[stage] (all TMA
-            // bytes of the stage, from both CTAs, landed) and fenced its own writes
-            mbar_wait(bar_conv + 8 * stage, phase);
+            // conv[stage] completes only after every converter thread of BOTH CTAs has seen its
+            // full[stage] (all TMA bytes landed) and fenced its own writes
+            mbar_wait_cluster(bar_conv + 8 * stage, phase);
             tc_fence_after();
             if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 3] = clock64();
             const uint32_t sb = smem_base + stage * TC_STAGE_BYTES;
             const uint64_t b_hi = tc_smem_desc(sb + TC_OFF_BHI), b_lo = tc_smem_desc(sb + TC_OFF_BLO);
 #pragma unroll
             for (int r = 0; r < TC_RB; ++r) {
-              if (kt == 0) {                                  // accumulator r drained by the epilogue?
-                mbar_wait(bar_tempty + 8 * r, tphase ^ 1u);
+              if (kt == 0 && r == 0) {                        // accumulator stage drained by both epilogues?
+                mbar_wait_cluster(bar_tempty + 8 * as, aphase ^ 1u);
                 tc_fence_after();
               }
-              const uint32_t d_tmem = tmem_base + (uint32_t)r * (uint32_t)p.nt;
+              const uint32_t d_tmem = tmem_base + (as * TC_RB + (uint32_t)r) * (uint32_t)p.nt;
               const uint64_t a_hi = tc_smem_desc(sb + TC_OFF_AHI + r * TC_BM * TC_ROW_BYTES);
               const uint64_t a_lo = tc_smem_desc(sb + TC_OFF_ALO + r * TC_BM * TC_ROW_BYTES);
               if (!(p.debug & 2)) {
@@ -315,45 +342,63 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
 #pragma unroll
               for (int ks = 0; ks < TC_BK / TC_UK; ++ks) {
                 const uint64_t ko = (uint64_t)(ks * TC_UK * 4 >> 4);
-                tc_mma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                tc_mma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, (p.debug & 2) ? (uint32_t)((kt | ks) != 0) : 1u);
               }
             }
-            tc_commit_mcast(bar_empty + 8 * stage, cta_all);  // tell every producer of the cluster: this CTA is done with the stage
-            if (kt == p.k_tiles - 1) tc_commit(bar_tfull);
+            tc_commit_mcast(bar_empty + 8 * stage, cta_all);  // both producers: the pair is done with the stage
+            if (kt == p.k_tiles - 1) tc_commit_mcast(bar_tfull + 8 * as, cta_all);
             if (p.trace && blockIdx.x == 0 && g < 256) p.trace[g * 5 + 4] = clock64();
             ++g;
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
           }
-          tphase ^= 1u;
+          if (++as == TC_ACC) { as = 0; aphase ^= 1u; }
         }
       }
     }
-  } else if (warp < 2 + TC_CONV_WARPS) {
+  } else if (warp < 2 + TC_CONV_GROUPS * TC_CONV_WARPS) {
     // ===== converter: centre and split the particle tile in place (swizzle aware) =====
-    const int tc = threadIdx.x - 64;                       // 0 .. 32 * TC_CONV_WARPS - 1
+    const int group = (warp - 2) / TC_CONV_WARPS;
+    const int tc = threadIdx.x - 64 - group * 32 * TC_CONV_WARPS;   // 0 .. 32 * TC_CONV_WARPS - 1 inside the group
+    const uint32_t leader_conv = mapa_u32(bar_conv, 0u);
     uint32_t stage = 0, phase = 0, g = 0;
     for (uint32_t it = 0; it < n_iter; ++it) {
       for (int nt = 0; nt < p.n_tiles; ++nt) {
         for (int kt = 0; kt < p.k_tiles; ++kt) {
+          if ((int)(g % TC_CONV_GROUPS) != group) {        // the other group's stage
+            ++g;
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_wait(bar_full + 8 * stage, phase);
           if (p.trace && blockIdx.x == 0 && tc == 0 && g < 256) p.trace[g * 5 + 1] = clock64();
           uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+          if (!(p.debug & 1)) {
+            constexpr int NCH = (int)(TC_A_BYTES / 16) / (32 * TC_CONV_WARPS);   // 16-byte chunks per thread
+            float4 v[NCH];
+            // A thread's chunks are 32 * TC_CONV_WARPS apart = a multiple of 8 rows, so they all sit in the
+            // same logical column group of the swizzled tile: one mean load per stage (shared memory
+            // bandwidth is what bounds this kernel).
+            static_assert((32 * TC_CONV_WARPS / TC_CHUNKS) % 8 == 0, "chunk stride must keep the swizzle phase");
+            const int r0 = tc / TC_CHUNKS, pc0 = tc % TC_CHUNKS;
+            const float4 m = *reinterpret_cast<const float4*>(
+                s_mean + kt * TC_BK + ((pc0 ^ ((r0 >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 2));
+            // all loads first: the stores below may alias them as far as the compiler knows
 #pragma unroll
-          for (int i = 0; i < ((p.debug & 1) ? 0 : (int)(TC_A_BYTES / 16) / (32 * TC_CONV_WARPS)); ++i) {
-            const int q = tc + 32 * TC_CONV_WARPS * i;     // physical 16-byte chunk of the tile
-            const int r = q / TC_CHUNKS, pc = q % TC_CHUNKS;
-            const int col = kt * TC_BK + ((pc ^ ((r >> TC_SWZ_SHIFT) & (TC_CHUNKS - 1))) << 2);   // logical column of the chunk
-            float4 v = *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16);
-            const float4 m = *reinterpret_cast<const float4*>(s_mean + col);
-            float4 hi, lo;
-            v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
-            hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
-            lo.x = rn_tf32(v.x - hi.x); lo.y = rn_tf32(v.y - hi.y); lo.z = rn_tf32(v.z - hi.z); lo.w = rn_tf32(v.w - hi.w);
-            *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16) = hi;
-            *reinterpret_cast<float4*>(sa + TC_OFF_ALO + q * 16) = lo;
+            for (int i = 0; i < NCH; ++i) v[i] = *reinterpret_cast<const float4*>(sa + TC_OFF_AHI + (tc + 32 * TC_CONV_WARPS * i) * 16);
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+              const int q = tc + 32 * TC_CONV_WARPS * i;
+              float4 hi, lo;
+              v[i].x -= m.x; v[i].y -= m.y; v[i].z -= m.z; v[i].w -= m.w;
+              hi.x = rn_tf32(v[i].x); hi.y = rn_tf32(v[i].y); hi.z = rn_tf32(v[i].z); hi.w = rn_tf32(v[i].w);
+              lo.x = rn_tf32(v[i].x - hi.x); lo.y = rn_tf32(v[i].y - hi.y); lo.z = rn_tf32(v[i].z - hi.z); lo.w = rn_tf32(v[i].w - hi.w);
+              *reinterpret_cast<float4*>(sa + TC_OFF_AHI + q * 16) = hi;
+              *reinterpret_cast<float4*>(sa + TC_OFF_ALO + q * 16) = lo;
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
-          mbar_arrive(bar_conv + 8 * stage);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(32 * TC_CONV_WARPS) : "memory");   // the converter threads of this group
+          if (tc == 0) mbar_arrive_cluster(leader_conv + 8 * stage);      // one remote arrival instead of 128
           if (p.trace && blockIdx.x == 0 && tc == 0 && g < 256) p.trace[g * 5 + 2] = clock64();
           ++g;
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -363,17 +408,18 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
   } else {
     // ===== epilogue: TMEM -> registers -> F =====
     // Shared memory is the scarce resource of this kernel (tensor-core operand reads + converter +
-    // TMA fills ~ 128 B/cycle), so the accumulator goes straight from registers to global memory.
-    // The 32x32b load shape (thread = row) would scatter 16-byte pieces over 32 rows per store
-    // (measured 21k cycles per tile); the 16x256b fragment shape lets a warp-wide 8-byte store write
-    // 8 rows x one full 32-byte sector.
+    // TMA fills), so the accumulator goes straight from registers to global memory.  The 32x32b
+    // load shape (thread = row) would scatter 16-byte pieces over 32 rows per store (measured 21k
+    // cycles per tile); the 16x256b fragment shape lets a warp-wide 8-byte store write 8 rows x one
+    // full 32-byte sector.
     const int quad = warp & 3;                             // TMEM lanes 32*quad .. +31 belong to this warp
-    uint32_t tphase = 0;
+    const uint32_t leader_tempty = mapa_u32(bar_tempty, 0u);
+    uint32_t as = 0, aphase = 0;
     for (uint32_t it = 0; it < n_iter; ++it) {
-      const uint32_t mt = blockIdx.x + it * gridDim.x;
+      const uint32_t mt = (pair0 + it * pairs_in_grid) * 2u + cta_rank;
       const bool live = mt < p.n_m_tiles;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
-        mbar_wait(bar_tfull, tphase);
+        mbar_wait(bar_tfull + 8 * as, aphase);
         tc_fence_after();
 #pragma unroll 1
         for (int r = 0; r < TC_RB; ++r) {
@@ -386,7 +432,7 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
             for (int c0 = 0; c0 < p.nt; c0 += 64) {
               uint32_t v[32];
               const int ncol = min(64, p.nt - c0);         // nt = 32: half of the 64-column load is another tile's columns
-              tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)r * (uint32_t)p.nt + (uint32_t)c0, v);
+              tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (as * TC_RB + (uint32_t)r) * (uint32_t)p.nt + (uint32_t)c0, v);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (8 * i < ncol) {
@@ -396,18 +442,19 @@ gaussian_full_drift_tc_kernel(const __grid_constant__ CUtensorMap map_y, const _
               }
             }
           }
-          tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * r);
         }
-        tphase ^= 1u;
+        tc_fence_before();
+        asm volatile("bar.sync 8, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");        // all epilogue threads of this CTA
+        if (threadIdx.x == 32 * (2 + TC_CONV_GROUPS * TC_CONV_WARPS)) mbar_arrive_cluster(leader_tempty + 8 * as);
+        if (++as == TC_ACC) { as = 0; aphase ^= 1u; }
       }
     }
   }
   tc_fence_before();
-  cluster_sync_all();            // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  cluster_sync_all();            // no CTA leaves while the pair's MMAs read its shared memory or peers arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
