@@ -45,7 +45,7 @@ TARGET_MEAN, TARGET_VAR = 2.0, 3.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-log2", type=int, default=24)
@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (configs 2 and 4)")
     return ap.parse_args()
 
 
@@ -143,25 +144,47 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        """Starts `nvidia-smi -lms 20` and waits (<= 3 s) until it is actually sampling: its start-up
+        takes longer than the whole timed region."""
+        import threading
+
+        self.lines, self.first = [], threading.Event()
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def pump():
+            for ln in self.proc.stdout:
+                self.lines.append((time.perf_counter(), ln))
+                self.first.set()
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+        self.first.wait(3.0)
+
+    def mark(self):
+        """Only samples taken after this call count (the timed region starts here)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
+        self.thread.join(timeout=2)
+        t0 = getattr(self, "t_mark", 0.0)
+        out = [ln for (ts, ln) in self.lines if t0 <= ts <= t_end + 0.05]
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
+        for ln in out:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -201,6 +224,91 @@ def build_problem(a, dev):
     gen.manual_seed(1234 + int(os.environ.get("RANK", "0")))
     y0 = torch.randn((n, d), generator=gen, device=dev, dtype=torch.float32)
     return terms, solver, y0
+
+
+def time_steps(solver, terms, y, times, steps, warmup=3):
+    """ms per step of `steps` consecutive steps (CUDA events on the current stream)."""
+    import torch
+
+    state = None
+    for i in range(warmup):
+        y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, warmup + steps):
+        y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, solver.last_path
+
+
+def extra_workloads(dev, peak_gbs):
+    """The other single-GPU configurations of BASELINE.json, timed the same way (device-resident
+    state, CUDA events): reported under "extras", not part of the headline value."""
+    import torch
+
+    import mccube_b200 as mccube
+    from mccube_b200 import diffrax_compat as dfx
+
+    out = {}
+    times = dfx.step_times(0.0, DT0 * 64, DT0, np.float32)
+
+    def mc_problem(n, d, replace, drift):
+        terms = mccube.MCCTerm(
+            dfx.ODETerm(drift),
+            dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                          mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+        return terms, mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=42))
+
+    try:   # config 2: n = 2^20, d = 10, MonteCarloKernel (default: without replacement = 3-round sort shuffle of 2^25)
+        n, d = 1 << 20, 10
+        terms, solver = mc_problem(n, d, False, mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev))
+        ms, path = time_steps(solver, terms, torch.randn((n, d), device=dev), times, 10)
+        out["config2_mc_n2^20_d10"] = {"ms_per_step": ms, "particle_steps_per_sec": n / ms * 1e3, "path": path,
+                                       "note": "bit-exact jax.random shuffle: 3 rounds x (threefry bits + stable radix sort of 2^25 pairs)"}
+    except Exception as e:  # noqa: BLE001
+        out["config2_mc_n2^20_d10"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    try:   # config-3 size with the global MonteCarloKernel(with_replacement=True): the fused expand+resample step
+        n, d = 1 << 24, 64
+        terms, solver = mc_problem(n, d, True, mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev))
+        ms, path = time_steps(solver, terms, torch.randn((n, d), device=dev), times, 10)
+        gbs = 2.0 * n * d * 4 / (ms * 1e-3) / 1e9
+        out["mc_replace_n2^24_d64"] = {"ms_per_step": ms, "particle_steps_per_sec": n / ms * 1e3, "path": path,
+                                       "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak_gbs,
+                                       "note": "whole step (index draw + fused expand+select) vs 2*n*d*4 bytes"}
+    except Exception as e:  # noqa: BLE001
+        out["mc_replace_n2^24_d64"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    try:   # config 4: n = 2^20, d = 512, full covariance: tcgen05 3xTF32 drift + fused step
+        n, d = 1 << 20, 512
+        rs = np.random.default_rng(1)
+        am = rs.normal(size=(d, d))
+        cov = am @ am.T / d + np.eye(d)
+        drift = mccube.GaussianFullDrift(np.full(d, TARGET_MEAN), cov, device=dev)
+        y = torch.randn((n, d), device=dev) * 1.5 + TARGET_MEAN
+        for _ in range(2):
+            drift(0.0, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            drift(0.0, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_d = e0.elapsed_time(e1) / 5
+        flop = 2.0 * n * d * d
+        terms, solver = mc_problem(n, d, True, drift)
+        ms, path = time_steps(solver, terms, y, times, 5)
+        out["config4_fullcov_n2^20_d512"] = {
+            "drift_ms": ms_d, "drift_path": drift.last_path, "drift_useful_tflops": flop / ms_d / 1e9,
+            "drift_tensor_pipe_tflops": 3 * flop / ms_d / 1e9, "step_ms": ms, "particle_steps_per_sec": n / ms * 1e3,
+            "path": path, "note": "step = tcgen05 3xTF32 drift + index draw (with_replacement=True) + fused expand+select"}
+    except Exception as e:  # noqa: BLE001
+        out["config4_fullcov_n2^20_d512"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -243,22 +351,25 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- warm-up (solver_state is threaded through the steps the way diffrax does)
+    state = None
     for i in range(W):
-        y, *_ = solver.step(terms, times[i][0], times[i][1], y, None, None, False)
+        y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
     path = solver.last_path
     barrier()
 
     # ---- timed region (device-resident state; 4 GiB per state >> 126 MB L2, no flush needed)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.mark()
     ev0.record()
     for i in range(W, W + K):
-        y, *_ = solver.step(terms, times[i][0], times[i][1], y, None, None, False)
+        y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -277,8 +388,9 @@ def main():
         _lib.profile_enable(True)
         reps = min(K, 5)
         yy = y
+        st2 = state
         for i in range(W + K, W + K + reps):
-            yy, *_ = solver.step(terms, times[i][0], times[i][1], yy, None, None, False)
+            yy, _, _, st2, _ = solver.step(terms, times[i][0], times[i][1], yy, None, st2, False)
         for name, ms in _lib.profile_read():
             phases.setdefault(name, []).append(ms)
         _lib.profile_enable(False)
@@ -347,6 +459,13 @@ def main():
                     "algorithmic_bytes_per_launch": alg[dom_name], "kernel_ms": dur_ms,
                     "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9), "all_kernels": kernels}
 
+    extras = None
+    if world == 1 and not a.no_extras and a.workload == "box_prk":
+        del y
+        torch.cuda.empty_cache()
+        _lib.release_workspace()
+        extras = extra_workloads(dev, peak)
+
     cpu_baseline = None
     if not a.no_cpu_baseline:
         val, ms, sample = run_oracle(a, a.cpu_n_log2, a.cpu_steps, 1)
@@ -361,7 +480,7 @@ def main():
                    "l2": "state is 4 GiB per array (>> 126 MB L2): no flush between iterations",
                    "threefry_partitionable": False, "phase_ms_per_step": phase_ms},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

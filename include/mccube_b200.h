@@ -177,7 +177,8 @@ MCCB200_API int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32
  * keys of child c = i*k + j computed from parent i in-kernel. */
 MCCB200_API int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
                              const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
-                             float* bounds, void* workspace, size_t workspace_bytes, void* stream);
+                             const float* keycols /* optional, see box_prk_rank_gather */, float* bounds,
+                             void* workspace, size_t workspace_bytes, void* stream);
 MCCB200_API int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
                            const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
                            const float* bounds, uint32_t* keys, void* stream);
@@ -204,7 +205,11 @@ MCCB200_API int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const m
  *     selection (idx_local)     -> `sel`     (mccb200_box_prk_selection_bytes)
  *     count     (y0, bounds, tables)         -> workspace (same size as for box_prk_step)
  *     rank_gather (tables, sel, workspace of count) -> y1
- * box_prk_step == tables; selection; count; rank_gather on one stream. */
+ * box_prk_step == tables; selection; count; rank_gather on one stream.
+ * Key-column hand-over (optional, 4 consecutive 16-byte aligned key columns only): rank_gather can
+ * also write y1[:, dims[0] .. dims[0]+3] packed into keycols_out [n_out, 4]; the NEXT step's
+ * box_child_bounds / box_prk_count then take that array as `keycols` (it must describe their y0
+ * exactly) and read 16 contiguous bytes per parent instead of one DRAM fill per 256-byte row. */
 MCCB200_API size_t mccb200_box_prk_tables_bytes(int k, int n_dims, int bits);
 MCCB200_API int mccb200_box_prk_tables(int k, const int32_t* dims_host, int n_dims, int bits, void* tables,
                                        size_t tables_bytes, void* stream);
@@ -213,13 +218,14 @@ MCCB200_API int mccb200_box_prk_selection(const uint32_t* idx_local, uint64_t ou
                                           void* sel, size_t sel_bytes, void* stream);
 MCCB200_API int mccb200_box_prk_count(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                       const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
-                                      const float* bounds, uint64_t in_per_part, const void* tables, void* workspace,
-                                      size_t workspace_bytes, void* stream);
+                                      const float* bounds, uint64_t in_per_part, const void* tables,
+                                      const float* keycols /* optional */, void* workspace, size_t workspace_bytes,
+                                      void* stream);
 MCCB200_API int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                             const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
                                             uint64_t out_per_part, uint64_t in_per_part, const void* tables,
-                                            const void* sel, float* y1, void* workspace, size_t workspace_bytes,
-                                            void* stream);
+                                            const void* sel, float* y1, float* keycols_out /* optional */,
+                                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ A11: moments
  * One pass each: sums[d] (+ weight sum) and centred second moments [d, d] in fp64:

@@ -80,7 +80,7 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "mccb200_box_child_bounds": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                            C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int,
-                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_box_child_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                          C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
@@ -96,11 +96,11 @@ _SIGNATURES = {
     "mccb200_box_prk_selection": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_box_prk_count": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
                                         C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
-                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_box_prk_rank_gather": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
                                               C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_uint64,
-                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
-                                              C.c_void_p]),
+                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_size_t, C.c_void_p]),
     "mccb200_moments_sum": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "mccb200_moments_m2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
@@ -342,15 +342,16 @@ def box_keys(p, dims, bits, bounds):
     return keys
 
 
-def box_child_bounds(y0, d, drift, dt, cub, dims, bits):
+def box_child_bounds(y0, d, drift, dt, cub, dims, bits, keycols=None):
     lib = load()
-    _require_cuda(y0)
+    _require_cuda(y0, keycols)
     _f32c(y0)
     bounds = torch.empty(2 * len(dims), dtype=torch.float32, device=y0.device)
     ws = workspace(lib.mccb200_box_bounds_workspace_bytes(), y0.device)
     _check(lib.mccb200_box_child_bounds(y0.data_ptr(), y0.shape[0], d, y0.shape[1], C.byref(drift),
                                         float(np.float32(dt)), C.byref(cub), _dims_array(dims), len(dims), bits,
-                                        bounds.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "box_child_bounds")
+                                        _ptr(keycols), bounds.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+           "box_child_bounds")
     return bounds
 
 
@@ -422,7 +423,7 @@ def box_prk_selection(idx_local, in_per_part):
     return sel
 
 
-def box_prk_count(y0, d, drift, dt, cub, dims, bits, bounds, in_per_part, tables):
+def box_prk_count(y0, d, drift, dt, cub, dims, bits, bounds, in_per_part, tables, keycols=None):
     """Counting pass + scan; returns the workspace that box_prk_rank_gather consumes."""
     lib = load()
     _require_cuda(y0, bounds, tables)
@@ -432,11 +433,15 @@ def box_prk_count(y0, d, drift, dt, cub, dims, bits, bounds, in_per_part, tables
     ws = workspace(nbytes, y0.device)
     _check(lib.mccb200_box_prk_count(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
                                      _dims_array(dims), len(dims), bits, bounds.data_ptr(), in_per_part,
-                                     tables.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "box_prk_count")
+                                     tables.data_ptr(), _ptr(keycols), ws.data_ptr(), ws.numel(), _stream()),
+           "box_prk_count")
     return ws
 
 
-def box_prk_rank_gather(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_part, tables, sel, ws, out=None):
+def box_prk_rank_gather(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_part, tables, sel, ws, out=None,
+                        keycols_out=None):
+    """`keycols_out` [n_out, 4] float32 (optional): receives y1[:, dims[0]:dims[0]+4] packed, for the
+    next step's box_child_bounds / box_prk_count."""
     lib = load()
     _require_cuda(y0, tables, sel, ws)
     n = y0.shape[0]
@@ -444,8 +449,8 @@ def box_prk_rank_gather(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_
     out = torch.empty((n_out, y0.shape[1]), dtype=torch.float32, device=y0.device) if out is None else out
     _check(lib.mccb200_box_prk_rank_gather(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
                                            _dims_array(dims), len(dims), bits, out_per_part, in_per_part,
-                                           tables.data_ptr(), sel.data_ptr(), out.data_ptr(), ws.data_ptr(),
-                                           ws.numel(), _stream()), "box_prk_rank_gather")
+                                           tables.data_ptr(), sel.data_ptr(), out.data_ptr(), _ptr(keycols_out),
+                                           ws.data_ptr(), ws.numel(), _stream()), "box_prk_rank_gather")
     return out
 
 

@@ -164,7 +164,7 @@ class MCCSolver(AbstractWrappedSolver):
               and type(kernel.partitioning_kernel) is BoxPartitionKernel
               and type(kernel.recombination_kernel) is MonteCarloKernel
               and isinstance(kernel.partitioning_kernel.partition_count, int)):
-            y1_hat = self._box_prk_step(terms, t0, times[0], y0c, args, kernel)
+            y1_hat, solver_state = self._box_prk_step(terms, t0, times[0], y0c, args, kernel, solver_state)
         if y1_hat is None:
             y1_hat = self._generic_step(terms, t0, times, y0c, args, kernel)
         # renormalise the weights after recombination (_solvers.py:146)
@@ -176,7 +176,20 @@ class MCCSolver(AbstractWrappedSolver):
         dense_info = dict(y0=y0, y1=y1_hat)
         return y1_res, None, dense_info, solver_state, RESULTS.successful
 
-    def _box_prk_step(self, terms, t0, times0, y0c, args, kernel):
+    @staticmethod
+    def _carried_keycols(solver_state, y0c, dims):
+        """The packed key columns the previous step's gather wrote for exactly this state tensor
+        (same object, not modified since), or None.  Carried in `solver_state`, which diffrax hands
+        from one step to the next (the reference's MCCSolver carries None there)."""
+        if not isinstance(solver_state, dict):
+            return None
+        kc = solver_state.get("mccb200_keycols")
+        if kc is None or solver_state.get("y1") is not y0c or solver_state.get("version") != y0c._version \
+                or solver_state.get("dims") != tuple(dims):
+            return None
+        return kc
+
+    def _box_prk_step(self, terms, t0, times0, y0c, args, kernel, solver_state=None):
         part: BoxPartitionKernel = kernel.partitioning_kernel
         mc: MonteCarloKernel = kernel.recombination_kernel
         drift, cub, dt, k, d = self._describe(terms, y0c, *times0, args)
@@ -200,18 +213,28 @@ class MCCSolver(AbstractWrappedSolver):
         with torch.cuda.stream(side):
             idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
             sel = _lib.box_prk_selection(idx_local, in_per_part) if use_kernel else None
+        # 4 consecutive, 16-byte aligned key columns: the gather also emits them packed for the next step
+        vec4 = (use_kernel and len(dims) == 4 and dims[0] % 4 == 0 and tuple(dims) == tuple(range(dims[0], dims[0] + 4))
+                and d % 4 == 0 and getattr(self, "carry_key_columns", True))
+        keycols = self._carried_keycols(solver_state, y0c, dims) if vec4 else None
         bounds = part.fixed_bounds(dims, y0c.device)
         if bounds is None:
-            bounds = _lib.box_child_bounds(y0c, d, drift, dt, cub, dims, part.bits)
+            bounds = _lib.box_child_bounds(y0c, d, drift, dt, cub, dims, part.bits, keycols=keycols)
         if use_kernel:
-            ws = _lib.box_prk_count(y0c, d, drift, dt, cub, dims, part.bits, bounds, in_per_part, tables)
+            ws = _lib.box_prk_count(y0c, d, drift, dt, cub, dims, part.bits, bounds, in_per_part, tables, keycols=keycols)
             main.wait_stream(side)
             idx_local.record_stream(main)
             sel.record_stream(main)
+            n_out = m * out_per_part
+            keycols_out = torch.empty((n_out, 4), dtype=torch.float32, device=y0c.device) if vec4 else None
             out = _lib.box_prk_rank_gather(y0c, d, drift, dt, cub, dims, part.bits, out_per_part, in_per_part,
-                                           tables, sel, ws)
-            self.last_path = "fused:box_prk_step"
-            return out
+                                           tables, sel, ws, keycols_out=keycols_out)
+            self.last_path = "fused:box_prk_step" + ("+keycols" if keycols is not None else "")
+            state = solver_state
+            if vec4:
+                state = dict(solver_state) if isinstance(solver_state, dict) else {}
+                state.update(mccb200_keycols=keycols_out, y1=out, version=out._version, dims=tuple(dims))
+            return out, state
         main.wait_stream(side)
         idx_local.record_stream(main)
         keys = _lib.box_child_keys(y0c, d, drift, dt, cub, dims, part.bits, bounds)
@@ -219,7 +242,7 @@ class MCCSolver(AbstractWrappedSolver):
         out = _lib.expand_select(y0c, d, False, drift, dt, cub, idx_local, perm=perm, out_per_part=out_per_part,
                                  in_per_part=in_per_part, n_out=m * out_per_part)
         self.last_path = "fused:box_child_keys+sort+expand_select"
-        return out
+        return out, solver_state
 
     def _generic_step(self, terms, t0, times, y0c, args, kernel):
         """The reference's data flow with the expansion materialised on the GPU

@@ -808,6 +808,7 @@ static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cud
 #undef MCCB_FLAT
   // gather: the HBM-bound fused expand+select materialises the selected children
   ExpandArgs g = p.a;
+  g.keycols = nullptr;
   const uint64_t total = p.a.n * (uint64_t)p.a.k;
   g.idx = p.idx_out; g.perm = nullptr; g.out_per_part = 1; g.in_per_part = 1;
   g.n_out = total / p.in_per_part * p.out_per_part; g.y1 = y1;
@@ -863,8 +864,8 @@ extern "C" size_t mccb200_box_prk_step_workspace_bytes(uint64_t n, int k, int n_
 
 extern "C" int mccb200_box_prk_count(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                      const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
-                                     const float* bounds, uint64_t in_per_part, const void* tables, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+                                     const float* bounds, uint64_t in_per_part, const void* tables,
+                                     const float* keycols, void* workspace, size_t workspace_bytes, void* stream) {
   BoxPrkParams p{};
   PrkPlan pl;
   int rc = setup_params(p, pl, y0, n, d, drift, dt, cub, dims_host, n_dims, bits, 1, in_per_part, workspace,
@@ -874,14 +875,15 @@ extern "C" int mccb200_box_prk_count(const float* y0, uint64_t n, int d, const m
   if (n == 0) return MCCB200_OK;
   p.bounds = bounds;
   bind_tables(p, pl.tl, tables);
+  p.a.keycols = (box_dims_vec4(p.spec, p.a) && keycols && (((uintptr_t)keycols & 15) == 0)) ? keycols : nullptr;
   return launch_count(p, pl, (cudaStream_t)stream);
 }
 
 extern "C" int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                            const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
                                            uint64_t out_per_part, uint64_t in_per_part, const void* tables,
-                                           const void* sel, float* y1, void* workspace, size_t workspace_bytes,
-                                           void* stream) {
+                                           const void* sel, float* y1, float* keycols_out, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
   BoxPrkParams p{};
   PrkPlan pl;
   int rc = setup_params(p, pl, y0, n, d, drift, dt, cub, dims_host, n_dims, bits, out_per_part, in_per_part, workspace,
@@ -895,6 +897,12 @@ extern "C" int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, c
   p.pre = (const uint32_t*)((const char*)sel + sl.off_pre);
   p.sp = (const uint2*)((const char*)sel + sl.off_sp);
   p.sel_ext = sl.ext;
+  if (keycols_out && box_dims_vec4(p.spec, p.a) && (((uintptr_t)keycols_out | (uintptr_t)y1) & 15) == 0) {
+    p.a.keycols_out = keycols_out;
+    p.a.keycol0 = p.spec.dims[0];
+  } else if (keycols_out) {
+    return fail(MCCB200_ERR_UNSUPPORTED, "box_prk_rank_gather: keycols_out needs 4 consecutive 16-byte aligned key columns");
+  }
   return launch_rank_gather(p, pl, y1, (cudaStream_t)stream);
 }
 

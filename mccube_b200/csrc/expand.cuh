@@ -23,6 +23,9 @@ struct ExpandArgs {
   uint32_t out_per_part, in_per_part;
   uint64_t n_out;
   float* y1;
+  const float* keycols;   // optional [n, 4]: y0[:, c0 .. c0+3] of the 4 vectorised box key columns, packed
+  float* keycols_out;     // optional [n_out, 4]: the same columns of y1, written by the expand kernel
+  int keycol0;            // c0 of keycols_out
   int vpr;            // vectors per row = d / VEC
   int rows_per_iter;  // rows covered by one CTA pass = blockDim / vpr
 };
@@ -87,7 +90,9 @@ inline bool box_dims_vec4(const BoxSpec& s, const ExpandArgs& a) {
 __device__ __forceinline__ void key_children4(const ExpandArgs& a, const BoxSpec& s, uint64_t i, float (&vm)[4],
                                               float (&vp)[4]) {
   const int c0 = s.dims[0];
-  const float4 y4 = ld_strided4(a.y0 + i * a.ld + c0);
+  // the previous step's gather can hand over its key columns packed (16 contiguous bytes per
+  // parent instead of a 64-byte DRAM fill per 256-byte row)
+  const float4 y4 = a.keycols ? __ldg(reinterpret_cast<const float4*>(a.keycols) + i) : ld_strided4(a.y0 + i * a.ld + c0);
   const float y[4] = {y4.x, y4.y, y4.z, y4.w};
   float f[4] = {0.f, 0.f, 0.f, 0.f};
   if (a.drift_kind == 1) {

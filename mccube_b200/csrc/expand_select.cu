@@ -128,6 +128,8 @@ expand_kernel(const ExpandArgs a) {
         out[e] = __fadd_rn(y[u][e], step);
       }
       store_vec_stream<VEC>(a.y1 + r[u] * a.ld + col, out);
+      if (VEC == 4 && a.keycols_out != nullptr && col == a.keycol0)      // packed key columns for the next step's partitioner
+        store_vec_stream<VEC>(a.keycols_out + r[u] * 4, out);
       if (do_w) {
         // quirk Q3 (_solvers.py:138-141): weights are flattened from a [k, n] array
         uint64_t cc = c[u];

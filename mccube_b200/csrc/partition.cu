@@ -228,8 +228,8 @@ extern "C" int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32_
 
 extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
                                         float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
-                                        int bits, float* bounds, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        int bits, const float* keycols, float* bounds, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
   BoxSpec s;
   int rc = make_box_spec(s, dims_host, n_dims, bits, d);
   if (rc) return rc;
@@ -242,6 +242,7 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 6));
   cudaStream_t st = (cudaStream_t)stream;
   phase_mark("box_child_bounds", st);
+  a.keycols = (!a.points && box_dims_vec4(s, a) && keycols && (((uintptr_t)keycols & 15) == 0)) ? keycols : nullptr;
   if (!a.points && box_dims_vec4(s, a)) box_bounds_children_kernel<true><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
   else box_bounds_children_kernel<false><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
   box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);

@@ -317,6 +317,44 @@ def test_partitioned_step_golden(dev):
             assert np.array_equal(got.cpu().numpy(), z[name]), (name, solver.last_path)
 
 
+def test_box_step_key_column_carry(dev):
+    """solver_state hand-over of the packed key columns: a trajectory with the carry is bit-identical
+    to one without, the carry is used from the second step on, and it is dropped when the state
+    tensor handed back is not the one the previous step produced (or was modified in place)."""
+    rs = np.random.default_rng(5)
+    n, d = 4096, 16
+    y0 = cuda((rs.normal(size=(n, d)) * 1.5 + 1.0).astype(np.float32), dev)
+    terms = _terms(d, np.full(d, 2.0, np.float32), np.full(d, 1.0 / 3.0, np.float32), dev)
+
+    def make(carry):
+        solver = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+            mccube.BoxPartitionKernel(n // 16, dims=(4, 5, 6, 7), bits=2), mccube.MonteCarloKernel(16, key=7)))
+        solver.carry_key_columns = carry
+        return solver
+
+    times = dfx.step_times(0.0, 0.05 * 6, 0.05, np.float32)
+    outs = {}
+    for carry in (True, False):
+        solver, y, state, paths = make(carry), y0, None, []
+        for (a, b) in times[:5]:
+            y, _, _, state, _ = solver.step(terms, a, b, y, None, state, False)
+            paths.append(solver.last_path)
+        outs[carry] = y
+        if carry:
+            assert paths[0] == "fused:box_prk_step" and all(q == "fused:box_prk_step+keycols" for q in paths[1:]), paths
+            assert torch.equal(state["mccb200_keycols"], y[:, 4:8])
+            # a different tensor with the same values: no carry
+            solver.step(terms, *times[5], y.clone(), None, state, False)
+            assert solver.last_path == "fused:box_prk_step"
+            # modified in place since: no carry
+            y.add_(0.0)
+            solver.step(terms, *times[5], y, None, state, False)
+            assert solver.last_path == "fused:box_prk_step"
+        else:
+            assert all(q == "fused:box_prk_step" for q in paths), paths
+    assert torch.equal(outs[True], outs[False])
+
+
 # ------------------------------------------------------------------ A11: metrics
 def test_moments_and_w2(dev):
     rs = np.random.default_rng(5)
