@@ -4,13 +4,25 @@
 // (reached from /root/reference/mccube/_kernels/random.py:65) and `jnp.argsort`
 // (/root/reference/mccube/_kernels/stratified.py:43).
 //
-// 8-bit digits.  Per pass three launches:
+// 8-bit digits.  Default form, per pass:
 //   1. rs_histogram : per-tile digit counts -> table[digit][tile]           (reads keys)
 //   2. rs_scan_*    : exclusive scan of the digit-major table               (tiny)
-//   3. rs_scatter   : per-tile stable ranking with warp match_any + per-warp counters,
+//   3. rs_scatter   : per-tile stable ranking with ballot peer masks + per-warp counters,
 //                     re-ordering of the tile in shared memory, then digit-run-coalesced
 //                     stores of keys and values.
+// "Onesweep" form (MCCB200_SORT_MODE=1): one kernel reads the keys once and builds the GLOBAL
+// histogram of every digit position (order independent), then ONE kernel per pass ranks and
+// scatters: a tile's offset inside a digit = sum of that digit's counts in all earlier tiles, found
+// by decoupled look-back over per-(tile, digit) status words (aggregate / inclusive prefix, 64-bit so
+// flag and value travel together), tiles handed out by an atomic ticket so that every predecessor
+// of a running tile is itself running or done.  Bit-identical results, 7 launches instead of 20 per
+// sort, but MEASURED SLOWER at 2^25 pairs (3.98 vs 3.69 ms for the 3-round shuffle): ncu shows the
+// scatter kernel is issue-bound (154 M warp-instructions per pass, 37 % of them the 8 ballots per
+// element that build the peer masks; 2 TB/s of DRAM), so removing the 39 us histogram pass does not
+// pay for the ticket + look-back latency inside every tile.  Left switchable for the next round.
 // Tile order (and therefore stability) is: tile, warp, iteration, lane.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mccb {
@@ -138,11 +150,82 @@ rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __rest
   }
 }
 
-template <bool IOTA_VALUES, bool WRITE_KEYS>
+// ---- onesweep support
+constexpr uint64_t OS_AGG = 1ull << 62, OS_PRE = 2ull << 62, OS_VALUE = (1ull << 56) - 1;   // [63:62] state, [61:56] pass tag
+
+// global digit histograms of all digit positions in one read of the keys: ghist[pass][digit]
+__global__ void __launch_bounds__(256)
+rs_digit_histograms(const uint32_t* __restrict__ keys, uint64_t count, int passes, uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t h[4][RS_RADIX];
+  for (int i = threadIdx.x; i < 4 * RS_RADIX; i += 256) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const bool aligned = (((uintptr_t)keys) & 15) == 0;
+  const int lane = threadIdx.x & 31;
+  for (uint64_t cb = (uint64_t)blockIdx.x * 1024; cb < count; cb += (uint64_t)gridDim.x * 1024) {   // CTA-uniform trip count
+    const uint64_t g0 = cb + (uint64_t)threadIdx.x * 4;
+    uint32_t kv[4] = {0u, 0u, 0u, 0u};
+    int nk = 0;
+    if (aligned && g0 + 3 < count) {
+      const uint4 t = __ldcs(reinterpret_cast<const uint4*>(keys + g0));
+      kv[0] = t.x; kv[1] = t.y; kv[2] = t.z; kv[3] = t.w; nk = 4;
+    } else {
+      for (; nk < 4 && g0 + nk < count; ++nk) kv[nk] = keys[g0 + nk];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = e < nk;
+      for (int ps = 0; ps < passes; ++ps) {
+        const uint32_t dg = ok ? ((kv[e] >> (8 * ps)) & 0xFFu) : 0xFFFFFFFFu;
+        int same;
+        __match_all_sync(0xffffffffu, dg, &same);        // skewed keys (box keys, high digits): one add per warp
+        if (same) { if (ok && lane == 0) atomicAdd(&h[ps][dg], 32u); }
+        else if (ok) atomicAdd(&h[ps][dg], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * RS_RADIX; i += 256)
+    if ((&h[0][0])[i]) atomicAdd(&ghist[i], (&h[0][0])[i]);
+}
+
+// exclusive scan over the 256 digits of every pass (one warp-scan CTA; 32-bit: count < 2^32)
+__global__ void __launch_bounds__(RS_RADIX)
+rs_digit_scan(uint32_t* __restrict__ ghist, int passes) {
+  __shared__ uint32_t wt[8];
+  for (int ps = 0; ps < passes; ++ps) {
+    const uint32_t v = ghist[ps * RS_RADIX + threadIdx.x];
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wt[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += wt[w];
+    ghist[ps * RS_RADIX + threadIdx.x] = off + x - v;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// LOOKBACK = false: `table` holds the scanned per-(digit, tile) offsets (earlier form).
+// LOOKBACK = true : `table` = digit bases of this pass [256]; status / ticket as described on top.
+template <bool IOTA_VALUES, bool WRITE_KEYS, bool LOOKBACK>
 __global__ void __launch_bounds__(RS_THREADS, 3)
 rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t count, int shift,
            uint32_t num_tiles, const uint32_t* __restrict__ table, uint32_t* __restrict__ keys_out,
-           uint32_t* __restrict__ vals_out) {
+           uint32_t* __restrict__ vals_out, uint64_t* __restrict__ status, uint32_t* __restrict__ ticket,
+           uint32_t pass_tag) {
+  __shared__ uint32_t s_ticket;
   __shared__ uint32_t s_keys[RS_TILE];
   __shared__ uint32_t s_vals[RS_TILE];
   __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
@@ -154,7 +237,14 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
   const int warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  for (uint32_t tile_static = blockIdx.x;; tile_static += gridDim.x) {
+    uint32_t tile = tile_static;
+    if (LOOKBACK) {       // tickets: every predecessor of this tile has been taken by a CTA that is running or done
+      if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+      __syncthreads();
+      tile = s_ticket;
+    }
+    if (tile >= num_tiles) break;
     const uint64_t base = (uint64_t)tile * RS_TILE;
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
     __syncthreads();
@@ -200,6 +290,7 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     __syncthreads();
 
     // digit totals + exclusive prefix across warps (thread t owns digit t)
+    uint32_t my_run = 0;
     {
       const int dg = threadIdx.x;
       uint32_t run = 0;
@@ -220,7 +311,16 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
       uint32_t woff = 0;
       for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
       lstart[dg] = woff + x - run;
-      goff[dg] = table[(uint64_t)dg * num_tiles + tile];
+      my_run = run;
+      if (!LOOKBACK) {
+        goff[dg] = table[(uint64_t)dg * num_tiles + tile];
+      } else {
+        // publish this tile's digit count right away; the look-back itself runs after the shared-memory
+        // re-ordering below, which gives the predecessors time to resolve their own prefixes
+        const uint64_t tag = (uint64_t)pass_tag << 56;
+        if (tile == 0) st_status(status + dg, OS_PRE | tag | (uint64_t)run);
+        else st_status(status + (uint64_t)tile * RS_RADIX + dg, OS_AGG | tag | (uint64_t)run);
+      }
     }
     __syncthreads();
 
@@ -234,6 +334,31 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         s_keys[pos] = key[it];
         s_vals[pos] = IOTA_VALUES ? (uint32_t)g : __ldcs(vals_in + g);
       }
+    }
+    if (LOOKBACK) {
+      // decoupled look-back: this digit's count in all earlier tiles
+      const int dg = threadIdx.x;
+      const uint64_t tag = (uint64_t)pass_tag << 56;
+      uint64_t excl = 0;
+      if (tile != 0) {
+        long long t0 = 0;
+        uint32_t spin = 0;
+        for (int64_t tt = (int64_t)tile - 1;;) {
+          const uint64_t wv = ld_status(status + (uint64_t)tt * RS_RADIX + dg);
+          if ((wv >> 62) == 0 || ((wv >> 56) & 0x3Full) != pass_tag) {      // predecessor not there yet
+            if ((++spin & 1023u) == 0) {
+              if (t0 == 0) t0 = clock64();
+              else if (clock64() - t0 > 4000000000ll) __trap();              // a protocol bug, not a slow tile
+            }
+            continue;
+          }
+          excl += wv & OS_VALUE;
+          if ((wv >> 62) == 2) break;
+          --tt;
+        }
+        st_status(status + (uint64_t)tile * RS_RADIX + dg, OS_PRE | tag | (excl + (uint64_t)my_run));
+      }
+      goff[dg] = table[dg] + (uint32_t)excl;
     }
     __syncthreads();
 
@@ -258,8 +383,9 @@ struct SortPlan {
   uint32_t num_tiles;
   uint64_t table_len;
   uint32_t n_chunks;
-  size_t off_tmp_keys, off_tmp_vals, off_alt_keys, off_table, off_sums, total;
+  size_t off_tmp_keys, off_tmp_vals, off_alt_keys, off_table, off_sums, off_ctl, total;
 };
+constexpr size_t OS_CTL_BYTES = 4 * RS_RADIX * 4 + 256;   // ghist[4][256] + tickets[4] (padded)
 
 static SortPlan make_plan(uint64_t count) {
   SortPlan p;
@@ -271,9 +397,10 @@ static SortPlan make_plan(uint64_t count) {
   p.off_tmp_keys = 0;
   p.off_tmp_vals = p.off_tmp_keys + arr;
   p.off_alt_keys = p.off_tmp_vals + arr;
-  p.off_table = p.off_alt_keys + arr;
-  p.off_sums = p.off_table + align_up((size_t)p.table_len * 4, 256);
-  p.total = p.off_sums + align_up((size_t)p.n_chunks * 4, 256);
+  p.off_table = p.off_alt_keys + arr;                     // earlier form: uint32 table; onesweep: uint64 status words
+  p.off_sums = p.off_table + align_up((size_t)p.table_len * 8, 256);
+  p.off_ctl = p.off_sums + align_up((size_t)p.n_chunks * 4, 256);
+  p.total = p.off_ctl + OS_CTL_BYTES;
   return p;
 }
 
@@ -300,6 +427,40 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
   phase_mark("sort_pairs", st);
   const uint32_t* src_k = keys_in;
   const uint32_t* src_v = vals_in;
+  static const bool onesweep = []() { const char* e = getenv("MCCB200_SORT_MODE"); return e && atoi(e) == 1; }();
+  if (onesweep) {
+    uint64_t* status = (uint64_t*)table;
+    uint32_t* ghist = (uint32_t*)(w + p.off_ctl);
+    uint32_t* tickets = ghist + 4 * RS_RADIX;
+    // status words and control block start from zero (stale tags of an earlier call must not match)
+    if (cudaMemsetAsync(status, 0, (size_t)p.table_len * 8, st) != cudaSuccess ||
+        cudaMemsetAsync(ghist, 0, OS_CTL_BYTES, st) != cudaSuccess)
+      return fail(MCCB200_ERR_CUDA, "sort_pairs: memset failed");
+    const int hgrid = (int)min((count + 1023) / 1024, (uint64_t)sm_count() * 8);
+    rs_digit_histograms<<<hgrid, 256, 0, st>>>(keys_in, count, passes, ghist);
+    rs_digit_scan<<<1, RS_RADIX, 0, st>>>(ghist, passes);
+    for (int pass = 0; pass < passes; ++pass) {
+      const bool to_out = ((passes - 1 - pass) % 2) == 0;
+      uint32_t* dst_k = to_out ? out_keys : tmp_keys;
+      uint32_t* dst_v = to_out ? vals_out : tmp_vals;
+      const int shift = pass * 8;
+      const bool last = pass == passes - 1;
+      const bool iota = (src_v == nullptr);
+      const bool write_keys = !(last && keys_out == nullptr);
+      const uint32_t* dbase = ghist + pass * RS_RADIX;
+      uint32_t* tk = tickets + pass;
+      const uint32_t tag = (uint32_t)pass + 1u;
+#define MCCB_OS(I, WK) rs_scatter<I, WK, true><<<grid, RS_THREADS, 0, st>>>(src_k, src_v, count, shift, p.num_tiles, dbase, dst_k, dst_v, status, tk, tag)
+      if (iota) { if (write_keys) MCCB_OS(true, true); else MCCB_OS(true, false); }
+      else { if (write_keys) MCCB_OS(false, true); else MCCB_OS(false, false); }
+#undef MCCB_OS
+      src_k = dst_k;
+      src_v = dst_v;
+    }
+    phase_mark("end", st);
+    count_launches(4 + passes);
+    return check_launch("sort_pairs");
+  }
   for (int pass = 0; pass < passes; ++pass) {
     const bool to_out = ((passes - 1 - pass) % 2) == 0;
     uint32_t* dst_k = to_out ? out_keys : tmp_keys;
@@ -313,11 +474,11 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
     const bool iota = (src_v == nullptr);
     const bool write_keys = !(last && keys_out == nullptr);
     if (iota) {
-      if (write_keys) rs_scatter<true, true><<<grid, RS_THREADS, 0, st>>>(src_k, nullptr, count, shift, p.num_tiles, table, dst_k, dst_v);
-      else rs_scatter<true, false><<<grid, RS_THREADS, 0, st>>>(src_k, nullptr, count, shift, p.num_tiles, table, dst_k, dst_v);
+      if (write_keys) rs_scatter<true, true, false><<<grid, RS_THREADS, 0, st>>>(src_k, nullptr, count, shift, p.num_tiles, table, dst_k, dst_v, nullptr, nullptr, 0u);
+      else rs_scatter<true, false, false><<<grid, RS_THREADS, 0, st>>>(src_k, nullptr, count, shift, p.num_tiles, table, dst_k, dst_v, nullptr, nullptr, 0u);
     } else {
-      if (write_keys) rs_scatter<false, true><<<grid, RS_THREADS, 0, st>>>(src_k, src_v, count, shift, p.num_tiles, table, dst_k, dst_v);
-      else rs_scatter<false, false><<<grid, RS_THREADS, 0, st>>>(src_k, src_v, count, shift, p.num_tiles, table, dst_k, dst_v);
+      if (write_keys) rs_scatter<false, true, false><<<grid, RS_THREADS, 0, st>>>(src_k, src_v, count, shift, p.num_tiles, table, dst_k, dst_v, nullptr, nullptr, 0u);
+      else rs_scatter<false, false, false><<<grid, RS_THREADS, 0, st>>>(src_k, src_v, count, shift, p.num_tiles, table, dst_k, dst_v, nullptr, nullptr, 0u);
     }
     src_k = dst_k;
     src_v = dst_v;
