@@ -33,6 +33,11 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096
 constexpr int RS_RADIX = 256;
 constexpr int SCAN_CHUNK = 4096;  // table entries per CTA in the scan kernels
+// peer masks of equal digits: 8 ballots (0) or one MATCH.ANY (1).  Measured on B200 at 2^25 random keys, 3-round
+// shuffle: ballots 3.69 ms, MATCH.ANY 5.20 ms (it serialises over the ~28 distinct digits a warp holds).
+#ifndef RS_USE_MATCH
+#define RS_USE_MATCH 0
+#endif
 
 __device__ __forceinline__ uint32_t tile_elem(int warp, int it, int lane) {
   return warp * (32 * RS_ITEMS) + it * 32 + lane;
@@ -267,13 +272,18 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
       const uint32_t dg = (key[it] >> shift) & 0xFF;
       // peer mask of equal digits from 8 ballots (fixed cost; MATCH.ANY serialises over the ~30
       // distinct digit values a warp of random keys holds)
-      uint32_t m = __ballot_sync(0xffffffffu, ok);
+      uint32_t m;
+      if (RS_USE_MATCH) {
+        m = __match_any_sync(0xffffffffu, ok ? dg : (0x100u + (uint32_t)lane));
+      } else {
+        m = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const uint32_t vote = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
-        m &= ((dg >> b) & 1u) ? vote : ~vote;
+        for (int b = 0; b < 8; ++b) {
+          const uint32_t vote = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
+          m &= ((dg >> b) & 1u) ? vote : ~vote;
+        }
+        if (!ok) m = 1u << lane;
       }
-      if (!ok) m = 1u << lane;
       const uint32_t leader = __ffs(m) - 1;
       old[it] = 0u;
       if (ok && leader == (uint32_t)lane) old[it] = atomicAdd(&warp_cnt[warp][dg], (uint32_t)__popc(m));
