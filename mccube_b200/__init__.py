@@ -14,6 +14,11 @@ from ._formulae import (
     AbstractCubature as AbstractCubature,
     AbstractGaussianCubature as AbstractGaussianCubature,
     Hadamard as Hadamard,
+    StroudSecrest63_31 as StroudSecrest63_31,
+    StroudSecrest63_32 as StroudSecrest63_32,
+    StroudSecrest63_52 as StroudSecrest63_52,
+    StroudSecrest63_53 as StroudSecrest63_53,
+    search_cubature_registry as search_cubature_registry,
 )
 from ._kernels import (
     AbstractKernel as AbstractKernel,

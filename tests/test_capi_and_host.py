@@ -137,3 +137,66 @@ def test_prk_recombination_count():
     assert mccube.BoxPartitionKernel(8).resolve_dims(64) == (0, 1, 2, 3)
     with pytest.raises(ValueError):
         mccube.BoxPartitionKernel(8, dims=range(8), bits=5).resolve_dims(64)
+
+
+# ------------------------------------------------------------------ cubature formulae (host side)
+def _hermite_monomial(mono):
+    """E[prod x_i^m_i] under N(0, I): 0 if any exponent is odd, else prod (m_i - 1)!!
+    (the closed form the reference test computes with gamma functions, tests/test_formulae.py:181-193)."""
+    from scipy.special import factorial2
+
+    return float(np.prod([0.0 if m % 2 else (1.0 if m == 0 else factorial2(m - 1)) for m in mono]))
+
+
+@pytest.mark.parametrize("name,degree,dims", [
+    ("Hadamard", 3, [1, 2, 3, 4]), ("StroudSecrest63_31", 3, [1, 2, 3, 4]), ("StroudSecrest63_32", 3, [1, 2, 3, 4]),
+    ("StroudSecrest63_52", 5, [2, 3, 4]), ("StroudSecrest63_53", 5, [3, 4]),
+])
+def test_gaussian_cubature_exactness(name, degree, dims):
+    """/root/reference/tests/test_formulae.py:132-161: every monomial of degree <= m integrates
+    exactly; points / weights / point_count are consistent (:20-31)."""
+    from itertools import product
+
+    import mccube_b200 as mccube
+
+    for d in dims:
+        f = getattr(mccube, name)(mccube.GaussianRegion(d))
+        pts = f.points if isinstance(f.points, tuple) else (f.points,)
+        assert f.point_count == sum(q.shape[0] for q in pts) == f.stacked_points.shape[0] == f.stacked_weights.shape[0]
+        assert f.stacked_points.shape[1] == d and f.degree == degree
+        for mono in product(range(degree + 1), repeat=d):
+            if sum(mono) > degree:
+                continue
+            got, vals = f(lambda x: float(np.prod(x ** np.array(mono))))
+            assert abs(got - _hermite_monomial(mono)) <= 1e-5 * abs(_hermite_monomial(mono)) + 1e-8, (name, d, mono)
+            assert vals.shape == (f.point_count,)
+
+
+def test_cubature_registry_search_and_permutations():
+    """/root/reference/tests/test_formulae.py:34-129."""
+    import mccube_b200 as mccube
+    from mccube_b200._formulae import _generate_point_permutations, builtin_cubature_registry
+
+    assert builtin_cubature_registry == mccube.all_subclasses(mccube.AbstractCubature)
+    pool = {mccube.Hadamard, mccube.StroudSecrest63_31, mccube.StroudSecrest63_32, mccube.StroudSecrest63_52}
+    region = mccube.GaussianRegion(5)
+    cases = [
+        ((None, False, False), ["StroudSecrest63_31", "Hadamard", "StroudSecrest63_32", "StroudSecrest63_52"]),
+        ((3, False, False), ["StroudSecrest63_31", "Hadamard", "StroudSecrest63_32"]),
+        ((3, False, True), ["StroudSecrest63_31"]),
+        ((3, True, False), ["StroudSecrest63_31"]),
+        ((5, True, True), ["StroudSecrest63_52"]),
+    ]
+    for (deg, sparse, minimal), want in cases:
+        got = mccube.search_cubature_registry(region, deg, sparse, minimal, pool)
+        assert [type(f).__name__ for f in got] == want and all(f.region is region for f in got)
+    assert [type(f).__name__ for f in mccube.search_cubature_registry(region, 3, False, True)] == ["StroudSecrest63_31"]
+    with pytest.raises(ValueError, match="only valid for regions with d > 2"):
+        mccube.StroudSecrest63_53(mccube.GaussianRegion(2))
+    fs = _generate_point_permutations(np.array([3, 0, 0]), "FS")
+    assert np.array_equal(fs, [[-3, 0, 0], [0, -3, 0], [0, 0, -3], [0, 0, 3], [0, 3, 0], [3, 0, 0]])
+    assert np.array_equal(_generate_point_permutations(np.array([3, 0, 0]), "S"), fs[3:])
+    rr = _generate_point_permutations(np.array([3, 3, 3]), "R")
+    assert np.array_equal(rr, [[-3, -3, -3], [-3, -3, 3], [-3, 3, -3], [-3, 3, 3], [3, -3, -3], [3, -3, 3], [3, 3, -3], [3, 3, 3]])
+    with pytest.raises(ValueError):
+        _generate_point_permutations(np.ones(2), "X")

@@ -211,6 +211,39 @@ def test_table_cubature_and_generic_kernel_protocol(dev):
     assert solver.last_path.startswith("generic") and np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("name", ["StroudSecrest63_31", "StroudSecrest63_32", "StroudSecrest63_52", "StroudSecrest63_53"])
+def test_stroud_secrest_formulae_steps(dev, name):
+    """Every Gaussian formula of the reference (tests/test_solvers.py:67 parametrises over them) through
+    the table-cubature path of the fused kernel: unweighted step bit-exact vs the oracle, weighted step
+    (non-uniform lambda for 5-2 / 5-3, quirk Q3) with weights summing to one."""
+    n, d = 24, 3
+    yy, mean, inv_var = _setup(n, d, seed=11)
+    formula = getattr(mccube, name)(mccube.GaussianRegion(d))
+    k = formula.point_count
+    M, lam = formula.stacked_points, formula.stacked_weights.astype(np.float64)
+    drift = lambda y: ref.gaussian_diag_drift(y, mean, inv_var)  # noqa: E731
+    f = mccube.GaussianDiagDrift(mean, 1.0 / inv_var.astype(np.float64), device=dev)
+    f.inv_var, f.mean = cuda(inv_var, dev), cuda(mean, dev)
+    terms = mccube.MCCTerm(dfx.ODETerm(f), dfx.WeaklyDiagonalControlTerm(
+        lambda t, y, args: math.sqrt(2.0), mccube.LocalLinearCubaturePath(formula)))
+    t0, t1 = np.float32(0.2), np.float32(0.25)
+    want = ref.mcc_step(yy, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, key=jr.prng_key(3)))
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=3))
+    got, *_ = solver.step(terms, t0, t1, cuda(yy, dev), None, None, False)
+    assert solver.last_path.startswith("fused") and got.shape == (n, d)
+    assert np.array_equal(got.cpu().numpy(), want), (name, k)
+
+    w0 = np.random.default_rng(4).uniform(0.5, 1.5, size=n).astype(np.float32)
+    yw = ref.pack_particles(yy, w0)
+    want_w = ref.mcc_step(yw, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, key=jr.prng_key(3)), weighted=True)
+    solver_w = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=3), weighted=True)
+    got_w, *_ = solver_w.step(terms, t0, t1, cuda(yw, dev), None, None, False)
+    got_w = got_w.cpu().numpy()
+    assert got_w.shape == (n, d + 1) and abs(got_w[:, -1].sum() - 1.0) < 1e-5
+    assert np.array_equal(got_w[:, :-1], want_w[:, :-1])
+    np.testing.assert_allclose(got_w[:, -1], want_w[:, -1], rtol=1e-5, atol=1e-8)
+
+
 def test_substeps_and_weighted_step(dev):
     """n_substeps=2 and the weighted state layout (quirk Q3) through the generic path
     (/root/reference/tests/test_solvers.py:93-125)."""
