@@ -33,7 +33,7 @@ from ._kernels import (
 from ._path import LocalLinearCubaturePath
 from ._formulae import Hadamard
 from ._term import MCCTerm
-from ._utils import pack_particles, unpack_particles
+from ._utils import nop, pack_particles, unpack_particles
 from .diffrax_compat import (
     AbstractSolver,
     AbstractWrappedSolver,
@@ -154,12 +154,18 @@ class MCCSolver(AbstractWrappedSolver):
 
         fusable = (self.fused and self.n_substeps == 1 and not self.weighted)
         y1_hat = None
-        if fusable and type(kernel) is MonteCarloKernel and isinstance(kernel.recombination_count, int):
-            drift, cub, dt, k, d = self._describe(terms, y0c, *times[0], args)
+        # weighted states with the default weighting_function=nop sample uniformly (quirk Q6): the fused
+        # kernel carries the weight column along (child weight = w_parent * lambda, k-major quirk Q3)
+        fusable_mc = (self.fused and self.n_substeps == 1 and type(kernel) is MonteCarloKernel
+                      and isinstance(kernel.recombination_count, int)
+                      and (not self.weighted or kernel.weighting_function is nop))
+        if fusable_mc:
+            yv = y0c[:, :-1] if self.weighted else y0c
+            drift, cub, dt, k, d = self._describe(terms, yv, *times[0], args)
             n = y0c.shape[0]
             idx = kernel.indices(t0, n * k, kernel.recombination_count, y0c.device)
-            y1_hat = _lib.expand_select(y0c, d, False, drift, dt, cub, idx)
-            self.last_path = "fused:mc_indices+expand_select"
+            y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
+            self.last_path = "fused:mc_indices+expand_select" + ("(weighted)" if self.weighted else "")
         elif (fusable and type(kernel) is PartitioningRecombinationKernel
               and type(kernel.partitioning_kernel) is BoxPartitionKernel
               and type(kernel.recombination_kernel) is MonteCarloKernel

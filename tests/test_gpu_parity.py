@@ -238,10 +238,17 @@ def test_stroud_secrest_formulae_steps(dev, name):
     want_w = ref.mcc_step(yw, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, key=jr.prng_key(3)), weighted=True)
     solver_w = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=3), weighted=True)
     got_w, *_ = solver_w.step(terms, t0, t1, cuda(yw, dev), None, None, False)
+    assert solver_w.last_path == "fused:mc_indices+expand_select(weighted)"
     got_w = got_w.cpu().numpy()
     assert got_w.shape == (n, d + 1) and abs(got_w[:, -1].sum() - 1.0) < 1e-5
     assert np.array_equal(got_w[:, :-1], want_w[:, :-1])
     np.testing.assert_allclose(got_w[:, -1], want_w[:, -1], rtol=1e-5, atol=1e-8)
+    # the generic (materialising) path gives the same weighted step
+    solver_g = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=3), weighted=True, fused=False)
+    got_g, *_ = solver_g.step(terms, t0, t1, cuda(yw, dev), None, None, False)
+    assert solver_g.last_path.startswith("generic")
+    assert np.array_equal(got_g.cpu().numpy()[:, :-1], got_w[:, :-1])
+    np.testing.assert_allclose(got_g.cpu().numpy()[:, -1], got_w[:, -1], rtol=1e-5, atol=1e-8)
 
 
 def test_substeps_and_weighted_step(dev):
