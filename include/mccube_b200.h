@@ -143,6 +143,14 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
                           uint64_t out_per_part, uint64_t in_per_part, uint64_t n_out, float* y1,
                           void* stream);
 
+/* The same with n_substeps inner Euler steps fused (MCCSolver(..., n_substeps=s), mccube/_solvers.py:127-136):
+ * child c = ((i*k + j_1)*k + j_2)..., y <- y + (dts[s] * f(y) + scales[s] * M[j_s, :]) for s = 0..n_substeps-1,
+ * the drift re-evaluated at every intermediate state.  Hadamard cubature, drift kinds 0 / 2 (an array drift
+ * is only known at the parents), unweighted, n * k^n_substeps <= 2^32.  dts / scales are HOST arrays. */
+MCCB200_API int mccb200_expand_select_substeps(const float* y0, uint64_t n, int d, const mccb200_drift* drift,
+                                               int n_substeps, const float* dts_host, const float* scales_host,
+                                               int k, const uint32_t* idx, uint64_t n_out, float* y1, void* stream);
+
 /* Materialise the full [n*k, ld] expansion (what _solvers.py:136 builds).  Only for the
  * generic kernel protocol (user-defined recombination kernels) and for parity tests. */
 MCCB200_API int mccb200_expand_all(const float* y0, uint64_t n, int d, int weighted, const mccb200_drift* drift,
@@ -167,6 +175,7 @@ MCCB200_API int mccb200_stratified_keys(const float* p, uint64_t n, int d, int l
  * bounds = device [2 * n_dims]: lo[0..), inv_h[0..).  mccb200_box_bounds fills it with
  * the bounding box of the rows (lo = min, inv_h = 2^bits / (max - min)). */
 #define MCCB200_BOX_MAX_DIMS 8
+#define MCCB200_MAX_SUBSTEPS 4
 MCCB200_API int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int32_t* dims_host, int n_dims, int bits,
                        float* bounds, void* workspace, size_t workspace_bytes, void* stream);
 MCCB200_API size_t mccb200_box_bounds_workspace_bytes(void);

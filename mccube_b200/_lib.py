@@ -67,6 +67,9 @@ _SIGNATURES = {
     "mccb200_expand_select": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                         C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                         C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_expand_select_substeps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_int,
+                                                 C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p,
+                                                 C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_expand_all": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                      C.POINTER(Cubature), C.c_void_p, C.c_void_p]),
     "mccb200_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -277,6 +280,22 @@ def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=No
     _check(lib.mccb200_expand_select(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
                                      C.byref(cub), idx.data_ptr(), _ptr(perm), out_per_part, in_per_part, n_out,
                                      out.data_ptr(), _stream()), "expand_select")
+    return out
+
+
+def expand_select_substeps(y0, d, drift: Drift, dts, scales, k, idx):
+    """Fused n_substeps > 1 step (Hadamard, drift kind 0 / 2): only the selected children of the k^s
+    expansion are computed."""
+    lib = load()
+    _require_cuda(y0, idx)
+    _f32c(y0)
+    s = len(dts)
+    arr_dt = (C.c_float * s)(*[float(np.float32(x)) for x in dts])
+    arr_sc = (C.c_float * s)(*[float(np.float32(x)) for x in scales])
+    out = torch.empty((idx.numel(), y0.shape[1]), dtype=torch.float32, device=y0.device)
+    _check(lib.mccb200_expand_select_substeps(y0.data_ptr(), y0.shape[0], d, C.byref(drift), s, arr_dt, arr_sc, int(k),
+                                              idx.data_ptr(), idx.numel(), out.data_ptr(), _stream()),
+           "expand_select_substeps")
     return out
 
 

@@ -166,6 +166,8 @@ class MCCSolver(AbstractWrappedSolver):
             idx = kernel.indices(t0, n * k, kernel.recombination_count, y0c.device)
             y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
             self.last_path = "fused:mc_indices+expand_select" + ("(weighted)" if self.weighted else "")
+        elif self._substeps_fusable(terms, kernel, y0c):
+            y1_hat = self._substeps_step(terms, t0, times, y0c, args, kernel)
         elif (fusable and type(kernel) is PartitioningRecombinationKernel
               and type(kernel.partitioning_kernel) is BoxPartitionKernel
               and type(kernel.recombination_kernel) is MonteCarloKernel
@@ -181,6 +183,35 @@ class MCCSolver(AbstractWrappedSolver):
             y1_res = y1_hat
         dense_info = dict(y0=y0, y1=y1_hat)
         return y1_res, None, dense_info, solver_state, RESULTS.successful
+
+    MAX_FUSED_SUBSTEPS = 4
+
+    def _substeps_fusable(self, terms, kernel, y0c) -> bool:
+        """n_substeps in 2..4 with the Hadamard formula, no drift or the analytic diagonal-Gaussian drift
+        (an arbitrary callable is only evaluated on arrays, i.e. at materialised intermediate states),
+        unweighted, global MonteCarloKernel, and at most 2^32 children."""
+        if not (self.fused and 1 < self.n_substeps <= self.MAX_FUSED_SUBSTEPS and not self.weighted):
+            return False
+        if type(kernel) is not MonteCarloKernel or not isinstance(kernel.recombination_count, int):
+            return False
+        if not isinstance(terms, MCCTerm) or not isinstance(terms.cde.control, LocalLinearCubaturePath):
+            return False
+        cubature = terms.cde.control.gaussian_cubature
+        if not isinstance(cubature, Hadamard) or not isinstance(terms.ode.vector_field, GaussianDiagDrift):
+            return False
+        return y0c.shape[0] * cubature.point_count ** self.n_substeps <= 2 ** 32
+
+    def _substeps_step(self, terms, t0, times, y0c, args, kernel):
+        """All inner Euler steps in one kernel: only the selected children of the k^s expansion are computed."""
+        dts, scales = [], []
+        for (a, b) in times:
+            drift, cub, dt, k, d = self._describe(terms, y0c, a, b, args)
+            dts.append(dt)
+            scales.append(cub.scale)
+        n = y0c.shape[0]
+        idx = kernel.indices(t0, n * k ** self.n_substeps, kernel.recombination_count, y0c.device)
+        self.last_path = f"fused:mc_indices+expand_select(substeps={self.n_substeps})"
+        return _lib.expand_select_substeps(y0c, d, drift, dts, scales, k, idx)
 
     @staticmethod
     def _carried_keycols(solver_state, y0c, dims):

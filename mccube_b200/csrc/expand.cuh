@@ -23,6 +23,11 @@ struct ExpandArgs {
   uint32_t out_per_part, in_per_part;
   uint64_t n_out;
   float* y1;
+  // n_substeps > 1 (Hadamard, drift kinds 0 / 2 only): child c = ((i*k + j_1)*k + j_2)... ; substep s
+  // adds dt_sub[s] * f(y_s) + sign(j_s) * scale_sub[s] to the running state (MCCSolver.step loop,
+  // mccube/_solvers.py:132-136).  n_sub == 1 uses dt / scale above.
+  int n_sub;
+  float dt_sub[MCCB200_MAX_SUBSTEPS], scale_sub[MCCB200_MAX_SUBSTEPS];
   const float* keycols;   // optional [n, 4]: y0[:, c0 .. c0+3] of the 4 vectorised box key columns, packed
   float* keycols_out;     // optional [n_out, 4]: the same columns of y1, written by the expand kernel
   int keycol0;            // c0 of keycols_out

@@ -97,7 +97,11 @@ expand_kernel(const ExpandArgs a) {
     uint32_t pi[EX_UNROLL], pj[EX_UNROLL];
 #pragma unroll
     for (int u = 0; u < EX_UNROLL; ++u) {
-      if (a.k_shift != 0xFFFFFFFFu) {
+      if (a.n_sub > 1) {                                   // k^n_sub children per parent (k a power of two)
+        const uint32_t sh = a.k_shift * (uint32_t)a.n_sub;
+        pi[u] = sh >= 32u ? 0u : (c[u] >> sh);
+        pj[u] = sh >= 32u ? c[u] : (c[u] & ((1u << sh) - 1u));
+      } else if (a.k_shift != 0xFFFFFFFFu) {
         pi[u] = c[u] >> a.k_shift;
         pj[u] = c[u] & (a.k - 1u);
       } else {
@@ -124,8 +128,19 @@ expand_kernel(const ExpandArgs a) {
         float noise;
         if (TABLE) noise = tab[e];
         else noise = hadamard_neg(pj[u], a.half_mask, (uint32_t)(col + e)) ? -a.scale : a.scale;
-        float step = __fadd_rn(__fmul_rn(a.dt, fv), noise);
-        out[e] = __fadd_rn(y[u][e], step);
+        if (!TABLE && DRIFT != 1 && a.n_sub > 1) {           // fused sub-steps (warp-uniform branch)
+          float yy = y[u][e];
+          for (int sb = 0; sb < a.n_sub; ++sb) {
+            const uint32_t j = (pj[u] >> (a.k_shift * (uint32_t)(a.n_sub - 1 - sb))) & (a.k - 1u);
+            const float fs = DRIFT == 2 ? __fmul_rn(__fsub_rn(mean[e], yy), ivar[e]) : 0.0f;
+            const float ns = hadamard_neg(j, a.half_mask, (uint32_t)(col + e)) ? -a.scale_sub[sb] : a.scale_sub[sb];
+            yy = __fadd_rn(yy, __fadd_rn(__fmul_rn(a.dt_sub[sb], fs), ns));
+          }
+          out[e] = yy;
+        } else {
+          float step = __fadd_rn(__fmul_rn(a.dt, fv), noise);
+          out[e] = __fadd_rn(y[u][e], step);
+        }
       }
       store_vec_stream<VEC>(a.y1 + r[u] * a.ld + col, out);
       if (VEC == 4 && a.keycols_out != nullptr && col == a.keycol0)      // packed key columns for the next step's partitioner
@@ -211,6 +226,7 @@ int fill_expand_args(ExpandArgs& a, const float* y0, uint64_t n, int d, int weig
   a.y0 = y0; a.n = n; a.d = d; a.ld = d + (weighted ? 1 : 0); a.weighted = weighted;
   a.drift_kind = drift->kind; a.f = drift->f; a.mean = drift->mean; a.inv_var = drift->inv_var;
   a.dt = dt;
+  a.n_sub = 1;
   a.k = (uint32_t)cub->k;
   const bool pow2 = (a.k & (a.k - 1u)) == 0;
   a.k_shift = 0xFFFFFFFFu;
@@ -270,6 +286,28 @@ extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int wei
     MCCB_REQUIRE(out_per_part < 0x100000000ull && in_per_part < 0x100000000ull, "expand_select: partition too large");
   }
   a.idx = idx; a.perm = perm; a.out_per_part = (uint32_t)out_per_part; a.in_per_part = (uint32_t)in_per_part;
+  a.n_out = n_out; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_expand_select_substeps(const float* y0, uint64_t n, int d, const mccb200_drift* drift,
+                                              int n_substeps, const float* dts_host, const float* scales_host,
+                                              int k, const uint32_t* idx, uint64_t n_out, float* y1, void* stream) {
+  MCCB_REQUIRE(n_substeps >= 1 && n_substeps <= MCCB200_MAX_SUBSTEPS && dts_host && scales_host,
+               "expand_select_substeps: n_substeps=%d out of range [1, %d]", n_substeps, MCCB200_MAX_SUBSTEPS);
+  mccb200_cubature cub{};
+  cub.k = k; cub.points = nullptr; cub.scale = scales_host[0]; cub.lam = nullptr;
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, 0, drift, dts_host[0], &cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(drift->kind != 1, "expand_select_substeps: an array drift is only known at the parents (use the generic path)");
+  MCCB_REQUIRE(idx && y1, "expand_select_substeps: NULL idx / y1");
+  long double total = (long double)n;
+  for (int sb = 0; sb < n_substeps; ++sb) total *= (long double)k;
+  MCCB_REQUIRE(total <= 4294967296.0L, "expand_select_substeps: n*k^s exceeds 2^32 child ids");
+  a.n_sub = n_substeps;
+  for (int sb = 0; sb < n_substeps; ++sb) { a.dt_sub[sb] = dts_host[sb]; a.scale_sub[sb] = scales_host[sb]; }
+  a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
   a.n_out = n_out; a.y1 = y1;
   return run_expand(a, (cudaStream_t)stream);
 }

@@ -251,6 +251,26 @@ def test_stroud_secrest_formulae_steps(dev, name):
     np.testing.assert_allclose(got_g.cpu().numpy()[:, -1], got_w[:, -1], rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("n,d,s,replace", [(16, 3, 2, False), (40, 3, 3, True), (9, 8, 2, False), (5, 4, 4, False),
+                                            (64, 10, 2, True)])
+def test_fused_substeps_step(dev, n, d, s, replace):
+    """n_substeps > 1 fused into one kernel (only the selected children of the k^s expansion are
+    computed, drift re-evaluated at every intermediate state) == oracle == materialising path."""
+    yy, mean, inv_var = _setup(n, d, seed=20 + s)
+    drift = lambda y: ref.gaussian_diag_drift(y, mean, inv_var)  # noqa: E731
+    M, lam = ref.hadamard_points(d), ref.hadamard_weights(d)
+    t0, t1 = np.float32(0.3), np.float32(0.35)
+    want = ref.mcc_step(yy, t0, t1, drift, M, lam, SQRT2, ref.MonteCarloKernel(n, replace, key=jr.prng_key(7)),
+                        n_substeps=s)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=7), n_substeps=s)
+    got, *_ = solver.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(yy, dev), None, None, False)
+    assert solver.last_path == f"fused:mc_indices+expand_select(substeps={s})"
+    assert np.array_equal(got.cpu().numpy(), want)
+    generic = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=7), n_substeps=s, fused=False)
+    got_g, *_ = generic.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(yy, dev), None, None, False)
+    assert generic.last_path.startswith("generic") and torch.equal(got, got_g)
+
+
 def test_substeps_and_weighted_step(dev):
     """n_substeps=2 and the weighted state layout (quirk Q3) through the generic path
     (/root/reference/tests/test_solvers.py:93-125)."""
