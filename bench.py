@@ -341,6 +341,56 @@ def extra_workloads(dev, peak_gbs):
     return out
 
 
+def sharded_global_mc(dev, rank, world, steps=5):
+    """N > 1 only: the global MonteCarloKernel(with_replacement=True) resample over all ranks' particles
+    (SURVEY.md 8e): `step` = one variable-size NCCL all-to-all, shards bit-identical to the single-device
+    step; `step_owner` = owner-computes, only the binomial imbalance crosses the links.  "strong-ish":
+    2^21 (8 ranks) or 2^22 particles per rank, d = 64, so that n_tot * k stays below 2^32 child ids."""
+    import torch
+    import torch.distributed as dist
+
+    import mccube_b200 as mccube
+    from mccube_b200 import diffrax_compat as dfx
+    from mccube_b200._distributed import ShardedMonteCarloStep
+
+    d = 64
+    n_loc = 1 << (21 if world > 4 else 22)
+    n_tot = n_loc * world
+    terms = mccube.MCCTerm(
+        dfx.ODETerm(mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev)),
+        dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                      mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+    sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)), terms, world)
+    times = dfx.step_times(0.0, DT0 * (steps + 4), DT0, np.float32)
+    gen = torch.Generator(device=dev)
+    out = {"n_per_gpu": n_loc, "d": d, "n_gpus": world}
+    for name in ("step", "step_owner"):
+        gen.manual_seed(11 + rank)
+        ys = torch.randn((n_loc, d), generator=gen, device=dev)
+
+        def one(i, ys):
+            r = getattr(sh, name)(times[i][0], times[i][1], ys, rank)
+            return r[0] if isinstance(r, tuple) else r
+
+        for i in range(3):
+            ys = one(i, ys)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(3, 3 + steps):
+            ys = one(i, ys)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3)}
+        del ys
+    out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
+    out["note"] = ("step: NCCL all-to-all of the selected children, shards bit-identical to the single-device step; "
+                   "step_owner: owner-computes, only the imbalance is exchanged (row order differs by the exported slot map)")
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -453,6 +503,17 @@ def main():
                "ms_per_step": ms_e / Ke, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4}
         del host_in, host_out
 
+    sharded = None
+    if world > 1 and not a.no_extras:
+        del y
+        torch.cuda.empty_cache()
+        _lib.release_workspace()
+        try:
+            sharded = sharded_global_mc(dev, rank, world)
+        except Exception as e:  # noqa: BLE001
+            sharded = {"error": repr(e)}
+        y = None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,6 +551,8 @@ def main():
                     "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9), "all_kernels": kernels}
 
     extras = None
+    if world > 1:
+        extras = {"sharded_global_mc": sharded} if sharded is not None else None
     if world == 1 and not a.no_extras and a.workload == "box_prk":
         del y
         torch.cuda.empty_cache()
