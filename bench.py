@@ -351,7 +351,7 @@ def sharded_global_mc(dev, rank, world, steps=5):
 
     import mccube_b200 as mccube
     from mccube_b200 import diffrax_compat as dfx
-    from mccube_b200._distributed import ShardedMonteCarloStep
+    from mccube_b200._distributed import PeerShards, ShardedMonteCarloStep
 
     d = 64
     n_loc = 1 << (21 if world > 4 else 22)
@@ -364,11 +364,14 @@ def sharded_global_mc(dev, rank, world, steps=5):
     times = dfx.step_times(0.0, DT0 * (steps + 4), DT0, np.float32)
     gen = torch.Generator(device=dev)
     out = {"n_per_gpu": n_loc, "d": d, "n_gpus": world}
-    for name in ("step", "step_owner"):
+    shards = PeerShards(n_loc, d, rank, world, dev)
+    for name in ("step_p2p", "step", "step_owner"):
         gen.manual_seed(11 + rank)
         ys = torch.randn((n_loc, d), generator=gen, device=dev)
 
         def one(i, ys):
+            if name == "step_p2p":
+                return sh.step_p2p(times[i][0], times[i][1], ys, rank, shards)
             r = getattr(sh, name)(times[i][0], times[i][1], ys, rank)
             return r[0] if isinstance(r, tuple) else r
 
@@ -385,8 +388,11 @@ def sharded_global_mc(dev, rank, world, steps=5):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[name] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3)}
         del ys
+    shards.close()
     out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
-    out["note"] = ("step: NCCL all-to-all of the selected children, shards bit-identical to the single-device step; "
+    out["note"] = ("step_p2p: fused expand + scatter into the destination rank's shard over NVLink peer memory (no "
+                   "collective in the data path, no host sync), shards bit-identical to the single-device step; "
+                   "step: the same through a send buffer + NCCL all-to-all; "
                    "step_owner: owner-computes, only the imbalance is exchanged (row order differs by the exported slot map)")
     return out
 

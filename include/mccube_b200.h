@@ -278,6 +278,29 @@ MCCB200_API int mccb200_shard_send_ids(const uint32_t* idx, const uint32_t* orde
 MCCB200_API int mccb200_scatter_rows(const float* in, int ld, const uint32_t* slots, uint64_t slot_offset,
                                      uint64_t n_rows, float* out, void* stream);
 
+/* Fused expand + exchange for the sharded resample: every selected child of this rank's parents is
+ * written straight into the output shard of the rank that stores its slot,
+ *     peer_out[slot / rows_per_rank][(slot % rows_per_rank), :] = child(idx[slot]),
+ * for the slots order[start .. start + count) of this rank's group (start / count are read on the device
+ * from the replicated counts matrix, so the host never synchronises).  peer_out is a DEVICE array of
+ * n_ranks pointers into peer memory (CUDA IPC mappings over NVLink; the own shard is an ordinary
+ * pointer).  The caller separates steps with a cross-rank barrier.  Hadamard cubature only. */
+/* Peer shards for mccb200_expand_scatter_peers: cudaMalloc buffers exchanged between the ranks of a node as
+ * 64-byte CUDA IPC handles; peer_open (importer's device current) maps the exporter's buffer for kernels of
+ * the importing device. */
+MCCB200_API int mccb200_peer_alloc(size_t bytes, void** ptr);
+MCCB200_API int mccb200_peer_free(void* ptr);
+MCCB200_API int mccb200_peer_export(const void* ptr, unsigned char* handle64);
+MCCB200_API int mccb200_peer_open(const unsigned char* handle64, void** ptr);
+MCCB200_API int mccb200_peer_close(void* ptr);
+/* Lets kernels of the current device dereference memory of `peer_device` (needed once per peer before
+ * mccb200_expand_scatter_peers; IPC mappings opened by another library do not imply it). */
+MCCB200_API int mccb200_enable_peer_access(int peer_device);
+MCCB200_API int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                                             const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
+                                             const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
+                                             float* const* peer_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

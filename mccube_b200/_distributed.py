@@ -122,6 +122,53 @@ def exchange_rows(send_buf: torch.Tensor, send_splits, recv_splits, group=None) 
     return recv
 
 
+class PeerShards:
+    """Two ping-pong output shards per rank, every rank's shards mapped into every other rank's address
+    space (cudaMalloc buffers + CUDA IPC handles gathered over the process group; the importer opens
+    them with cudaIpcMemLazyEnablePeerAccess, i.e. NVLink peer loads / stores from its kernels).
+    `ptrs[b]` is an int64 device tensor with the base pointer of buffer b on every rank."""
+
+    def __init__(self, n_loc: int, d: int, rank: int, world: int, device, group=None):
+        from . import _lib
+
+        self.rank, self.world, self.group = rank, world, group
+        self.local = [_lib.peer_alloc((n_loc, d), device) for _ in range(2)]
+        handles = [_lib.peer_export(t) for t in self.local]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.opened, self.ptrs = [], []
+        for b in range(2):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(self.local[b].data_ptr())
+                else:
+                    ptr = _lib.peer_open(gathered[r][b], device)
+                    self.opened.append(ptr)
+                    row.append(ptr)
+            self.ptrs.append(torch.tensor(row, dtype=torch.int64, device=device))
+        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.turn = 0
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier (a 4-byte all-reduce: synchronisation only, no data path)."""
+        dist.all_reduce(self.flag, group=self.group)
+
+    def close(self):
+        """Unmaps the peers' buffers and frees the own ones (every rank must have stopped using them)."""
+        from . import _lib
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for ptr in self.opened:
+            _lib.peer_close(ptr)
+        self.opened = []
+        dist.barrier(group=self.group)
+        for t in self.local:
+            _lib.peer_free(t)
+        self.local = []
+
+
 class ShardedMonteCarloStep:
     """One MCCSolver step with a GLOBAL MonteCarloKernel resample over row-sharded particles.
 
@@ -174,6 +221,36 @@ class ShardedMonteCarloStep:
         if self.n_ranks == 1:
             return self.place(send_buf, placement)
         return self.place(exchange_rows(send_buf, send_splits, recv_splits, group), placement)
+
+    # ---- fused expand + exchange over peer memory: no send buffer, no collective in the data path
+    def step_p2p(self, t0, t1, y_shard: torch.Tensor, rank: int, shards: PeerShards) -> torch.Tensor:
+        """Same result as `step` (shards bit-identical to the single-device step), but the gather kernel
+        writes every selected child directly into the output shard of the rank that stores its slot
+        (NVLink peer stores), and nothing is synchronised with the host: the block of slots this rank
+        materialises is read on the device from the replicated counts matrix.  `y_shard` must not be
+        the ping-pong buffer this call writes (it alternates; feed the returned tensor back in)."""
+        import math
+
+        from . import _lib
+
+        solver, kernel = self.solver, self.solver.recombination_kernel
+        n_loc, d = y_shard.shape
+        n_tot = n_loc * self.n_ranks
+        if kernel.recombination_count != n_tot:
+            raise ValueError(f"MonteCarloKernel.recombination_count must be the GLOBAL particle count {n_tot}")
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        idx = kernel.indices(t0, n_tot * k, n_tot, y_shard.device)            # replicated, deterministic
+        keys, counts_dev = _lib.shard_owner_keys(idx, n_loc, k, self.n_ranks)
+        order = _lib.sort_pairs(keys, None, max(1, math.ceil(math.log2(self.n_ranks))))
+        b = shards.turn
+        out = shards.local[b]
+        if out.data_ptr() == y_shard.data_ptr():
+            raise ValueError("step_p2p: the input is the buffer this step writes; feed the previous result back in")
+        _lib.expand_scatter_peers(y_shard.contiguous(), d, drift, dt, cub, idx, order, counts_dev, rank, self.n_ranks,
+                                  n_loc, shards.ptrs[b])
+        shards.barrier()          # every rank's rows have landed (and nobody still reads the other buffer)
+        shards.turn ^= 1
+        return out
 
     # ---- owner-computes variant: no row leaves its rank except the binomial imbalance
     def prepare_owner(self, t0, t1, y_shard: torch.Tensor, rank: int):

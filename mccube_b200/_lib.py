@@ -70,6 +70,15 @@ _SIGNATURES = {
     "mccb200_expand_select_substeps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_int,
                                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p,
                                                  C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_expand_scatter_peers": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                               C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
+    "mccb200_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mccb200_peer_free": (C.c_int, [C.c_void_p]),
+    "mccb200_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mccb200_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mccb200_peer_close": (C.c_int, [C.c_void_p]),
     "mccb200_expand_all": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                      C.POINTER(Cubature), C.c_void_p, C.c_void_p]),
     "mccb200_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -297,6 +306,62 @@ def expand_select_substeps(y0, d, drift: Drift, dts, scales, k, idx):
                                               idx.data_ptr(), idx.numel(), out.data_ptr(), _stream()),
            "expand_select_substeps")
     return out
+
+
+class _DevicePtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+def peer_alloc(shape, device) -> torch.Tensor:
+    """float32 tensor over a plain cudaMalloc buffer (IPC-exportable, outside torch's caching allocator)."""
+    lib = load()
+    nbytes = 4 * int(np.prod(shape))
+    ptr = C.c_void_p()
+    with torch.cuda.device(device):
+        _check(lib.mccb200_peer_alloc(nbytes, C.byref(ptr)), "peer_alloc")
+        return torch.as_tensor(_DevicePtr(ptr.value, shape), device=device)
+
+
+def peer_export(t: torch.Tensor) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(load().mccb200_peer_export(t.data_ptr(), buf), "peer_export")
+    return buf.raw
+
+
+def peer_open(handle: bytes, device) -> int:
+    """Maps a peer's buffer for kernels of `device`; returns the device pointer."""
+    ptr = C.c_void_p()
+    with torch.cuda.device(device):
+        _check(load().mccb200_peer_open(handle, C.byref(ptr)), "peer_open")
+    return int(ptr.value)
+
+
+def peer_close(ptr: int):
+    _check(load().mccb200_peer_close(C.c_void_p(ptr)), "peer_close")
+
+
+def peer_free(t: torch.Tensor):
+    _check(load().mccb200_peer_free(C.c_void_p(t.data_ptr())), "peer_free")
+
+
+def enable_peer_access(peer_device: int):
+    _check(load().mccb200_enable_peer_access(int(peer_device)), "enable_peer_access")
+
+
+def expand_scatter_peers(y0, d, drift: Drift, dt, cub: Cubature, idx, order, counts, rank, n_ranks, rows_per_rank,
+                         peer_ptrs):
+    """Fused expand + exchange: the selected children of this rank's parents go straight into the
+    shards `peer_ptrs` (int64 device tensor of n_ranks base pointers) over peer memory."""
+    lib = load()
+    _require_cuda(y0, idx, order, counts, peer_ptrs)
+    _f32c(y0)
+    _check(lib.mccb200_expand_scatter_peers(y0.data_ptr(), y0.shape[0], d, C.byref(drift), float(np.float32(dt)),
+                                            C.byref(cub), idx.data_ptr(), order.data_ptr(), counts.data_ptr(), int(rank),
+                                            int(n_ranks), int(rows_per_rank), peer_ptrs.data_ptr(), _stream()),
+           "expand_scatter_peers")
 
 
 def expand_all(y0, d, weighted, drift: Drift, dt, cub: Cubature):

@@ -28,6 +28,15 @@ struct ExpandArgs {
   // mccube/_solvers.py:132-136).  n_sub == 1 uses dt / scale above.
   int n_sub;
   float dt_sub[MCCB200_MAX_SUBSTEPS], scale_sub[MCCB200_MAX_SUBSTEPS];
+  // Multi-GPU scatter form (expand_scatter_peers): output row q of THIS rank is slot
+  // sc_order[start + q] of the global result, start / count read on the device from the replicated
+  // counts matrix; the child is written straight into the shard of the rank that stores the slot
+  // (peer memory over NVLink), no send buffer, no collective.
+  const uint32_t* sc_order;   // [n_tot] output slots grouped by owner rank (ascending slot inside a group)
+  const uint32_t* sc_counts;  // [G][G] counts[owner][dest]
+  float* const* sc_peers;     // [G] base pointer of every rank's output shard
+  uint32_t sc_rank, sc_G;
+  uint64_t sc_rows_per_rank, sc_child_offset;
   const float* keycols;   // optional [n, 4]: y0[:, c0 .. c0+3] of the 4 vectorised box key columns, packed
   float* keycols_out;     // optional [n_out, 4]: the same columns of y1, written by the expand kernel
   int keycol0;            // c0 of keycols_out

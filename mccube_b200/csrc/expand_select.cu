@@ -66,13 +66,23 @@ __device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r
   return a.idx ? a.idx[r] : (uint32_t)r;
 }
 
-template <int VEC, int DRIFT, bool TABLE>
+template <int VEC, int DRIFT, bool TABLE, bool SCATTER = false>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const ExpandArgs a) {
   const int row_in_iter = threadIdx.x / a.vpr;
   const int col = (threadIdx.x - row_in_iter * a.vpr) * VEC;
   const bool active = row_in_iter < a.rows_per_iter;
   if (!active) return;
+  uint64_t n_out = a.n_out, sc_start = 0;
+  if (SCATTER) {   // this rank's block of the owner-grouped slot list, from the replicated counts matrix
+    uint64_t run = 0;
+    for (uint32_t o = 0; o <= a.sc_rank; ++o) {
+      uint64_t per = 0;
+      for (uint32_t dd = 0; dd < a.sc_G; ++dd) per += __ldg(a.sc_counts + o * a.sc_G + dd);
+      if (o < a.sc_rank) run += per; else n_out = per;
+    }
+    sc_start = run;
+  }
 
   float mean[VEC], ivar[VEC];
   if (DRIFT == 2) {
@@ -82,16 +92,23 @@ expand_kernel(const ExpandArgs a) {
   const bool do_w = a.weighted && col == 0;
 
   const uint64_t rows_per_cta_iter = (uint64_t)a.rows_per_iter * EX_UNROLL;
-  for (uint64_t base = (uint64_t)blockIdx.x * rows_per_cta_iter; base < a.n_out;
+  for (uint64_t base = (uint64_t)blockIdx.x * rows_per_cta_iter; base < n_out;
        base += (uint64_t)gridDim.x * rows_per_cta_iter) {
     uint32_t c[EX_UNROLL];
     uint64_t r[EX_UNROLL];
     bool ok[EX_UNROLL];
+    uint32_t slot[EX_UNROLL];
 #pragma unroll
     for (int u = 0; u < EX_UNROLL; ++u) {
       r[u] = base + (uint64_t)u * a.rows_per_iter + row_in_iter;
-      ok[u] = r[u] < a.n_out;
-      c[u] = ok[u] ? child_of_row(a, r[u]) : 0u;
+      ok[u] = r[u] < n_out;
+      if (SCATTER) {
+        slot[u] = ok[u] ? __ldg(a.sc_order + sc_start + r[u]) : 0u;
+        c[u] = ok[u] ? (uint32_t)((uint64_t)__ldg(a.idx + slot[u]) - a.sc_child_offset) : 0u;
+      } else {
+        slot[u] = 0u;
+        c[u] = ok[u] ? child_of_row(a, r[u]) : 0u;
+      }
     }
     float y[EX_UNROLL][VEC], f[EX_UNROLL][VEC];
     uint32_t pi[EX_UNROLL], pj[EX_UNROLL];
@@ -141,6 +158,12 @@ expand_kernel(const ExpandArgs a) {
           float step = __fadd_rn(__fmul_rn(a.dt, fv), noise);
           out[e] = __fadd_rn(y[u][e], step);
         }
+      }
+      if (SCATTER) {   // straight into the destination rank's shard (peer memory)
+        const uint32_t dest = (uint32_t)(slot[u] / a.sc_rows_per_rank);
+        const uint64_t row = slot[u] - (uint64_t)dest * a.sc_rows_per_rank;
+        store_vec_stream<VEC>(a.sc_peers[dest] + row * a.ld + col, out);
+        continue;
       }
       store_vec_stream<VEC>(a.y1 + r[u] * a.ld + col, out);
       if (VEC == 4 && a.keycols_out != nullptr && col == a.keycol0)      // packed key columns for the next step's partitioner
@@ -206,6 +229,12 @@ static int pick_vec(int d, int ld, const void* p0, const void* p1) {
 template <int VEC>
 static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
   const bool table = a.points != nullptr;
+  if (a.sc_peers) {   // scatter form: Hadamard only
+    if (a.drift_kind == 2) expand_kernel<VEC, 2, false, true><<<grid, EX_THREADS, 0, st>>>(a);
+    else if (a.drift_kind == 1) expand_kernel<VEC, 1, false, true><<<grid, EX_THREADS, 0, st>>>(a);
+    else expand_kernel<VEC, 0, false, true><<<grid, EX_THREADS, 0, st>>>(a);
+    return;
+  }
 #define MCCB_LAUNCH(D, T) expand_kernel<VEC, D, T><<<grid, EX_THREADS, 0, st>>>(a)
   if (a.drift_kind == 2) { if (table) MCCB_LAUNCH(2, true); else MCCB_LAUNCH(2, false); }
   else if (a.drift_kind == 1) { if (table) MCCB_LAUNCH(1, true); else MCCB_LAUNCH(1, false); }
@@ -287,6 +316,28 @@ extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int wei
   }
   a.idx = idx; a.perm = perm; a.out_per_part = (uint32_t)out_per_part; a.in_per_part = (uint32_t)in_per_part;
   a.n_out = n_out; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                                            const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
+                                            const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
+                                            float* const* peer_out, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n_loc, d, 0, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(idx && order && counts && peer_out, "expand_scatter_peers: NULL argument");
+  MCCB_REQUIRE(n_ranks >= 1 && n_ranks <= 64 && rank >= 0 && rank < n_ranks && rows_per_rank >= 1,
+               "expand_scatter_peers: rank %d / %d", rank, n_ranks);
+  if (cub->points != nullptr) return fail(MCCB200_ERR_UNSUPPORTED, "expand_scatter_peers: Hadamard cubature only");
+  MCCB_REQUIRE(rows_per_rank * (uint64_t)n_ranks * (uint64_t)cub->k <= 0x100000000ull,
+               "expand_scatter_peers: n_tot * k exceeds 2^32 child ids");
+  a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
+  a.sc_order = order; a.sc_counts = counts; a.sc_peers = peer_out;
+  a.sc_rank = (uint32_t)rank; a.sc_G = (uint32_t)n_ranks;
+  a.sc_rows_per_rank = rows_per_rank; a.sc_child_offset = (uint64_t)rank * n_loc * (uint64_t)cub->k;
+  a.n_out = rows_per_rank + rows_per_rank / 8 + 1024;   // grid sizing only: the true count is read on the device
+  a.y1 = const_cast<float*>(y0);                        // alignment probe only (never written in this form)
   return run_expand(a, (cudaStream_t)stream);
 }
 

@@ -5,6 +5,8 @@
 // rank because it is a pure function of (key, t)) says which child lands in which output slot.
 //   owner(s) = parent(idx[s]) / n_loc   -- the rank that can materialise slot s without moving data
 //   dest(s)  = s / n_loc                -- the rank that stores output slot s
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mccb {
@@ -52,6 +54,54 @@ scatter_rows_kernel(const float* __restrict__ in, int ld, const uint32_t* __rest
 }  // namespace mccb
 
 using namespace mccb;
+
+// ---- peer shards: plain cudaMalloc buffers shared between the ranks of one node through CUDA IPC.
+// The importer opens a handle with ITS device current and cudaIpcMemLazyEnablePeerAccess, which maps
+// the exporter's memory for kernels of the importing device (NVLink peer loads / stores).
+extern "C" int mccb200_peer_alloc(size_t bytes, void** ptr) {
+  MCCB_REQUIRE(ptr && bytes > 0, "peer_alloc: bad argument");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return fail(MCCB200_ERR_CUDA, "peer_alloc: %s", cudaGetErrorString(e));
+  return MCCB200_OK;
+}
+extern "C" int mccb200_peer_free(void* ptr) {
+  if (ptr && cudaFree(ptr) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "peer_free failed");
+  return MCCB200_OK;
+}
+extern "C" int mccb200_peer_export(const void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  MCCB_REQUIRE(ptr && handle64, "peer_export: NULL argument");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(ptr));
+  if (e != cudaSuccess) return fail(MCCB200_ERR_CUDA, "peer_export: %s", cudaGetErrorString(e));
+  memcpy(handle64, &h, 64);
+  return MCCB200_OK;
+}
+extern "C" int mccb200_peer_open(const unsigned char* handle64, void** ptr) {
+  MCCB_REQUIRE(ptr && handle64, "peer_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(MCCB200_ERR_CUDA, "peer_open: %s", cudaGetErrorString(e));
+  return MCCB200_OK;
+}
+extern "C" int mccb200_peer_close(void* ptr) {
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "peer_close failed");
+  return MCCB200_OK;
+}
+
+extern "C" int mccb200_enable_peer_access(int peer_device) {
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "enable_peer_access: no current device");
+  if (cur == peer_device) return MCCB200_OK;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can)
+    return fail(MCCB200_ERR_UNSUPPORTED, "enable_peer_access: device %d cannot access device %d", cur, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MCCB200_OK; }
+  if (e != cudaSuccess) return fail(MCCB200_ERR_CUDA, "enable_peer_access: %s", cudaGetErrorString(e));
+  return MCCB200_OK;
+}
 
 extern "C" int mccb200_shard_owner_keys(const uint32_t* idx, uint64_t n_tot, uint64_t n_loc, int k, int n_ranks,
                                         uint32_t* keys, uint32_t* counts, void* stream) {

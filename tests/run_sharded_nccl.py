@@ -16,7 +16,7 @@ import torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import mccube_b200 as mccube  # noqa: E402
 from mccube_b200 import diffrax_compat as dfx  # noqa: E402
-from mccube_b200._distributed import ShardedMonteCarloStep  # noqa: E402
+from mccube_b200._distributed import PeerShards, ShardedMonteCarloStep  # noqa: E402
 
 
 def terms_for(d, dev):
@@ -52,6 +52,20 @@ def main():
         sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, rep, key=42)), terms, world)
         got = sh.step(t0, t1, y[rank * n_loc:(rank + 1) * n_loc].contiguous(), rank)
         assert torch.equal(got, want[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: sharded != single (replace={rep})"
+    # fused expand + exchange over peer memory (no collective in the data path): same shards, two steps
+    # so that both ping-pong buffers are exercised
+    for rep in (False, True):
+        single = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, rep, key=42))
+        want1, *_ = single.step(terms, t0, t1, y, None, None, False)
+        want2, *_ = single.step(terms, t1, np.float32(0.35), want1, None, None, False)
+        sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, rep, key=42)), terms, world)
+        shards = PeerShards(n_loc, d, rank, world, dev)
+        got1 = sh.step_p2p(t0, t1, y[rank * n_loc:(rank + 1) * n_loc].contiguous(), rank, shards)
+        assert torch.equal(got1, want1[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: p2p step 1 != single (replace={rep})"
+        got2 = sh.step_p2p(t1, np.float32(0.35), got1, rank, shards)
+        assert torch.equal(got2, want2[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: p2p step 2 != single (replace={rep})"
+        del got1, got2
+        shards.close()
     # owner-computes variant: rows equal the single-device result through the exported slot map
     want, *_ = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)).step(
         terms, t0, t1, y, None, None, False)
@@ -92,7 +106,24 @@ def main():
     torch.cuda.synchronize(); dist.barrier()
     ms_o = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms_o, op=dist.ReduceOp.MAX)
+    # fused p2p timing
+    gen.manual_seed(11 + rank)
+    yp = torch.randn((n_loc, d), generator=gen, device=dev)
+    shards = PeerShards(n_loc, d, rank, world, dev)
+    for i in range(3):
+        yp = sh.step_p2p(times[i][0], times[i][1], yp, rank, shards)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for i in range(3, 3 + a.steps):
+        yp = sh.step_p2p(times[i][0], times[i][1], yp, rank, shards)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms_p = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms_p, op=dist.ReduceOp.MAX)
     if rank == 0:
+        print(json.dumps({"variant": "fused expand + peer-memory scatter (no collective in the data path), bit-exact shards",
+                          "n_gpus": world, "n_per_gpu": n_loc, "d": d, "ms_per_step": float(ms_p) / a.steps,
+                          "particle_steps_per_sec": n_tot * a.steps / (float(ms_p) * 1e-3)}))
         print(json.dumps({"variant": "owner-computes (imbalance exchange only)", "n_gpus": world, "n_per_gpu": n_loc, "d": d,
                           "ms_per_step": float(ms_o) / a.steps,
                           "particle_steps_per_sec": n_tot * a.steps / (float(ms_o) * 1e-3)}))

@@ -574,6 +574,32 @@ def test_sharded_monte_carlo_step_emulated_ranks(dev, replace):
     assert torch.equal(torch.cat(outs), want)
 
 
+@pytest.mark.parametrize("replace", [False, True])
+def test_sharded_p2p_scatter_emulated_ranks(dev, replace):
+    """Fused expand + scatter-to-peers kernel with the ranks emulated on one GPU (every "peer" shard is a
+    local tensor): the shards written by all ranks together equal the single-device step bit for bit."""
+    import math as _m
+
+    G, n_loc, d = 4, 256, 12
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=23)
+    terms = _terms(d, mean, inv_var, dev)
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    yt = cuda(y, dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, replace, key=42))
+    want, *_ = solver.step(terms, t0, t1, yt, None, None, False)
+    shards = [torch.full((n_loc, d), float("nan"), device=dev) for _ in range(G)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards], dtype=torch.int64, device=dev)
+    for r in range(G):
+        ys = yt[r * n_loc:(r + 1) * n_loc].contiguous()
+        drift, cub, dt, k, _ = solver._describe(terms, ys, *solver.substep_times(t0, t1)[0], None)
+        idx = solver.recombination_kernel.indices(t0, n_tot * k, n_tot, dev)
+        keys, counts = _lib.shard_owner_keys(idx, n_loc, k, G)
+        order = _lib.sort_pairs(keys, None, max(1, _m.ceil(_m.log2(G))))
+        _lib.expand_scatter_peers(ys, d, drift, dt, cub, idx, order, counts, r, G, n_loc, ptrs)
+    assert torch.equal(torch.cat(shards), want)
+
+
 def test_sharded_owner_computes_emulated_ranks(dev):
     """Owner-computes variant: only the imbalance is exchanged; rows equal the single-device
     result after applying the exported slot map (a permutation of all output slots)."""
