@@ -66,9 +66,13 @@ __device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r
   return a.idx ? a.idx[r] : (uint32_t)r;
 }
 
-template <int VEC, int DRIFT, bool TABLE, bool SCATTER = false>
+// MODE 0: plain (the hot path: nothing below costs it an instruction); 1: scatter to peer shards;
+// 2: fused sub-steps.
+template <int VEC, int DRIFT, bool TABLE, int MODE = 0>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const ExpandArgs a) {
+  constexpr bool SCATTER = MODE == 1;
+  constexpr bool SUBSTEPS = MODE == 2;
   const int row_in_iter = threadIdx.x / a.vpr;
   const int col = (threadIdx.x - row_in_iter * a.vpr) * VEC;
   const bool active = row_in_iter < a.rows_per_iter;
@@ -114,7 +118,7 @@ expand_kernel(const ExpandArgs a) {
     uint32_t pi[EX_UNROLL], pj[EX_UNROLL];
 #pragma unroll
     for (int u = 0; u < EX_UNROLL; ++u) {
-      if (a.n_sub > 1) {                                   // k^n_sub children per parent (k a power of two)
+      if (SUBSTEPS) {                                      // k^n_sub children per parent (k a power of two)
         const uint32_t sh = a.k_shift * (uint32_t)a.n_sub;
         pi[u] = sh >= 32u ? 0u : (c[u] >> sh);
         pj[u] = sh >= 32u ? c[u] : (c[u] & ((1u << sh) - 1u));
@@ -145,7 +149,7 @@ expand_kernel(const ExpandArgs a) {
         float noise;
         if (TABLE) noise = tab[e];
         else noise = hadamard_neg(pj[u], a.half_mask, (uint32_t)(col + e)) ? -a.scale : a.scale;
-        if (!TABLE && DRIFT != 1 && a.n_sub > 1) {           // fused sub-steps (warp-uniform branch)
+        if (SUBSTEPS && !TABLE && DRIFT != 1) {              // fused sub-steps
           float yy = y[u][e];
           for (int sb = 0; sb < a.n_sub; ++sb) {
             const uint32_t j = (pj[u] >> (a.k_shift * (uint32_t)(a.n_sub - 1 - sb))) & (a.k - 1u);
@@ -230,9 +234,14 @@ template <int VEC>
 static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
   const bool table = a.points != nullptr;
   if (a.sc_peers) {   // scatter form: Hadamard only
-    if (a.drift_kind == 2) expand_kernel<VEC, 2, false, true><<<grid, EX_THREADS, 0, st>>>(a);
-    else if (a.drift_kind == 1) expand_kernel<VEC, 1, false, true><<<grid, EX_THREADS, 0, st>>>(a);
-    else expand_kernel<VEC, 0, false, true><<<grid, EX_THREADS, 0, st>>>(a);
+    if (a.drift_kind == 2) expand_kernel<VEC, 2, false, 1><<<grid, EX_THREADS, 0, st>>>(a);
+    else if (a.drift_kind == 1) expand_kernel<VEC, 1, false, 1><<<grid, EX_THREADS, 0, st>>>(a);
+    else expand_kernel<VEC, 0, false, 1><<<grid, EX_THREADS, 0, st>>>(a);
+    return;
+  }
+  if (a.n_sub > 1) {  // fused sub-steps: Hadamard, drift kinds 0 / 2 (checked by the caller)
+    if (a.drift_kind == 2) expand_kernel<VEC, 2, false, 2><<<grid, EX_THREADS, 0, st>>>(a);
+    else expand_kernel<VEC, 0, false, 2><<<grid, EX_THREADS, 0, st>>>(a);
     return;
   }
 #define MCCB_LAUNCH(D, T) expand_kernel<VEC, D, T><<<grid, EX_THREADS, 0, st>>>(a)
