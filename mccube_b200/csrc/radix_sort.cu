@@ -500,6 +500,68 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
 
 size_t sort_pairs_ws(uint64_t count) { return make_plan(count).total; }
 
+// ---- first `top` entries of the stable sort, top << count (the last round of jax.random._shuffle
+// feeds permutation(...)[:n]): one stable pass on the MOST significant byte over everything, then
+// a full stable LSD sort of a prefix of `u` elements that contains the `top` smallest.  u = top +
+// two average bucket sizes: for the uniform 32-bit keys of the shuffle the bucket holding rank top-1
+// ends inside that prefix with overwhelming probability; a device-side check traps otherwise (a loud
+// failure instead of a wrong permutation).
+__global__ void __launch_bounds__(RS_RADIX)
+rs_top_check(const uint32_t* __restrict__ table, uint32_t num_tiles, uint64_t count, uint64_t top, uint64_t u) {
+  __shared__ uint32_t base[RS_RADIX + 1];
+  base[threadIdx.x] = table[(uint64_t)threadIdx.x * num_tiles];   // scanned table: start of digit = offset of its tile 0
+  if (threadIdx.x == 0) base[RS_RADIX] = (uint32_t)count;
+  __syncthreads();
+  // the bucket that holds rank top-1 must end inside the prefix
+  if ((uint64_t)base[threadIdx.x] <= top - 1 && top - 1 < (uint64_t)base[threadIdx.x + 1] &&
+      (uint64_t)base[threadIdx.x + 1] > u)
+    __trap();
+}
+
+static uint64_t top_prefix(uint64_t count, uint64_t top) {
+  uint64_t u = top + 2 * ((count + RS_RADIX - 1) / RS_RADIX) + 4096;
+  return u < count ? u : count;
+}
+
+bool sort_pairs_top_worthwhile(uint64_t count, uint64_t top) {
+  return count >= (1ull << 20) && top_prefix(count, top) <= count / 4;
+}
+
+size_t sort_pairs_top_ws(uint64_t count, uint64_t top) {
+  SortPlan p = make_plan(count);
+  return p.total + 2 * align_up((size_t)count * 4, 256) + make_plan(top_prefix(count, top)).total;
+}
+
+// vals_out must hold top_prefix(count, top) entries; its first `top` are the result.
+int sort_pairs_top_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t count, uint64_t top,
+                        uint32_t* vals_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MCCB_REQUIRE(count < 0xFFFFFFFFull && top >= 1 && top <= count, "sort_pairs_top: bad sizes");
+  const uint64_t u = top_prefix(count, top);
+  SortPlan p = make_plan(count);
+  const size_t arr = align_up((size_t)count * 4, 256);
+  if (ws_bytes < sort_pairs_top_ws(count, top))
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "sort_pairs_top: workspace %zu < %zu", ws_bytes, sort_pairs_top_ws(count, top));
+  char* w = (char*)ws;
+  uint32_t* table = (uint32_t*)(w + p.off_table);
+  uint32_t* sums = (uint32_t*)(w + p.off_sums);
+  uint32_t* msd_keys = (uint32_t*)(w + p.total);
+  uint32_t* msd_vals = (uint32_t*)(w + p.total + arr);
+  void* inner_ws = w + p.total + 2 * arr;
+  const size_t inner_bytes = ws_bytes - (p.total + 2 * arr);
+  const int grid = (int)min((uint64_t)p.num_tiles, (uint64_t)sm_count() * 8);
+  phase_mark("sort_pairs", st);
+  rs_histogram<<<grid, RS_THREADS, 0, st>>>(keys_in, count, 24, p.num_tiles, table);
+  rs_scan_reduce<<<p.n_chunks, 256, 0, st>>>(table, p.table_len, sums);
+  rs_scan_sums<<<1, 1024, 0, st>>>(sums, p.n_chunks);
+  rs_scan_apply<<<p.n_chunks, 256, 0, st>>>(table, p.table_len, sums);
+  rs_top_check<<<1, RS_RADIX, 0, st>>>(table, p.num_tiles, count, top, u);
+  if (vals_in) rs_scatter<false, true, false><<<grid, RS_THREADS, 0, st>>>(keys_in, vals_in, count, 24, p.num_tiles, table, msd_keys, msd_vals, nullptr, nullptr, 0u);
+  else rs_scatter<true, true, false><<<grid, RS_THREADS, 0, st>>>(keys_in, nullptr, count, 24, p.num_tiles, table, msd_keys, msd_vals, nullptr, nullptr, 0u);
+  count_launches(6);
+  // stable LSD sort of the prefix by the full key (ties keep the MSD pass's = the input's order)
+  return sort_pairs_impl(msd_keys, msd_vals, u, 32, nullptr, vals_out, inner_ws, inner_bytes, st);
+}
+
 }  // namespace mccb
 
 extern "C" size_t mccb200_sort_pairs_workspace_bytes(uint64_t count) { return mccb::sort_pairs_ws(count); }

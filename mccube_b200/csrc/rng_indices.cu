@@ -14,6 +14,9 @@ namespace mccb {
 int sort_pairs_impl(const uint32_t*, const uint32_t*, uint64_t, int, uint32_t*, uint32_t*, void*, size_t,
                     cudaStream_t);
 size_t sort_pairs_ws(uint64_t);
+bool sort_pairs_top_worthwhile(uint64_t count, uint64_t top);
+size_t sort_pairs_top_ws(uint64_t count, uint64_t top);
+int sort_pairs_top_impl(const uint32_t*, const uint32_t*, uint64_t, uint64_t, uint32_t*, void*, size_t, cudaStream_t);
 
 __global__ void derive_keys_kernel(mccb200_rng rng, int rounds, DerivedKeys* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -157,10 +160,12 @@ static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
     p.off_keys = cur; cur += arr;
     p.off_va = cur; cur += arr;
     p.off_vb = cur; cur += arr;
-    p.off_sort = cur; cur += sort_pairs_ws(n_inputs);
+    p.off_sort = cur;
+    size_t sw = sort_pairs_ws(n_inputs);
+    if (count >= 1 && sort_pairs_top_worthwhile(n_inputs, count)) sw = max(sw, sort_pairs_top_ws(n_inputs, count));
+    cur += sw;
   }
   p.total = cur;
-  (void)count;
   return p;
 }
 
@@ -231,7 +236,10 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   uint32_t* dst = va;
   for (int r = 0; r < p.rounds; ++r) {
     random_bits_kernel<<<grid, 256, 0, st>>>(dk, r, n, rng->partitionable, keys);
-    int rc = sort_pairs_impl(keys, src, n, 32, nullptr, dst, sort_ws, sort_ws_bytes, st);
+    // only permutation[:count] is used: the last round needs just the `count` smallest keys in order
+    const bool top_only = r == p.rounds - 1 && sort_pairs_top_worthwhile(n, count);
+    int rc = top_only ? sort_pairs_top_impl(keys, src, n, count, dst, sort_ws, sort_ws_bytes, st)
+                      : sort_pairs_impl(keys, src, n, 32, nullptr, dst, sort_ws, sort_ws_bytes, st);
     if (rc) return rc;
     src = dst;
     dst = (dst == va) ? vb : va;

@@ -66,6 +66,18 @@ def test_mc_indices_config2_size_properties(dev):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_mc_indices_truncated_last_round(dev, partitionable):
+    """Large inputs with count << n_inputs: the last shuffle round only orders the `count` smallest keys
+    (one MSD pass + a sort of a short prefix); bit-exact vs the oracle's full shuffle, ragged size."""
+    P, n = (1 << 21) + 123, 1 << 15
+    rng = _lib.make_rng(KEY, 0.15, partitionable=partitionable)
+    got = u32(_lib.mc_indices(rng, P, n, False, dev))
+    want = jr.choice_indices(jr.mc_step_key(jr.prng_key(42), 0.15, partitionable=partitionable), P, n, False,
+                             partitionable=partitionable)
+    assert np.array_equal(got, want)
+
+
 def test_sort_pairs_stable(dev):
     rs = np.random.default_rng(0)
     for n, hi, bits in [(1, 10, 32), (31, 4, 8), (4096, 1 << 32, 32), (4097, 256, 8), (100003, 1 << 12, 12),
