@@ -468,6 +468,18 @@ def main():
     ms_step = ms_total / K
     value = world * n * K / (ms_total * 1e-3)
 
+    # ---- sampling quality of the state the timed steps produced: Gaussian 2-Wasserstein distance to the target
+    w2_final = None
+    if rank == 0:
+        try:
+            import mccube_b200 as mccube
+
+            m_t, c_t = mccube.mean_and_cov(y)
+            w2 = mccube.gaussian_wasserstein_metric((np.full(d, TARGET_MEAN), m_t), (TARGET_VAR * np.eye(d), c_t))
+            w2_final = float(np.real(w2))
+        except Exception as e:  # noqa: BLE001
+            w2_final = repr(e)
+
     # ---- per-phase timing of the same step (library events on the launching stream)
     phases = {}
     if rank == 0:
@@ -618,7 +630,8 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "path": path, "n_per_gpu": n, "d": d,
                    "l2": "state is 4 GiB per array (>> 126 MB L2): no flush between iterations",
-                   "threefry_partitionable": False, "phase_ms_per_step": phase_ms},
+                   "threefry_partitionable": False, "phase_ms_per_step": phase_ms,
+                   "w2_to_target_after_timed_steps": w2_final, "t_final": float(times[W + K - 1][1])},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }

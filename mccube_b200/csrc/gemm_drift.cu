@@ -11,23 +11,26 @@
 // parity bar is 1e-5).  prec is split once (mccb200_gaussian_full_drift_tc_prepare), the
 // particle tile is centred and split in shared memory by converter warps.
 //
-// Kernel anatomy (persistent, one CTA per SM, 10 warps, warp-specialised).  A CTA tile is
-// 256 particles (two M = 128 accumulators sharing every prec tile: the prec traffic from L2 per
-// flop is half that of an M = 128 tile) x NT <= 256 output columns; the k-step is 16 fp32 (one
-// 64-byte swizzle row), 64 KB per stage, 3 stages:
-//   warp 0      TMA producer : Y tile [256 x 16] + prec_hi / prec_lo tiles [NT x 16] per k-step,
-//                              64-byte swizzle, mbarrier complete_tx
-//   warps 2-5   converter    : a = y - mean; hi = rn_tf32(a); lo = rn_tf32(a - hi), written back
-//                              to the (swizzled) stage buffers; fence.proxy.async; arrive
-//   warp 1      MMA issuer   : one thread issues 12 tcgen05.mma (M128 x N256 x K8, a_negate) per
-//                              k-step into the two TMEM accumulators, tcgen05.commit frees the stage
-//   warps 6-9   epilogue     : tcgen05.ld 32x32b.x32 -> 128-byte row segments of F; TMA / converter
-//                              keep filling stages meanwhile, and the second accumulator drains
-//                              while the next tile's first MMAs run on the first
-// Roofline: 3 * 2 n d^2 flop on the TF32 pipe (128 cycles per M128 N256 K8 instruction, 1536 per
-// k-step) against 48 KB per k-step through L2 (~31 B/cycle/SM, under the ~42 B/cycle/SM L2 cap).
-// First version of this kernel (M = 128 tile, 32-float k-step, 2 stages of 96 KB) measured 3.29 ms
-// at n = 2^20, d = 512: bound by its 53 B/cycle/SM of L2 traffic and the 2-deep ring.
+// Kernel anatomy (persistent, one CTA per SM, clusters of two CTAs = one CTA-pair UMMA, 14 warps,
+// warp-specialised).  A pair tile is 256 particles (128 per CTA) x NT <= 256 output columns; each
+// CTA holds its particles and HALF of every prec tile (the tensor cores of the pair read both halves);
+// the k-step is 32 fp32 (one 128-byte swizzle row), 64 KB per stage, 3 stages:
+//   warp 0      TMA producer : Y tile [128 x 32] + this CTA's half of the prec_hi / prec_lo tiles
+//                              [NT/2 x 32] per k-step, 128-byte swizzle, mbarrier complete_tx
+//   warps 2-9   converter    : two groups of 4 warps on alternate stages: a = y - mean; hi = rn_tf32(a);
+//                              lo = rn_tf32(a - hi), written back to the (swizzled) stage buffers;
+//                              fence.proxy.async; group barrier; ONE remote arrive on the leader's barrier
+//   warp 1      MMA issuer   : one thread of the LEADER CTA issues 12 tcgen05.mma.cta_group::2
+//                              (M256 x N256 x K8, a_negate) per k-step; tcgen05.commit ... multicast frees
+//                              the stage in both CTAs and publishes the accumulators
+//   warps 10-13 epilogue     : tcgen05.ld 16x256b.x8 -> 8 rows x 32-byte sectors of F straight from
+//                              registers; the TMEM accumulator is double-buffered (2 x 256 columns), so
+//                              the epilogue of a tile overlaps the main loop of the next
+// What bounds it (knock-out runs, clock64 stage tracer, eleven variants: profiles/README.md): 3 * 2 n d^2
+// flop on the TF32 pipe would take 1536 cycles per k-step; the stage period follows the shared-memory
+// bytes per stage (operand reads of the three products 96 KB + converter 50 KB + TMA fills 48 KB at
+// 128 B/cycle).  Measured 2.30 ms at n = 2^20, d = 512 = 718 TFLOP/s on the pipe, 74 % tensor-pipe active.
+// TMA moves a box row by row (~2.5-4 cycles per row): 64- and 32-byte rows starved the ring.
 // Accuracy: the tensor core truncates (round-toward-zero) at every accumulation, a bias of
 // ~2^-24 per K = 8 instruction: measured max error 7.6e-6 (d = 512) / 1.3e-5 (d = 1024) of max|F|.
 #include <cuda.h>
