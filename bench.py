@@ -365,11 +365,15 @@ def sharded_global_mc(dev, rank, world, steps=5):
     gen = torch.Generator(device=dev)
     out = {"n_per_gpu": n_loc, "d": d, "n_gpus": world}
     shards = PeerShards(n_loc, d, rank, world, dev)
-    for name in ("step_p2p", "step", "step_owner"):
+    for name in ("step_pull", "step_p2p", "step", "step_owner"):
         gen.manual_seed(11 + rank)
         ys = torch.randn((n_loc, d), generator=gen, device=dev)
+        if name == "step_pull":
+            shards.load(ys)
 
         def one(i, ys):
+            if name == "step_pull":
+                return sh.step_pull(times[i][0], times[i][1], rank, shards)
             if name == "step_p2p":
                 return sh.step_p2p(times[i][0], times[i][1], ys, rank, shards)
             r = getattr(sh, name)(times[i][0], times[i][1], ys, rank)
@@ -390,7 +394,10 @@ def sharded_global_mc(dev, rank, world, steps=5):
         del ys
     shards.close()
     out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
-    out["note"] = ("step_p2p: fused expand + scatter into the destination rank's shard over NVLink peer memory (no "
+    out["note"] = ("step_pull: every rank draws only its own slice of the (counter-based) index vector and the gather "
+                   "kernel reads the selected parents from the owners' shards over NVLink peer memory: O(n_loc) work per "
+                   "rank, no collective in the data path, bit-identical shards; "
+                   "step_p2p: fused expand + scatter into the destination rank's shard over NVLink peer memory (no "
                    "collective in the data path, no host sync), shards bit-identical to the single-device step; "
                    "step: the same through a send buffer + NCCL all-to-all; "
                    "step_owner: owner-computes, only the imbalance is exchanged (row order differs by the exported slot map)")

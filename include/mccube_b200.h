@@ -293,6 +293,18 @@ MCCB200_API int mccb200_peer_free(void* ptr);
 MCCB200_API int mccb200_peer_export(const void* ptr, unsigned char* handle64);
 MCCB200_API int mccb200_peer_open(const unsigned char* handle64, void** ptr);
 MCCB200_API int mccb200_peer_close(void* ptr);
+/* Pull form of the same exchange for with_replacement=True: this rank draws only the indices of the output
+ * slots it stores (mccb200_mc_indices_slice: the draws are counter based) and the gather kernel reads every
+ * selected parent from the shard of the rank that owns it,
+ *     y1[q, :] = child(idx[q]) with parent row peer_in[p / rows_per_rank][p % rows_per_rank, :],  p = idx[q] / k
+ * (NVLink peer loads).  No index replication, no grouping pass, per-rank work O(n_loc).  Hadamard, drift kinds
+ * 0 / 2.  peer_in: DEVICE array of n_ranks pointers to the INPUT shards (all of rows_per_rank rows). */
+MCCB200_API int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, uint64_t first,
+                                         uint64_t slice, uint32_t* idx_out, void* workspace, size_t workspace_bytes,
+                                         void* stream);
+MCCB200_API int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, uint64_t rows_per_rank, int d,
+                                            const mccb200_drift* drift, float dt, const mccb200_cubature* cub,
+                                            const uint32_t* idx, uint64_t n_out, float* y1, void* stream);
 /* Lets kernels of the current device dereference memory of `peer_device` (needed once per peer before
  * mccb200_expand_scatter_peers; IPC mappings opened by another library do not imply it). */
 MCCB200_API int mccb200_enable_peer_access(int peer_device);

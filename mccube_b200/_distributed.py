@@ -150,6 +150,12 @@ class PeerShards:
         self.flag = torch.zeros(1, dtype=torch.float32, device=device)
         self.turn = 0
 
+    def load(self, y_shard: torch.Tensor):
+        """Copies this rank's state into the current buffer (start of a `step_pull` trajectory)."""
+        self.local[self.turn].copy_(y_shard)
+        self.barrier()
+        return self.local[self.turn]
+
     def barrier(self):
         """Stream-ordered cross-rank barrier (a 4-byte all-reduce: synchronisation only, no data path)."""
         dist.all_reduce(self.flag, group=self.group)
@@ -251,6 +257,28 @@ class ShardedMonteCarloStep:
         shards.barrier()          # every rank's rows have landed (and nobody still reads the other buffer)
         shards.turn ^= 1
         return out
+
+    def step_pull(self, t0, t1, rank: int, shards: PeerShards) -> torch.Tensor:
+        """with_replacement=True only.  The state lives in `shards` (load it once with `shards.load`): this
+        rank draws just the indices of the output slots it stores and the gather kernel reads every selected
+        parent from the shard of the rank that owns it (NVLink peer loads), writing its own next shard.
+        Per-rank work is O(n_loc): no replicated index vector, no grouping pass, no collective in the data
+        path, no host synchronisation.  Shards are bit-identical to the single-device step."""
+        from . import _lib
+
+        solver, kernel = self.solver, self.solver.recombination_kernel
+        cur, nxt = shards.turn, shards.turn ^ 1
+        y_in, y_out = shards.local[cur], shards.local[nxt]
+        n_loc, d = y_in.shape
+        n_tot = n_loc * self.n_ranks
+        if kernel.recombination_count != n_tot:
+            raise ValueError(f"MonteCarloKernel.recombination_count must be the GLOBAL particle count {n_tot}")
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_in, *solver.substep_times(t0, t1)[0], None)
+        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, y_in.device)
+        _lib.expand_gather_peers(shards.ptrs[cur], self.n_ranks, n_loc, d, drift, dt, cub, idx, y_out)
+        shards.barrier()          # everybody has finished reading the `cur` buffers
+        shards.turn = nxt
+        return y_out
 
     # ---- owner-computes variant: no row leaves its rank except the binomial imbalance
     def prepare_owner(self, t0, t1, y_shard: torch.Tensor, rank: int):

@@ -49,6 +49,14 @@ class MonteCarloKernel(AbstractRecombinationKernel):
         rng = _lib.make_rng(self.key, t, leaf=leaf, n_leaves=n_leaves, partitionable=self.threefry_partitionable)
         return _lib.mc_indices(rng, n_inputs, math.prod(shape), self.with_replacement, device)
 
+    def indices_slice(self, t, n_inputs: int, count: int, first: int, size: int, device) -> torch.Tensor:
+        """Entries [first, first + size) of `indices(t, n_inputs, count)` for with_replacement=True (counter
+        based draws: any slice can be produced on its own)."""
+        if not self.with_replacement:
+            raise ValueError("indices_slice needs with_replacement=True (the shuffle is not sliceable)")
+        rng = _lib.make_rng(self.key, t, partitionable=self.threefry_partitionable)
+        return _lib.mc_indices_slice(rng, n_inputs, count, first, size, device)
+
     def _probabilities(self, p, weighted):
         """`weights = self.weighting_function(weights)` (random.py:60-63); None = uniform."""
         if not weighted:

@@ -74,6 +74,10 @@ _SIGNATURES = {
                                                C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
+    "mccb200_mc_indices_slice": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_expand_gather_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                              C.POINTER(Cubature), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mccb200_peer_free": (C.c_int, [C.c_void_p]),
     "mccb200_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -265,6 +269,17 @@ def mc_indices(rng: Rng, n_inputs: int, count: int, replace: bool, device, out=N
     return out
 
 
+def mc_indices_slice(rng: Rng, n_inputs: int, count: int, first: int, size: int, device) -> torch.Tensor:
+    """Entries [first, first + size) of the with_replacement=True index vector of `count` draws."""
+    lib = load()
+    out = torch.empty(size, dtype=torch.int32, device=device)
+    nbytes = lib.mccb200_mc_indices_workspace_bytes(n_inputs, count, 1)
+    ws = workspace(nbytes, device)
+    _check(lib.mccb200_mc_indices_slice(C.byref(rng), n_inputs, count, first, size, out.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream()), "mc_indices_slice")
+    return out
+
+
 def sort_pairs(keys: torch.Tensor, values, key_bits: int = 32, want_keys: bool = False):
     """Stable argsort / sort_key_val of uint32 keys (int32 tensors reinterpreted)."""
     lib = load()
@@ -345,6 +360,16 @@ def peer_close(ptr: int):
 
 def peer_free(t: torch.Tensor):
     _check(load().mccb200_peer_free(C.c_void_p(t.data_ptr())), "peer_free")
+
+
+def expand_gather_peers(peer_ptrs, n_ranks, rows_per_rank, d, drift: Drift, dt, cub: Cubature, idx, out):
+    """Pull form: out[q] = child idx[q] (global child ids), parents read from the shards `peer_ptrs`."""
+    lib = load()
+    _require_cuda(peer_ptrs, idx, out)
+    _check(lib.mccb200_expand_gather_peers(peer_ptrs.data_ptr(), int(n_ranks), int(rows_per_rank), d, C.byref(drift),
+                                           float(np.float32(dt)), C.byref(cub), idx.data_ptr(), idx.numel(),
+                                           out.data_ptr(), _stream()), "expand_gather_peers")
+    return out
 
 
 def enable_peer_access(peer_device: int):

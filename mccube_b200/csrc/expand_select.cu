@@ -67,12 +67,13 @@ __device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r
 }
 
 // MODE 0: plain (the hot path: nothing below costs it an instruction); 1: scatter to peer shards;
-// 2: fused sub-steps.
+// 2: fused sub-steps; 3: pull -- parents are read from the peer shard that owns them.
 template <int VEC, int DRIFT, bool TABLE, int MODE = 0>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const ExpandArgs a) {
   constexpr bool SCATTER = MODE == 1;
   constexpr bool SUBSTEPS = MODE == 2;
+  constexpr bool PULL = MODE == 3;
   const int row_in_iter = threadIdx.x / a.vpr;
   const int col = (threadIdx.x - row_in_iter * a.vpr) * VEC;
   const bool active = row_in_iter < a.rows_per_iter;
@@ -130,8 +131,14 @@ expand_kernel(const ExpandArgs a) {
         pj[u] = c[u] - pi[u] * a.k;
       }
       if (ok[u]) {
-        load_vec_stream<VEC>(a.y0 + (uint64_t)pi[u] * a.ld + col, y[u]);
-        if (DRIFT == 1) load_vec_stream<VEC>(a.f + (uint64_t)pi[u] * a.d + col, f[u]);
+        if (PULL) {   // global parent id -> (owner rank, row): an NVLink peer load when the owner is another GPU
+          const uint32_t owner = (uint32_t)(pi[u] / a.sc_rows_per_rank);
+          const uint64_t row = pi[u] - (uint64_t)owner * a.sc_rows_per_rank;
+          load_vec_stream<VEC>(a.sc_peers[owner] + row * a.ld + col, y[u]);
+        } else {
+          load_vec_stream<VEC>(a.y0 + (uint64_t)pi[u] * a.ld + col, y[u]);
+          if (DRIFT == 1) load_vec_stream<VEC>(a.f + (uint64_t)pi[u] * a.d + col, f[u]);
+        }
       }
     }
 #pragma unroll
@@ -233,6 +240,11 @@ static int pick_vec(int d, int ld, const void* p0, const void* p1) {
 template <int VEC>
 static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
   const bool table = a.points != nullptr;
+  if (a.sc_peers && a.sc_order == nullptr) {   // pull form: Hadamard, drift kinds 0 / 2
+    if (a.drift_kind == 2) expand_kernel<VEC, 2, false, 3><<<grid, EX_THREADS, 0, st>>>(a);
+    else expand_kernel<VEC, 0, false, 3><<<grid, EX_THREADS, 0, st>>>(a);
+    return;
+  }
   if (a.sc_peers) {   // scatter form: Hadamard only
     if (a.drift_kind == 2) expand_kernel<VEC, 2, false, 1><<<grid, EX_THREADS, 0, st>>>(a);
     else if (a.drift_kind == 1) expand_kernel<VEC, 1, false, 1><<<grid, EX_THREADS, 0, st>>>(a);
@@ -347,6 +359,23 @@ extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int
   a.sc_rows_per_rank = rows_per_rank; a.sc_child_offset = (uint64_t)rank * n_loc * (uint64_t)cub->k;
   a.n_out = rows_per_rank + rows_per_rank / 8 + 1024;   // grid sizing only: the true count is read on the device
   a.y1 = const_cast<float*>(y0);                        // alignment probe only (never written in this form)
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, uint64_t rows_per_rank, int d,
+                                           const mccb200_drift* drift, float dt, const mccb200_cubature* cub,
+                                           const uint32_t* idx, uint64_t n_out, float* y1, void* stream) {
+  MCCB_REQUIRE(peer_in && idx && y1 && n_ranks >= 1 && n_ranks <= 64 && rows_per_rank >= 1,
+               "expand_gather_peers: bad argument");
+  ExpandArgs a{};
+  // y0 is only used for alignment checks here; parents come from peer_in[owner]
+  int rc = fill_expand_args(a, y1, rows_per_rank * (uint64_t)n_ranks, d, 0, drift, dt, cub);
+  if (rc) return rc;
+  if (cub->points != nullptr) return fail(MCCB200_ERR_UNSUPPORTED, "expand_gather_peers: Hadamard cubature only");
+  MCCB_REQUIRE(drift->kind != 1, "expand_gather_peers: an array drift lives with its parents (use the scatter form)");
+  a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
+  a.sc_peers = peer_in; a.sc_order = nullptr; a.sc_G = (uint32_t)n_ranks; a.sc_rows_per_rank = rows_per_rank;
+  a.n_out = n_out; a.y1 = y1;
   return run_expand(a, (cudaStream_t)stream);
 }
 

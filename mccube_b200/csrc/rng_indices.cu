@@ -67,19 +67,21 @@ random_bits_kernel(const DerivedKeys* __restrict__ dk, int round, uint32_t n, in
 }
 
 // jr.randint(key, (count,), 0, span) for int32 (jax/_src/random.py randint).
+// Elements [first, first + slice) of the `count` draws (the whole vector when first = 0, slice = count).
 __global__ void __launch_bounds__(256)
 randint_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint32_t span, int partitionable,
-               uint32_t* __restrict__ out) {
+               uint32_t* __restrict__ out, uint32_t first, uint32_t slice) {
   const u32x2 k1 = dk->randint_hi, k2 = dk->randint_lo;
   uint32_t mult = 65536u % span;
   mult = (mult * mult) % span;
   const bool part = partitionable != 0;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < slice; q += stride) {
+    const uint32_t i = first + q;
     uint32_t hi = random_bits32_at(k1, i, count, part);
     uint32_t lo = random_bits32_at(k2, i, count, part);
     uint32_t off = (hi % span) * mult + (lo % span);
-    out[i] = off % span;
+    out[q] = off % span;
   }
 }
 
@@ -214,7 +216,8 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   const int sms = sm_count();
   if (replace) {
     int grid = (int)min((uint64_t)(count + 255) / 256, (uint64_t)sms * 8);
-    randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out);
+    randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out, 0u,
+                                         (uint32_t)count);
     phase_mark("end", st);
     count_launches(2);
     return check_launch("mc_indices(randint)");
@@ -249,4 +252,29 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   phase_mark("end", st);
   count_launches(2 + p.rounds);
   return check_launch("mc_indices(shuffle)");
+}
+
+/* idx_out[q] = jr.choice(key_at(t), n_inputs, (count,), replace=True) [first + q], q in [0, slice): the
+ * draws are counter based, so a rank can produce exactly the output slots it stores. */
+extern "C" int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, uint64_t first,
+                                        uint64_t slice, uint32_t* idx_out, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MCCB_REQUIRE(rng && idx_out, "mc_indices_slice: NULL argument");
+  MCCB_REQUIRE(n_inputs >= 1 && n_inputs < 0xFFFFFFFFull && count < 0xFFFFFFFFull && first + slice <= count,
+               "mc_indices_slice: sizes out of range");
+  MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "mc_indices_slice: bad leaf");
+  IdxPlan p = make_idx_plan(n_inputs, count, 1);
+  if (workspace_bytes < p.total || workspace == nullptr)
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_indices_slice: workspace %zu < %zu", workspace_bytes, p.total);
+  if (slice == 0) return MCCB200_OK;
+  DerivedKeys* dk = (DerivedKeys*)((char*)workspace + p.off_dk);
+  phase_mark("mc_indices", st);
+  derive_keys_kernel<<<1, 32, 0, st>>>(*rng, 0, dk);
+  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * 8);
+  randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out,
+                                       (uint32_t)first, (uint32_t)slice);
+  phase_mark("end", st);
+  count_launches(2);
+  return check_launch("mc_indices_slice");
 }

@@ -66,6 +66,19 @@ def main():
         assert torch.equal(got2, want2[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: p2p step 2 != single (replace={rep})"
         del got1, got2
         shards.close()
+    # pull form (with_replacement=True): indices of the own slots only, parents read from the owners' shards
+    single = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42))
+    want1, *_ = single.step(terms, t0, t1, y, None, None, False)
+    want2, *_ = single.step(terms, t1, np.float32(0.35), want1, None, None, False)
+    sh = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)), terms, world)
+    shards = PeerShards(n_loc, d, rank, world, dev)
+    shards.load(y[rank * n_loc:(rank + 1) * n_loc])
+    got1 = sh.step_pull(t0, t1, rank, shards)
+    assert torch.equal(got1, want1[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: pull step 1 != single"
+    got2 = sh.step_pull(t1, np.float32(0.35), rank, shards)
+    assert torch.equal(got2, want2[rank * n_loc:(rank + 1) * n_loc]), f"rank {rank}: pull step 2 != single"
+    del got1, got2
+    shards.close()
     # owner-computes variant: rows equal the single-device result through the exported slot map
     want, *_ = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)).step(
         terms, t0, t1, y, None, None, False)
@@ -120,6 +133,24 @@ def main():
     torch.cuda.synchronize(); dist.barrier()
     ms_p = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms_p, op=dist.ReduceOp.MAX)
+    # pull timing
+    shp = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42)), terms, world)
+    gen.manual_seed(11 + rank)
+    shards.load(torch.randn((n_loc, d), generator=gen, device=dev))
+    for i in range(3):
+        shp.step_pull(times[i][0], times[i][1], rank, shards)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for i in range(3, 3 + a.steps):
+        shp.step_pull(times[i][0], times[i][1], rank, shards)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms_q = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms_q, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"variant": "pull: own index slice + gather from the owners' shards over peer memory, bit-exact shards",
+                          "n_gpus": world, "n_per_gpu": n_loc, "d": d, "ms_per_step": float(ms_q) / a.steps,
+                          "particle_steps_per_sec": n_tot * a.steps / (float(ms_q) * 1e-3)}))
     if rank == 0:
         print(json.dumps({"variant": "fused expand + peer-memory scatter (no collective in the data path), bit-exact shards",
                           "n_gpus": world, "n_per_gpu": n_loc, "d": d, "ms_per_step": float(ms_p) / a.steps,

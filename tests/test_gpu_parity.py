@@ -612,6 +612,33 @@ def test_sharded_p2p_scatter_emulated_ranks(dev, replace):
     assert torch.equal(torch.cat(shards), want)
 
 
+def test_sharded_pull_gather_emulated_ranks(dev):
+    """Pull form (with_replacement=True): every rank draws only its own slice of the index vector and reads
+    the parents from the owners' shards; ranks emulated on one GPU.  Also checks the index slices."""
+    G, n_loc, d = 4, 192, 12
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=29)
+    terms = _terms(d, mean, inv_var, dev)
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    yt = cuda(y, dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42))
+    want, *_ = solver.step(terms, t0, t1, yt, None, None, False)
+    kern = solver.recombination_kernel
+    shards_in = [yt[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards_in], dtype=torch.int64, device=dev)
+    drift, cub, dt, k, _ = solver._describe(terms, shards_in[0], *solver.substep_times(t0, t1)[0], None)
+    full = kern.indices(t0, n_tot * k, n_tot, dev)
+    outs = []
+    for r in range(G):
+        idx = kern.indices_slice(t0, n_tot * k, n_tot, r * n_loc, n_loc, dev)
+        assert torch.equal(idx, full[r * n_loc:(r + 1) * n_loc])
+        out = torch.empty((n_loc, d), device=dev)
+        outs.append(_lib.expand_gather_peers(ptrs, G, n_loc, d, drift, dt, cub, idx, out))
+    assert torch.equal(torch.cat(outs), want)
+    with pytest.raises(ValueError):
+        mccube.MonteCarloKernel(n_tot, False, key=42).indices_slice(t0, n_tot * k, n_tot, 0, n_loc, dev)
+
+
 def test_sharded_owner_computes_emulated_ranks(dev):
     """Owner-computes variant: only the imbalance is exchanged; rows equal the single-device
     result after applying the exported slot map (a permutation of all output slots)."""
