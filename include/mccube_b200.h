@@ -304,7 +304,13 @@ MCCB200_API int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_inpu
                                          void* stream);
 MCCB200_API int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, uint64_t rows_per_rank, int d,
                                             const mccb200_drift* drift, float dt, const mccb200_cubature* cub,
-                                            const uint32_t* idx, uint64_t n_out, float* y1, void* stream);
+                                            const uint32_t* idx /* or NULL */, const uint64_t* idx64 /* or NULL */,
+                                            uint64_t n_out, float* y1, void* stream);
+/* Index slice with jax_enable_x64 semantics (int64 randint: 64-bit draws, see oracle/jax_random.py::randint64;
+ * unpinned: no JAX in the image).  n_inputs = n_tot * k may exceed 2^32: BASELINE config 5 (n = 2^27, k = 128). */
+MCCB200_API int mccb200_mc_indices_slice64(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, uint64_t first,
+                                           uint64_t slice, uint64_t* idx_out, void* workspace, size_t workspace_bytes,
+                                           void* stream);
 /* Lets kernels of the current device dereference memory of `peer_device` (needed once per peer before
  * mccb200_expand_scatter_peers; IPC mappings opened by another library do not imply it). */
 MCCB200_API int mccb200_enable_peer_access(int peer_device);

@@ -274,7 +274,7 @@ class ShardedMonteCarloStep:
         if kernel.recombination_count != n_tot:
             raise ValueError(f"MonteCarloKernel.recombination_count must be the GLOBAL particle count {n_tot}")
         drift, cub, dt, k, _ = solver._describe(self.terms, y_in, *solver.substep_times(t0, t1)[0], None)
-        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, y_in.device)
+        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, y_in.device)   # int64 when kernel.x64
         _lib.expand_gather_peers(shards.ptrs[cur], self.n_ranks, n_loc, d, drift, dt, cub, idx, y_out)
         shards.barrier()          # everybody has finished reading the `cur` buffers
         shards.turn = nxt

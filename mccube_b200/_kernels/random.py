@@ -36,8 +36,11 @@ class MonteCarloKernel(AbstractRecombinationKernel):
     flag of the JAX the reference would run under (False = the reference's era)."""
 
     def __init__(self, recombination_count, with_replacement: bool = False, weighting_function=nop, *, key,
-                 threefry_partitionable: bool = False):
+                 threefry_partitionable: bool = False, x64: bool = False):
         super().__init__(recombination_count)
+        # mirrors jax_enable_x64 for the index draw of the sharded pull path (int64 randint: 64-bit draws,
+        # more than 2^32 children); the single-device paths use 32-bit child ids
+        self.x64 = x64
         self.with_replacement = with_replacement
         self.weighting_function = weighting_function
         self.key = key_words(key)
@@ -55,7 +58,10 @@ class MonteCarloKernel(AbstractRecombinationKernel):
         if not self.with_replacement:
             raise ValueError("indices_slice needs with_replacement=True (the shuffle is not sliceable)")
         rng = _lib.make_rng(self.key, t, partitionable=self.threefry_partitionable)
-        return _lib.mc_indices_slice(rng, n_inputs, count, first, size, device)
+        x64 = getattr(self, "x64", False)
+        if n_inputs > 2 ** 32 - 1 and not x64:
+            raise ValueError(f"{n_inputs} inputs need 64-bit indices: set kernel.x64 = True (jax_enable_x64 semantics)")
+        return _lib.mc_indices_slice(rng, n_inputs, count, first, size, device, x64=x64)
 
     def _probabilities(self, p, weighted):
         """`weights = self.weighting_function(weights)` (random.py:60-63); None = uniform."""

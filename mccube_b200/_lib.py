@@ -77,7 +77,10 @@ _SIGNATURES = {
     "mccb200_mc_indices_slice": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_expand_gather_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
-                                              C.POINTER(Cubature), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+                                              C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                              C.c_void_p]),
+    "mccb200_mc_indices_slice64": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "mccb200_peer_free": (C.c_int, [C.c_void_p]),
     "mccb200_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -269,9 +272,16 @@ def mc_indices(rng: Rng, n_inputs: int, count: int, replace: bool, device, out=N
     return out
 
 
-def mc_indices_slice(rng: Rng, n_inputs: int, count: int, first: int, size: int, device) -> torch.Tensor:
-    """Entries [first, first + size) of the with_replacement=True index vector of `count` draws."""
+def mc_indices_slice(rng: Rng, n_inputs: int, count: int, first: int, size: int, device, x64: bool = False) -> torch.Tensor:
+    """Entries [first, first + size) of the with_replacement=True index vector of `count` draws.
+    x64: `jax_enable_x64` semantics (int64 randint, 64-bit draws), int64 result, n_inputs may exceed 2^32."""
     lib = load()
+    if x64:
+        out = torch.empty(size, dtype=torch.int64, device=device)
+        ws = workspace(4096, device)
+        _check(lib.mccb200_mc_indices_slice64(C.byref(rng), n_inputs, count, first, size, out.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()), "mc_indices_slice64")
+        return out
     out = torch.empty(size, dtype=torch.int32, device=device)
     nbytes = lib.mccb200_mc_indices_workspace_bytes(n_inputs, count, 1)
     ws = workspace(nbytes, device)
@@ -366,9 +376,11 @@ def expand_gather_peers(peer_ptrs, n_ranks, rows_per_rank, d, drift: Drift, dt, 
     """Pull form: out[q] = child idx[q] (global child ids), parents read from the shards `peer_ptrs`."""
     lib = load()
     _require_cuda(peer_ptrs, idx, out)
+    wide = idx.dtype == torch.int64
     _check(lib.mccb200_expand_gather_peers(peer_ptrs.data_ptr(), int(n_ranks), int(rows_per_rank), d, C.byref(drift),
-                                           float(np.float32(dt)), C.byref(cub), idx.data_ptr(), idx.numel(),
-                                           out.data_ptr(), _stream()), "expand_gather_peers")
+                                           float(np.float32(dt)), C.byref(cub), None if wide else idx.data_ptr(),
+                                           idx.data_ptr() if wide else None, idx.numel(), out.data_ptr(), _stream()),
+           "expand_gather_peers")
     return out
 
 

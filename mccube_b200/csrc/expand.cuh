@@ -32,6 +32,7 @@ struct ExpandArgs {
   // sc_order[start + q] of the global result, start / count read on the device from the replicated
   // counts matrix; the child is written straight into the shard of the rank that stores the slot
   // (peer memory over NVLink), no send buffer, no collective.
+  const uint64_t* idx64;      // pull form with 64-bit GLOBAL child ids (n_tot * k may exceed 2^32), else nullptr
   const uint32_t* sc_order;   // [n_tot] output slots grouped by owner rank (ascending slot inside a group)
   const uint32_t* sc_counts;  // [G][G] counts[owner][dest]
   float* const* sc_peers;     // [G] base pointer of every rank's output shard

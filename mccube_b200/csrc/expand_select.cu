@@ -107,7 +107,11 @@ expand_kernel(const ExpandArgs a) {
     for (int u = 0; u < EX_UNROLL; ++u) {
       r[u] = base + (uint64_t)u * a.rows_per_iter + row_in_iter;
       ok[u] = r[u] < n_out;
-      if (SCATTER) {
+      if (PULL && a.idx64 != nullptr) {                    // 64-bit global child id -> (global parent, point)
+        const uint64_t cg = ok[u] ? __ldg(a.idx64 + r[u]) : 0ull;
+        slot[u] = (uint32_t)(cg >> a.k_shift);             // parent (n_tot < 2^32), decoded below
+        c[u] = (uint32_t)(cg & (uint64_t)(a.k - 1u));
+      } else if (SCATTER) {
         slot[u] = ok[u] ? __ldg(a.sc_order + sc_start + r[u]) : 0u;
         c[u] = ok[u] ? (uint32_t)((uint64_t)__ldg(a.idx + slot[u]) - a.sc_child_offset) : 0u;
       } else {
@@ -119,7 +123,10 @@ expand_kernel(const ExpandArgs a) {
     uint32_t pi[EX_UNROLL], pj[EX_UNROLL];
 #pragma unroll
     for (int u = 0; u < EX_UNROLL; ++u) {
-      if (SUBSTEPS) {                                      // k^n_sub children per parent (k a power of two)
+      if (PULL && a.idx64 != nullptr) {
+        pi[u] = slot[u];
+        pj[u] = c[u];
+      } else if (SUBSTEPS) {                               // k^n_sub children per parent (k a power of two)
         const uint32_t sh = a.k_shift * (uint32_t)a.n_sub;
         pi[u] = sh >= 32u ? 0u : (c[u] >> sh);
         pj[u] = sh >= 32u ? c[u] : (c[u] & ((1u << sh) - 1u));
@@ -364,13 +371,17 @@ extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int
 
 extern "C" int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, uint64_t rows_per_rank, int d,
                                            const mccb200_drift* drift, float dt, const mccb200_cubature* cub,
-                                           const uint32_t* idx, uint64_t n_out, float* y1, void* stream) {
-  MCCB_REQUIRE(peer_in && idx && y1 && n_ranks >= 1 && n_ranks <= 64 && rows_per_rank >= 1,
+                                           const uint32_t* idx, const uint64_t* idx64, uint64_t n_out, float* y1,
+                                           void* stream) {
+  MCCB_REQUIRE(peer_in && (idx || idx64) && y1 && n_ranks >= 1 && n_ranks <= 64 && rows_per_rank >= 1,
                "expand_gather_peers: bad argument");
+  MCCB_REQUIRE(rows_per_rank * (uint64_t)n_ranks <= 0xFFFFFFFFull, "expand_gather_peers: more than 2^32 - 1 parents");
   ExpandArgs a{};
-  // y0 is only used for alignment checks here; parents come from peer_in[owner]
-  int rc = fill_expand_args(a, y1, rows_per_rank * (uint64_t)n_ranks, d, 0, drift, dt, cub);
+  // y0 is only used for alignment checks here; parents come from peer_in[owner].  With 32-bit ids the
+  // global child count must fit 2^32; with idx64 only the per-rank one has to.
+  int rc = fill_expand_args(a, y1, idx64 ? rows_per_rank : rows_per_rank * (uint64_t)n_ranks, d, 0, drift, dt, cub);
   if (rc) return rc;
+  a.idx64 = idx64;
   if (cub->points != nullptr) return fail(MCCB200_ERR_UNSUPPORTED, "expand_gather_peers: Hadamard cubature only");
   MCCB_REQUIRE(drift->kind != 1, "expand_gather_peers: an array drift lives with its parents (use the scatter form)");
   a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;

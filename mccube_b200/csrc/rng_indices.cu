@@ -85,6 +85,36 @@ randint_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint32_t span
   }
 }
 
+// random_bits(key, 64, (n,))[i] (jax/_src/prng.py): original mode hashes iota(2n) and pairs word i with
+// word n + i; partitionable mode is one block per element.
+__device__ __forceinline__ uint64_t random_bits64_at(u32x2 key, uint32_t i, uint32_t n, bool partitionable) {
+  if (partitionable) {
+    const u32x2 o = threefry2x32(key.x, key.y, 0u, i);
+    return ((uint64_t)o.x << 32) | o.y;
+  }
+  const uint32_t hi = random_bits32_at(key, i, 2u * n, false);
+  const uint32_t lo = random_bits32_at(key, n + i, 2u * n, false);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// jr.randint with jax_enable_x64 (int64): elements [first, first + slice) of the `count` draws over [0, span).
+__global__ void __launch_bounds__(256)
+randint64_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint64_t span, int partitionable,
+                 uint64_t* __restrict__ out, uint32_t first, uint32_t slice) {
+  const u32x2 k1 = dk->randint_hi, k2 = dk->randint_lo;
+  uint64_t mult = (1ull << 32) % span;
+  mult = (mult * mult) % span;                            // the product wraps in 64 bits, as lax.mul on uint64 does
+  const bool part = partitionable != 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < slice; q += stride) {
+    const uint32_t i = first + q;
+    const uint64_t hi = random_bits64_at(k1, i, count, part);
+    const uint64_t lo = random_bits64_at(k2, i, count, part);
+    const uint64_t off = (hi % span) * mult + (lo % span);
+    out[q] = off % span;
+  }
+}
+
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t count, uint32_t* __restrict__ out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = i;
 }
@@ -277,4 +307,28 @@ extern "C" int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_input
   phase_mark("end", st);
   count_launches(2);
   return check_launch("mc_indices_slice");
+}
+
+/* The same with jax_enable_x64 semantics (int64 randint: 64-bit draws): n_inputs may exceed 2^32 (config 5:
+ * n * k = 2^34 children).  count < 2^31. */
+extern "C" int mccb200_mc_indices_slice64(const mccb200_rng* rng, uint64_t n_inputs, uint64_t count, uint64_t first,
+                                          uint64_t slice, uint64_t* idx_out, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MCCB_REQUIRE(rng && idx_out, "mc_indices_slice64: NULL argument");
+  MCCB_REQUIRE(n_inputs >= 1 && count < 0x80000000ull && first + slice <= count, "mc_indices_slice64: sizes out of range");
+  MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "mc_indices_slice64: bad leaf");
+  const size_t need = align_up(sizeof(DerivedKeys), 256);
+  if (workspace_bytes < need || workspace == nullptr)
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_indices_slice64: workspace %zu < %zu", workspace_bytes, need);
+  if (slice == 0) return MCCB200_OK;
+  DerivedKeys* dk = (DerivedKeys*)workspace;
+  phase_mark("mc_indices", st);
+  derive_keys_kernel<<<1, 32, 0, st>>>(*rng, 0, dk);
+  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * 8);
+  randint64_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, n_inputs, rng->partitionable, idx_out, (uint32_t)first,
+                                         (uint32_t)slice);
+  phase_mark("end", st);
+  count_launches(2);
+  return check_launch("mc_indices_slice64");
 }

@@ -110,6 +110,22 @@ def randint(key, size: int, minval: int, maxval: int, *, partitionable: bool = F
     return (np.int64(minval) + off.astype(np.int64)).astype(np.int32)
 
 
+def randint64(key, size: int, minval: int, maxval: int, *, partitionable: bool = False):
+    """`jr.randint(key, (size,), minval, maxval)` with `jax_enable_x64` (int64): the same recipe on 64-bit
+    words -- two 64-bit draws, multiplier = ((2^32 % span)^2 mod 2^64) % span, all arithmetic wrapping in
+    uint64 (jax/_src/random.py `_randint`).  UNPINNED: restated from the public source, no JAX here."""
+    U64 = np.uint64
+    k1, k2 = split(key, 2, partitionable=partitionable)
+    hi = random_bits(k1, 64, size, partitionable=partitionable)
+    lo = random_bits(k2, 64, size, partitionable=partitionable)
+    span = U64(maxval - minval) if maxval > minval else U64(1)
+    with np.errstate(over="ignore"):
+        mult = U64(1 << 32) % span
+        mult = U64(mult * mult) % span
+        off = ((hi % span) * mult + (lo % span)) % span
+    return (np.int64(minval) + off.astype(np.int64)).astype(np.int64)
+
+
 def uniform(key, size: int, dtype=np.float32, minval=0.0, maxval=1.0, *, partitionable=False):
     """`jr.uniform(key, (size,), dtype, minval, maxval)`."""
     dtype = np.dtype(dtype)
@@ -157,7 +173,7 @@ def shuffle_perm(key, size: int, *, partitionable: bool = False):
 
 
 def choice_indices(key, n_inputs: int, n_draws: int, replace: bool, p=None, *,
-                   partitionable: bool = False):
+                   partitionable: bool = False, x64: bool = False):
     """Index vector that `jr.choice(key, a, (n_draws,), replace, p)` gathers with.
 
     The reference never exposes this vector (`random.py:65` returns `a[ind]`); it is
@@ -165,6 +181,8 @@ def choice_indices(key, n_inputs: int, n_draws: int, replace: bool, p=None, *,
     """
     if p is None:
         if replace:
+            if x64:   # jax_enable_x64: randint's default dtype is int64
+                return randint64(key, n_draws, 0, n_inputs, partitionable=partitionable)
             return randint(key, n_draws, 0, n_inputs, partitionable=partitionable).astype(np.int64)
         return shuffle_perm(key, n_inputs, partitionable=partitionable)[:n_draws]
     p = np.asarray(p)

@@ -139,7 +139,8 @@ class MonteCarloKernel:
     """`MonteCarloKernel` (mccube/_kernels/random.py:22-68)."""
 
     def __init__(self, recombination_count, with_replacement=False, weighting_function=None, *,
-                 key, partitionable=False):
+                 key, partitionable=False, x64=False):
+        self.x64 = x64
         self.recombination_count = recombination_count
         self.with_replacement = with_replacement
         self.weighting_function = weighting_function
@@ -151,7 +152,7 @@ class MonteCarloKernel:
         shape = tuple(count) if isinstance(count, tuple) else (count,)
         key = jr.mc_step_key(self.key, t, partitionable=self.partitionable)
         idx = jr.choice_indices(key, n_inputs, int(np.prod(shape)), self.with_replacement, p,
-                                partitionable=self.partitionable)
+                                partitionable=self.partitionable, x64=self.x64)
         return idx.reshape(shape)
 
     def __call__(self, t, particles, args=None, weighted=False, count=None):

@@ -639,6 +639,38 @@ def test_sharded_pull_gather_emulated_ranks(dev):
         mccube.MonteCarloKernel(n_tot, False, key=42).indices_slice(t0, n_tot * k, n_tot, 0, n_loc, dev)
 
 
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_sharded_pull_x64_indices(dev, partitionable):
+    """jax_enable_x64 semantics of the index draw (int64 randint, 64-bit draws) for the pull path: slices vs the
+    oracle's restatement, also for a span beyond 2^32 (BASELINE config 5 has 2^34 children), and an emulated
+    sharded step vs the oracle's step with the x64 kernel.  Unpinned (no JAX in the image)."""
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    for span, count in ((1 << 34, 1000), (12345, 777), ((1 << 32) + 17, 64)):
+        want = jr.choice_indices(jr.mc_step_key(jr.prng_key(42), t0, partitionable=partitionable), span, count, True,
+                                 partitionable=partitionable, x64=True)
+        kern = mccube.MonteCarloKernel(count, True, key=42, threefry_partitionable=partitionable, x64=True)
+        got = torch.cat([kern.indices_slice(t0, span, count, a, b - a, dev) for a, b in ((0, 10), (10, count))])
+        assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+    G, n_loc, d = 2, 96, 8
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=31)
+    terms = _terms(d, mean, inv_var, dev)
+    yt = cuda(y, dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, True, key=42, threefry_partitionable=partitionable,
+                                                                    x64=True))
+    want = ref.mcc_step(y, t0, t1, lambda q: ref.gaussian_diag_drift(q, mean, inv_var), ref.hadamard_points(d),
+                        ref.hadamard_weights(d), SQRT2,
+                        ref.MonteCarloKernel(n_tot, True, key=jr.prng_key(42), partitionable=partitionable, x64=True))
+    shards_in = [yt[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards_in], dtype=torch.int64, device=dev)
+    drift, cub, dt, k, _ = solver._describe(terms, shards_in[0], *solver.substep_times(t0, t1)[0], None)
+    outs = []
+    for r in range(G):
+        idx = solver.recombination_kernel.indices_slice(t0, n_tot * k, n_tot, r * n_loc, n_loc, dev)
+        outs.append(_lib.expand_gather_peers(ptrs, G, n_loc, d, drift, dt, cub, idx, torch.empty((n_loc, d), device=dev)))
+    assert np.array_equal(torch.cat(outs).cpu().numpy(), want)
+
+
 def test_sharded_owner_computes_emulated_ranks(dev):
     """Owner-computes variant: only the imbalance is exchanged; rows equal the single-device
     result after applying the exported slot map (a permutation of all output slots)."""
