@@ -393,6 +393,39 @@ def sharded_global_mc(dev, rank, world, steps=5):
         out[name] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3)}
         del ys
     shards.close()
+    del shards
+    torch.cuda.empty_cache()
+    # BASELINE config 5: n = 2^27, d = 64 (k = 128 -> 2^34 children: 64-bit child ids, jax_enable_x64 index
+    # semantics), global MonteCarloKernel(with_replacement=True) over all ranks with the pull exchange
+    try:
+        n5 = 1 << 27
+        n_loc5 = n5 // world
+        sh5 = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n5, True, key=42, x64=True)),
+                                    terms, world)
+        shards5 = PeerShards(n_loc5, d, rank, world, dev)
+        gen.manual_seed(17 + rank)
+        shards5.load(torch.randn((n_loc5, d), generator=gen, device=dev))
+        for i in range(2):
+            sh5.step_pull(times[i][0], times[i][1], rank, shards5)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(2, 2 + steps):
+            y5 = sh5.step_pull(times[i][0], times[i][1], rank, shards5)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        fin = torch.tensor([float(torch.isfinite(y5).all())], device=dev)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        out["config5_n2^27_d64_step_pull"] = {
+            "n_per_gpu": n_loc5, "ms_per_step": float(ms) / steps, "particle_steps_per_sec": n5 * steps / (float(ms) * 1e-3),
+            "algorithmic_gbs_per_gpu": 2.0 * n_loc5 * d * 4 / (float(ms) / steps * 1e-3) / 1e9, "finite": bool(fin.item()),
+            "note": "2^34 implicit children, int64 index draw (jax_enable_x64 semantics, unpinned), parents pulled over NVLink"}
+        del y5
+        shards5.close()
+    except Exception as e:  # noqa: BLE001
+        out["config5_n2^27_d64_step_pull"] = {"error": repr(e)}
     out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
     out["note"] = ("step_pull: every rank draws only its own slice of the (counter-based) index vector and the gather "
                    "kernel reads the selected parents from the owners' shards over NVLink peer memory: O(n_loc) work per "

@@ -378,8 +378,8 @@ extern "C" int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, u
   MCCB_REQUIRE(rows_per_rank * (uint64_t)n_ranks <= 0xFFFFFFFFull, "expand_gather_peers: more than 2^32 - 1 parents");
   ExpandArgs a{};
   // y0 is only used for alignment checks here; parents come from peer_in[owner].  With 32-bit ids the
-  // global child count must fit 2^32; with idx64 only the per-rank one has to.
-  int rc = fill_expand_args(a, y1, idx64 ? rows_per_rank : rows_per_rank * (uint64_t)n_ranks, d, 0, drift, dt, cub);
+  // global child count must fit 2^32; with idx64 only the parent count has to (checked above).
+  int rc = fill_expand_args(a, y1, idx64 ? 1 : rows_per_rank * (uint64_t)n_ranks, d, 0, drift, dt, cub);
   if (rc) return rc;
   a.idx64 = idx64;
   if (cub->points != nullptr) return fail(MCCB200_ERR_UNSUPPORTED, "expand_gather_peers: Hadamard cubature only");
