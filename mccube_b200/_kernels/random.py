@@ -50,6 +50,13 @@ class MonteCarloKernel(AbstractRecombinationKernel):
     def indices(self, t, n_inputs: int, count, device, leaf: int = 0, n_leaves: int = 1) -> torch.Tensor:
         shape = tuple(count) if isinstance(count, (tuple, list)) else (count,)
         rng = _lib.make_rng(self.key, t, leaf=leaf, n_leaves=n_leaves, partitionable=self.threefry_partitionable)
+        if self.x64 and self.with_replacement:
+            # jax_enable_x64: randint draws int64 (different bits from the int32 recipe even for small spans);
+            # the single-device kernels take 32-bit child ids
+            if n_inputs > 2 ** 32:
+                raise ValueError(f"{n_inputs} inputs exceed the 32-bit child ids of the single-device path (use step_pull)")
+            idx = _lib.mc_indices_slice(rng, n_inputs, math.prod(shape), 0, math.prod(shape), device, x64=True)
+            return idx.to(torch.int32)          # wraps to the uint32 bit pattern the kernels read
         return _lib.mc_indices(rng, n_inputs, math.prod(shape), self.with_replacement, device)
 
     def indices_slice(self, t, n_inputs: int, count: int, first: int, size: int, device) -> torch.Tensor:

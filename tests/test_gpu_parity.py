@@ -671,6 +671,22 @@ def test_sharded_pull_x64_indices(dev, partitionable):
     assert np.array_equal(torch.cat(outs).cpu().numpy(), want)
 
 
+def test_x64_monte_carlo_step_single_device(dev):
+    """MonteCarloKernel(x64=True, with_replacement=True) on one device: the fused step equals the oracle's step
+    with the int64 index draw (and differs from the int32 draw)."""
+    n, d = 300, 10
+    y, mean, inv_var = _setup(n, d, seed=33)
+    t0, t1 = np.float32(0.1), np.float32(0.15)
+    want = ref.mcc_step(y, t0, t1, lambda q: ref.gaussian_diag_drift(q, mean, inv_var), ref.hadamard_points(d),
+                        ref.hadamard_weights(d), SQRT2, ref.MonteCarloKernel(n, True, key=jr.prng_key(5), x64=True))
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, True, key=5, x64=True))
+    got, *_ = solver.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(y, dev), None, None, False)
+    assert solver.last_path.startswith("fused") and np.array_equal(got.cpu().numpy(), want)
+    solver32 = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, True, key=5))
+    got32, *_ = solver32.step(_terms(d, mean, inv_var, dev), t0, t1, cuda(y, dev), None, None, False)
+    assert not torch.equal(got, got32)
+
+
 def test_sharded_owner_computes_emulated_ranks(dev):
     """Owner-computes variant: only the imbalance is exchanged; rows equal the single-device
     result after applying the exported slot map (a permutation of all output slots)."""
