@@ -141,3 +141,22 @@ def test_solver_quirks_and_times():
     y1 = ref.mcc_step(y0, 0.0, 0.05, lambda y: -y, ref.hadamard_points(d), ref.hadamard_weights(d),
                       np.float32(np.sqrt(2.0)), mc, n_substeps=2, weighted=True)
     assert y1.shape == (n, d + 1) and abs(float(y1[:, -1].sum()) - 1.0) < 1e-5
+
+
+def test_randint64_structure():
+    """x64 randint restatement (unpinned): with span = 2^34 the multiplier (2^32 mod span)^2 wraps to 0 in
+    uint64, so the draw is the low 64-bit word mod span; small spans stay in range and are deterministic."""
+    key = jr.mc_step_key(jr.prng_key(42), 0.25)
+    for part in (False, True):
+        k1, k2 = jr.split(key, 2, partitionable=part)
+        lo = jr.random_bits(k2, 64, 100, partitionable=part)
+        got = jr.randint64(key, 100, 0, 1 << 34, partitionable=part)
+        assert np.array_equal(got, (lo % np.uint64(1 << 34)).astype(np.int64))
+        small = jr.randint64(key, 1000, 0, 12345, partitionable=part)
+        assert small.min() >= 0 and small.max() < 12345
+        assert np.array_equal(small, jr.randint64(key, 1000, 0, 12345, partitionable=part))
+        assert not np.array_equal(small, jr.randint(key, 1000, 0, 12345, partitionable=part))
+        # 64-bit words are (word i << 32) | word n + i of one hash in the original mode
+        if not part:
+            bits = jr.random_bits(k2, 32, 200)
+            assert np.array_equal(lo, (bits[:100].astype(np.uint64) << np.uint64(32)) | bits[100:].astype(np.uint64))
