@@ -659,7 +659,7 @@ def main():
         extras = extra_workloads(dev, peak)
 
     cpu_baseline = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:      # reported at N = 1 only (the reference arm has its own run)
         val, ms, sample, procs = run_oracle_all_cores(a, a.cpu_n_log2, a.cpu_steps, 1)
         cpu_baseline = {"value": val, "unit": "particle-steps/s", "cores": procs, "kind": "port", "sample": sample,
                         "ms_per_step": ms, "host_cpus": os.cpu_count(), "blas_threads": host_threads()}

@@ -20,6 +20,8 @@ Parity pin status ("Oracle pinning"):
     tests/test_oracle_pin.py.
   * partitionable mode (JAX >= 0.5 default): structural checks only, NO external
     golden => "parity unpinned" for that mode.
+  * x64 index draw (`randint64`, jax_enable_x64 semantics, used by the sharded pull
+    path for more than 2^32 children): structural checks only => "parity unpinned".
   * BoxPartitionKernel: does not exist in the reference => oracle is the
     definition; "parity unpinned" by construction.
 """
