@@ -430,16 +430,16 @@ __device__ __forceinline__ uint32_t describe_parent4(const BoxPrkParams& p, uint
   return K0 | (D << 12) | (S << 24);
 }
 
-// ------------------------------------------------------------------ pass A (flat form)
-// CTA per segment, warps interleave its batches.  A round holds the records of ~32 / (classes
-// per parent) consecutive parents, so a shared-memory atomic sees a few-way address conflict at
-// most (lane = parent with a class loop would collide 32-way on box-ordered input).
+// ------------------------------------------------------------------ pass A
+// CTA per segment, warps interleave its batches; per batch the lanes are grouped by descriptor
+// (__match_any_sync) and one lane per group feeds the shared-memory histogram.
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
 box_count_flat_kernel(const BoxPrkParams p) {
   extern __shared__ uint32_t smem[];
   const ExpandArgs& a = p.a;
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t* hist = smem;
   const uint32_t cls_pad = 1u << p.cls_pad_log2;
   uint32_t* s_tab = hist + p.n_keys;
@@ -453,8 +453,6 @@ box_count_flat_kernel(const BoxPrkParams p) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) { lo[q] = __ldg(p.bounds + q); ih[q] = __ldg(p.bounds + 4 + q); }
   }
-  const uint32_t unit = a.k >> p.cls_pad_log2;
-  const uint32_t* s_tab_biased = s_tab - FLAT_TOFF_BIAS;
   const uint32_t seg = blockIdx.x;
   const uint64_t i0 = (uint64_t)seg * p.parents_per_seg;
   const uint64_t i1 = min(a.n, i0 + p.parents_per_seg);
@@ -467,10 +465,19 @@ box_count_flat_kernel(const BoxPrkParams p) {
       else { uint32_t K0, D, S; describe_parent(p, i, K0, D, S); desc = K0 | (D << 12) | (S << 24); }
       p.pdesc[i] = desc;                                 // pass B re-reads 4 coalesced bytes per parent
     }
-    const FlatBatch b = flat_batch(desc, have ? s_cnt[desc >> 24] : 0u, lane, p.cls_pad_log2);
-    for (uint32_t r0 = 0; r0 < b.R; r0 += 32) {
-      const FlatRecord rec = flat_record(b, r0, lane, s_tab_biased);
-      if (rec.valid) atomicAdd(&hist[rec.key], unit << rec.e);
+    // Parents with the same descriptor (K0, D, S) contribute the same classes: one lane per distinct
+    // descriptor of the batch adds (group size x class size) for each of its classes.  On box-ordered
+    // input a batch holds a dozen distinct descriptors for ~140 class records.
+    const uint32_t peers = __match_any_sync(0xffffffffu, have ? desc : 0xFFFFFFFFu);
+    if (have && (peers & lt_mask) == 0u) {
+      const uint32_t mult = (uint32_t)__popc(peers);
+      const uint32_t S = desc >> 24, K0 = desc & 0xFFFu, D = (desc >> 12) & 0xFFFu;
+      const uint32_t ncls = s_cnt[S];
+      const uint32_t* trow = s_tab + (S << p.cls_pad_log2);
+      for (uint32_t c = 0; c < ncls; ++c) {
+        const uint32_t ent = trow[c];
+        atomicAdd(&hist[K0 + (D & ent & 0xFFFu)], mult * (((ent >> 12) & 0x3FFu) + 1u));
+      }
     }
   }
   __syncthreads();
