@@ -290,7 +290,7 @@ extern "C" int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_input
                                         uint64_t slice, uint32_t* idx_out, void* workspace, size_t workspace_bytes,
                                         void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  MCCB_REQUIRE(rng && idx_out, "mc_indices_slice: NULL argument");
+  MCCB_REQUIRE(rng && (idx_out || slice == 0), "mc_indices_slice: NULL argument");
   MCCB_REQUIRE(n_inputs >= 1 && n_inputs < 0xFFFFFFFFull && count < 0xFFFFFFFFull && first + slice <= count,
                "mc_indices_slice: sizes out of range");
   MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "mc_indices_slice: bad leaf");
@@ -315,7 +315,7 @@ extern "C" int mccb200_mc_indices_slice64(const mccb200_rng* rng, uint64_t n_inp
                                           uint64_t slice, uint64_t* idx_out, void* workspace, size_t workspace_bytes,
                                           void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  MCCB_REQUIRE(rng && idx_out, "mc_indices_slice64: NULL argument");
+  MCCB_REQUIRE(rng && (idx_out || slice == 0), "mc_indices_slice64: NULL argument");
   MCCB_REQUIRE(n_inputs >= 1 && count < 0x80000000ull && first + slice <= count, "mc_indices_slice64: sizes out of range");
   MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "mc_indices_slice64: bad leaf");
   const size_t need = align_up(sizeof(DerivedKeys), 256);

@@ -775,3 +775,67 @@ def test_weighted_solver_step_with_weighting_function(dev):
     assert got.shape == want.shape and abs(got[:, -1].sum() - 1.0) < 1e-5
     same_rows = (got[:, :-1] == want[:, :-1]).all(axis=1).mean()
     assert same_rows > 0.95
+
+
+# ------------------------------------------------------------------ edge cases of the newer entry points
+def test_edge_cases_new_entry_points(dev):
+    """Tiny / ragged / empty inputs through the tensor-core drift, the fused sub-steps, the peer gather and
+    the split Box API."""
+    rs = np.random.default_rng(77)
+    # tensor-core drift: a single particle, and one row more than a tile
+    d = 64
+    a = rs.normal(size=(d, d)); cov = a @ a.T / d + np.eye(d); mu = rs.normal(size=d)
+    f = mccube.GaussianFullDrift(mu, cov, device=dev)
+    for n in (1, 129, 257):
+        y = (rs.normal(size=(n, d)) + mu).astype(np.float32)
+        got = f(0.0, cuda(y, dev)).cpu().numpy()
+        want = -(y.astype(np.float64) - f.mean.cpu().numpy()) @ f.prec.cpu().numpy().astype(np.float64)
+        assert f.last_path == "tcgen05:3xtf32" and np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # d not a multiple of 32: the SIMT tiles take over (no silent precision change: same tolerance)
+    d2 = 40
+    a = rs.normal(size=(d2, d2)); cov2 = a @ a.T / d2 + np.eye(d2)
+    f2 = mccube.GaussianFullDrift(np.zeros(d2), cov2, device=dev)
+    y = rs.normal(size=(50, d2)).astype(np.float32)
+    got = f2(0.0, cuda(y, dev)).cpu().numpy()
+    assert f2.last_path == "simt:fp32"
+    assert np.abs(got + y.astype(np.float64) @ f2.prec.cpu().numpy().astype(np.float64)).max() <= 1e-5 * np.abs(got).max()
+    # fused sub-steps with an odd dimension (scalar vector path) and a single particle
+    for n, dd in ((1, 3), (7, 5)):
+        yy, mean, inv_var = _setup(n, dd, seed=40 + n)
+        want = ref.mcc_step(yy, np.float32(0.0), np.float32(0.05), lambda q: ref.gaussian_diag_drift(q, mean, inv_var),
+                            ref.hadamard_points(dd), ref.hadamard_weights(dd), SQRT2,
+                            ref.MonteCarloKernel(n, key=jr.prng_key(9)), n_substeps=2)
+        solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=9), n_substeps=2)
+        got, *_ = solver.step(_terms(dd, mean, inv_var, dev), np.float32(0.0), np.float32(0.05), cuda(yy, dev), None, None, False)
+        assert "substeps=2" in solver.last_path and np.array_equal(got.cpu().numpy(), want)
+    # peer gather with one "rank" and an empty slice
+    n, dd = 33, 6
+    yy, mean, inv_var = _setup(n, dd, seed=50)
+    terms = _terms(dd, mean, inv_var, dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, True, key=11))
+    t0, t1 = np.float32(0.0), np.float32(0.05)
+    yt = cuda(yy, dev)
+    want, *_ = solver.step(terms, t0, t1, yt, None, None, False)
+    drift, cub, dt, k, _ = solver._describe(terms, yt, *solver.substep_times(t0, t1)[0], None)
+    ptrs = torch.tensor([yt.data_ptr()], dtype=torch.int64, device=dev)
+    idx = solver.recombination_kernel.indices_slice(t0, n * k, n, 0, n, dev)
+    out = _lib.expand_gather_peers(ptrs, 1, n, dd, drift, dt, cub, idx, torch.empty((n, dd), device=dev))
+    assert torch.equal(out, want)
+    assert solver.recombination_kernel.indices_slice(t0, n * k, n, 5, 0, dev).numel() == 0
+    # split Box API on a state smaller than one batch of 32 parents, non-power-of-two partition size
+    n, dd = 24, 8
+    yy, mean, inv_var = _setup(n, dd, seed=51)
+    kern = mccube.PartitioningRecombinationKernel(mccube.BoxPartitionKernel(16, dims=(0, 1, 2, 3), bits=2),
+                                                  mccube.MonteCarloKernel(3, key=13))
+    solver = mccube.MCCSolver(dfx.Euler(), kern)
+    got, _, _, state, _ = solver.step(_terms(dd, mean, inv_var, dev), t0, t1, cuda(yy, dev), None, None, False)
+    okern = ref.PartitioningRecombinationKernel(ref.BoxPartitionKernel(16, dims=(0, 1, 2, 3), bits=2),
+                                                ref.MonteCarloKernel(3, key=jr.prng_key(13)))
+    want = ref.mcc_step(yy, t0, t1, lambda q: ref.gaussian_diag_drift(q, mean, inv_var), ref.hadamard_points(dd),
+                        ref.hadamard_weights(dd), SQRT2, okern)
+    assert solver.last_path == "fused:box_prk_step" and np.array_equal(got.cpu().numpy(), want)
+    # and a second step that uses the carried key columns (48 rows now: the state grew)
+    got2, *_ = solver.step(_terms(dd, mean, inv_var, dev), t1, np.float32(0.1), got, None, state, False)
+    want2 = ref.mcc_step(want, t1, np.float32(0.1), lambda q: ref.gaussian_diag_drift(q, mean, inv_var),
+                         ref.hadamard_points(dd), ref.hadamard_weights(dd), SQRT2, okern)
+    assert solver.last_path == "fused:box_prk_step+keycols" and np.array_equal(got2.cpu().numpy(), want2)
