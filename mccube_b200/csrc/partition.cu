@@ -67,17 +67,22 @@ box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ parti
   for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   if (VEC4) {
-    // 4 consecutive aligned key columns and the Hadamard cubature: one 128-bit load (64-byte L2
-    // fill) per parent, two parents in flight per thread
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += 2 * stride) {
-      float vm0[4], vp0[4], vm1[4], vp1[4];
-      const bool two = i + stride < a.n;
-      key_children4(a, spec, i, vm0, vp0);
-      key_children4(a, spec, two ? i + stride : i, vm1, vp1);
+    // 4 consecutive aligned key columns and the Hadamard cubature: one 128-bit load per parent (from the
+    // packed key columns, or a 64-byte L2 fill from the strided state), four parents in flight per thread
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += 4 * stride) {
+      float vm[4][4], vp[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t iu = i + (uint64_t)u * stride;
+        key_children4(a, spec, iu < a.n ? iu : i, vm[u], vp[u]);   // past the end: repeat parent i (min/max unchanged)
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        lo[q] = fminf(lo[q], fminf(fminf(vm0[q], vp0[q]), fminf(vm1[q], vp1[q])));
-        hi[q] = fmaxf(hi[q], fmaxf(fmaxf(vm0[q], vp0[q]), fmaxf(vm1[q], vp1[q])));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          lo[q] = fminf(lo[q], fminf(vm[u][q], vp[u][q]));
+          hi[q] = fmaxf(hi[q], fmaxf(vm[u][q], vp[u][q]));
+        }
       }
     }
   } else {
