@@ -500,7 +500,9 @@ struct FlatRound {
   bool valid;
 };
 
-template <bool PRE_SMEM, bool MEM_SMEM>
+// POW2: in_per_part is a power of two (the runtime test made the compiler evaluate the ~20-instruction
+// integer modulo for every record and select afterwards: 11 % of the kernel's instructions).
+template <bool PRE_SMEM, bool MEM_SMEM, bool POW2>
 __global__ void __launch_bounds__(256, 4)
 box_rank_flat_kernel(const BoxPrkParams p) {
   extern __shared__ uint32_t smem[];
@@ -554,7 +556,7 @@ box_rank_flat_kernel(const BoxPrkParams p) {
       const uint4 e4 = hq[(q_head + (uint32_t)lane) & (FQ_CAP - 1)];
       const uint32_t rank0 = e4.x, first = e4.y, n_hit = e4.z & 0x7FFu;
       uint32_t part0, pos0;
-      if (p.in_shift != 0xFFFFFFFFu) { part0 = rank0 >> p.in_shift; pos0 = rank0 & (Pm - 1u); }
+      if (POW2) { part0 = rank0 >> p.in_shift; pos0 = rank0 & (Pm - 1u); }
       else { part0 = rank0 / Pm; pos0 = rank0 - part0 * Pm; }
       const uint16_t* mem = members + (e4.z >> 11) - pos0;
       uint32_t* out0 = p.idx_out + (uint64_t)part0 * nm;
@@ -587,7 +589,7 @@ box_rank_flat_kernel(const BoxPrkParams p) {
     uint32_t n_hit = 0, rank0 = 0, first = 0;
     if (o.valid) {
       rank0 = st + __ldg(p.key_start + o.key) + (o.exu << ushift);
-      const uint32_t pos0 = p.in_shift != 0xFFFFFFFFu ? (rank0 & (Pm - 1u)) : (rank0 % Pm);
+      const uint32_t pos0 = POW2 ? (rank0 & (Pm - 1u)) : (rank0 % Pm);
       first = PRE(pos0);
       n_hit = PRE(pos0 + ((1u << o.e) << ushift)) - first;   // size <= k <= Pm: the extended table covers the wrap
     }
@@ -803,16 +805,22 @@ static int launch_count(BoxPrkParams& p, const PrkPlan& pl, cudaStream_t st) {
 
 static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cudaStream_t st) {
   phase_mark("box_prk.rank", st);
-#define MCCB_FLAT(PS, MS)                                                                                          \
-  do {                                                                                                             \
-    cudaFuncSetAttribute(box_rank_flat_kernel<PS, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
-    box_rank_flat_kernel<PS, MS><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
+#define MCCB_FLAT2(PS, MS, P2)                                                                                          \
+  do {                                                                                                                  \
+    cudaFuncSetAttribute(box_rank_flat_kernel<PS, MS, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_b); \
+    box_rank_flat_kernel<PS, MS, P2><<<pl.grid_b, pl.warps_per_cta * 32, pl.smem_b, st>>>(p);                          \
+  } while (0)
+#define MCCB_FLAT(PS, MS)                                      \
+  do {                                                         \
+    if (p.in_shift != 0xFFFFFFFFu) MCCB_FLAT2(PS, MS, true);   \
+    else MCCB_FLAT2(PS, MS, false);                            \
   } while (0)
   if (pl.pre_in_smem && pl.mem_in_smem) MCCB_FLAT(true, true);
   else if (pl.pre_in_smem) MCCB_FLAT(true, false);
   else if (pl.mem_in_smem) MCCB_FLAT(false, true);
   else MCCB_FLAT(false, false);
 #undef MCCB_FLAT
+#undef MCCB_FLAT2
   // gather: the HBM-bound fused expand+select materialises the selected children
   ExpandArgs g = p.a;
   g.keycols = nullptr;
