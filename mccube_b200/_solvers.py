@@ -70,6 +70,7 @@ class MCCSolver(AbstractWrappedSolver):
         self.time_dtype = np.dtype(time_dtype)
         self.fused = fused
         self.last_path = None  # which implementation the last step took (for tests / bench)
+        self._point_tables: dict = {}
         self.__check_init__()
 
     def __check_init__(self):
@@ -123,10 +124,18 @@ class MCCSolver(AbstractWrappedSolver):
         if isinstance(cubature, Hadamard):
             cub = _lib.make_cubature(k, scale=np.float32(g * coeff))
         else:
-            pts = (g * (coeff * cubature.stacked_points.astype(np.float32))).astype(np.float32)
-            pts_t = torch.tensor(pts, dtype=torch.float32, device=y.device)
-            lam = torch.tensor(cubature.stacked_weights.astype(np.float32), device=y.device)
-            cub = _lib.make_cubature(k, points=pts_t, lam=lam)
+            # scaled point table, uploaded once per (formula, g, coeff): a constant-step solve re-uses it
+            # every step, and a step that uploads nothing can be captured in a CUDA graph
+            ck = (id(cubature), float(g), float(coeff), str(y.device))
+            hit = self._point_tables.get(ck)
+            if hit is None:
+                pts = (g * (coeff * cubature.stacked_points.astype(np.float32))).astype(np.float32)
+                hit = (torch.tensor(pts, dtype=torch.float32, device=y.device),
+                       torch.tensor(cubature.stacked_weights.astype(np.float32), device=y.device), cubature)
+                if len(self._point_tables) >= 256:   # distinct float32 step lengths of one solve: a handful
+                    self._point_tables.pop(next(iter(self._point_tables)))
+                self._point_tables[ck] = hit
+            cub = _lib.make_cubature(k, points=hit[0], lam=hit[1])
         f = terms.ode.vector_field
         if isinstance(f, GaussianDiagDrift) and self.fused:
             drift = _lib.make_drift(2, mean=f.mean, inv_var=f.inv_var)
@@ -247,6 +256,8 @@ class MCCSolver(AbstractWrappedSolver):
         tables = _lib.box_prk_tables(k, dims, part.bits, y0c.device) if use_kernel else None
         # (no side.wait_stream(main): the draw reads nothing the main stream produces, so it may
         # also overlap the previous step's gather)
+        if torch.cuda.is_current_stream_capturing():
+            side.wait_stream(main)       # fork the side stream into the capture
         with torch.cuda.stream(side):
             idx_local = mc.indices(t0, in_per_part, out_per_part, y0c.device)
             sel = _lib.box_prk_selection(idx_local, in_per_part) if use_kernel else None

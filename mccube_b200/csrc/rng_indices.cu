@@ -119,18 +119,34 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t count, uint32_t* __r
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[i] = i;
 }
 
-// _shuffle for small inputs in ONE launch: a single CTA derives the keys, then per round draws
-// the 32-bit sort keys and sorts (key << 32 | position) with a shared-memory bitonic network --
-// positions are unique, so the unstable network reproduces the stable sort_key_val exactly.
-constexpr int SMALL_SHUFFLE_MAX = 8192;
+// _shuffle for small inputs in ONE launch.  A single CTA derives the keys, then per round draws the 32-bit
+// sort keys (kept in registers, 16 per thread) and sorts by them entirely in shared memory.  The keys are
+// uniform random words, so the sort is one counting pass over their top 13 bits (8192 buckets, ~n/8192
+// elements each: shared-memory atomics hand out the slot inside the bucket) followed by an insertion sort
+// of every bucket on (key, position) -- positions are unique, which makes the order inside a bucket
+// independent of the order the atomics were served in and equal to the stable sort_key_val's.
+// One SM's issue rate bounds it: ~10 us per round at 16384 elements, mostly the threefry blocks.
+constexpr int SMALL_SHUFFLE_MAX = 16384;
+constexpr int SS_THREADS = 1024, SS_SLOTS = SMALL_SHUFFLE_MAX / SS_THREADS, SS_BUCKETS = 8192, SS_BUCKET_SHIFT = 19;
 
-__global__ void __launch_bounds__(1024)
-small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t npad, uint32_t count, uint32_t* __restrict__ out) {
-  extern __shared__ unsigned long long s_comp[];        // [npad]
-  uint32_t* xa = reinterpret_cast<uint32_t*>(s_comp + npad);   // [npad]
-  uint32_t* xb = xa + npad;                                      // [npad]
+static size_t small_shuffle_smem(uint32_t n) {
+  const size_t na = ((size_t)n + 7) & ~(size_t)7;
+  return na * 10 + (size_t)SS_BUCKETS * 4;
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t count, uint32_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const uint32_t na = (n + 7u) & ~7u;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(s_raw);           // [SS_BUCKETS] counts, then bucket starts
+  uint32_t* kb = cnt + SS_BUCKETS;                              // [na] keys in bucket order
+  uint16_t* pb = reinterpret_cast<uint16_t*>(kb + na);          // [na] their positions
+  uint16_t* xa = pb + na;                                       // [na] the sequence being shuffled
+  uint16_t* xb = xa + na;                                       // [na] ... and its next version
   __shared__ u32x2 s_sub[MAX_ROUNDS];
+  __shared__ uint32_t s_warp_tot[SS_THREADS / 32];
   const bool part = rng.partitionable != 0;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     u32x2 key = {rng.key[0], rng.key[1]};
     if (rng.key_dev) key = {rng.key_dev[0], rng.key_dev[1]};
@@ -145,31 +161,89 @@ small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t npad, uin
       key = nk;
     }
   }
-  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) xa[i] = i;
+  for (uint32_t i = threadIdx.x; i < SS_BUCKETS; i += SS_THREADS) cnt[i] = 0;
   __syncthreads();
+  const uint32_t h = (n + 1u) >> 1;                             // original mode: block b yields elements b and b + h
   for (int r = 0; r < rounds; ++r) {
     const u32x2 sub = s_sub[r];
-    for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
-      s_comp[i] = i < n ? (((unsigned long long)random_bits32_at(sub, i, n, part) << 32) | i) : ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= npad; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
-          const uint32_t ixj = i ^ j;
-          if (ixj > i) {
-            const unsigned long long a = s_comp[i], b = s_comp[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { s_comp[i] = b; s_comp[ixj] = a; }
-          }
-        }
-        __syncthreads();
+    uint32_t key[SS_SLOTS], slot[SS_SLOTS];                     // slot s of this thread: element pos_of(s)
+    auto pos_of = [&](int s) -> uint32_t {
+      return part ? threadIdx.x + (uint32_t)s * SS_THREADS
+                  : threadIdx.x + (uint32_t)(s >> 1) * SS_THREADS + ((s & 1) ? h : 0u);
+    };
+    auto live_at = [&](int s) -> bool {
+      const uint32_t b = threadIdx.x + (uint32_t)(s >> 1) * SS_THREADS;
+      return part ? pos_of(s) < n : (b < h && pos_of(s) < n);
+    };
+    if (part) {
+#pragma unroll
+      for (int s = 0; s < SS_SLOTS; ++s) {
+        const u32x2 o = threefry2x32(sub.x, sub.y, 0u, pos_of(s));
+        key[s] = o.x ^ o.y;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < SS_SLOTS; s += 2) {
+        const uint32_t b = threadIdx.x + (uint32_t)(s >> 1) * SS_THREADS;
+        const u32x2 o = threefry2x32(sub.x, sub.y, b, b + h < n ? b + h : 0u);   // the pad element counts as 0
+        key[s] = o.x;
+        key[s + 1] = o.y;
       }
     }
-    for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) xb[q] = xa[(uint32_t)s_comp[q]];
+#pragma unroll
+    for (int s = 0; s < SS_SLOTS; ++s)
+      if (live_at(s)) slot[s] = atomicAdd(&cnt[key[s] >> SS_BUCKET_SHIFT], 1u);
     __syncthreads();
-    uint32_t* t = xa; xa = xb; xb = t;
+    {  // exclusive scan of the bucket counts: 8 consecutive buckets per thread
+      static_assert(SS_BUCKETS == 8 * SS_THREADS, "scan layout");
+      uint32_t* mine = cnt + threadIdx.x * 8;
+      const uint4 v = *reinterpret_cast<uint4*>(mine), u = *reinterpret_cast<uint4*>(mine + 4);
+      const uint32_t sv = v.x + v.y + v.z + v.w;
+      const uint32_t sum = sv + u.x + u.y + u.z + u.w;
+      uint32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += up;
+      }
+      if (lane == 31) s_warp_tot[warp] = inc;
+      __syncthreads();
+      const uint32_t base = inc - sum + __reduce_add_sync(0xFFFFFFFFu, lane < warp ? s_warp_tot[lane] : 0u);
+      *reinterpret_cast<uint4*>(mine) = make_uint4(base, base + v.x, base + v.x + v.y, base + v.x + v.y + v.z);
+      const uint32_t b2 = base + sv;
+      *reinterpret_cast<uint4*>(mine + 4) = make_uint4(b2, b2 + u.x, b2 + u.x + u.y, b2 + u.x + u.y + u.z);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < SS_SLOTS; ++s)
+      if (live_at(s)) {
+        const uint32_t dst = cnt[key[s] >> SS_BUCKET_SHIFT] + slot[s];
+        kb[dst] = key[s];
+        pb[dst] = (uint16_t)pos_of(s);
+      }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < SS_BUCKETS; j += SS_THREADS) {   // insertion sort of bucket j on (key, position)
+      const uint32_t lo = cnt[j], hi = j + 1 < SS_BUCKETS ? cnt[j + 1] : n;
+      for (uint32_t a = lo + 1; a < hi; ++a) {
+        const uint32_t ak = kb[a];
+        const uint16_t ap = pb[a];
+        uint32_t q = a;
+        while (q > lo && (kb[q - 1] > ak || (kb[q - 1] == ak && pb[q - 1] > ap))) {
+          kb[q] = kb[q - 1];
+          pb[q] = pb[q - 1];
+          --q;
+        }
+        kb[q] = ak;
+        pb[q] = ap;
+      }
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n; q += SS_THREADS) xb[q] = r == 0 ? pb[q] : xa[pb[q]];
+    for (uint32_t i = threadIdx.x; i < SS_BUCKETS; i += SS_THREADS) cnt[i] = 0;
+    __syncthreads();
+    { uint16_t* t = xa; xa = xb; xb = t; }
   }
-  for (uint32_t q = threadIdx.x; q < count; q += blockDim.x) out[q] = xa[q];
+  for (uint32_t q = threadIdx.x; q < count; q += SS_THREADS) out[q] = xa[q];
 }
 
 static int shuffle_rounds(uint64_t size) {
@@ -225,16 +299,15 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
     return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_indices: workspace %zu < %zu", workspace_bytes, p.total);
   if (count == 0) return MCCB200_OK;
   if (!replace && p.rounds > 0 && n_inputs <= (uint64_t)SMALL_SHUFFLE_MAX) {
-    uint32_t npad = 2;
-    while (npad < n_inputs) npad <<= 1;
-    const size_t smem = (size_t)npad * 16;
+    const size_t smem = small_shuffle_smem((uint32_t)n_inputs);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(small_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SHUFFLE_MAX * 16);
+      cudaFuncSetAttribute(small_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)small_shuffle_smem(SMALL_SHUFFLE_MAX));
       attr_set = true;
     }
     phase_mark("mc_indices", st);
-    small_shuffle_kernel<<<1, 1024, smem, st>>>(*rng, p.rounds, (uint32_t)n_inputs, npad, (uint32_t)count, idx_out);
+    small_shuffle_kernel<<<1, SS_THREADS, smem, st>>>(*rng, p.rounds, (uint32_t)n_inputs, (uint32_t)count, idx_out);
     phase_mark("end", st);
     count_launches(1);
     return check_launch("mc_indices(small shuffle)");

@@ -216,3 +216,51 @@ def diffeqsolve(terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = S
         ts_out.append(np.dtype(time_dtype).type(t1)); ys_out.append(y)
     return Solution(t0=t0, t1=t1, ts=np.array(ts_out), ys=_stack(ys_out), result=result,
                     stats=dict(num_steps=len(times)), interpolation=interps or None)
+
+
+class CapturedSolve:
+    """A whole constant-step solve captured ONCE as a CUDA graph and replayed per call: the counterpart
+    of `jax.jit(diffeqsolve)` (the reference runs the loop inside one XLA executable, README.md:82-84).
+    Every step's scalars (t0 bits folded into the key, dt, cubature scale) are baked into the graph's
+    kernel arguments, so a replay launches the same kernels on the same addresses with no Python and no
+    per-kernel launch latency -- what makes the small configurations (README: n=512, 512 steps) fast.
+
+        solve = capture_solve(terms, solver, t0, t1, dt0, y0, args, saveat=...)
+        sol = solve(y0)            # any y0 of the captured shape / dtype / device
+    """
+
+    def __init__(self, terms, solver, t0, t1, dt0, y0, args=None, *, saveat: SaveAt = SaveAt(t1=True),
+                 max_steps: int = 4096, time_dtype=np.float32):
+        if not (isinstance(y0, torch.Tensor) and y0.is_cuda):
+            raise ValueError("capture_solve needs a CUDA tensor state")
+        if saveat.dense:
+            raise ValueError("capture_solve: SaveAt(dense=True) keeps every step alive; use ts= or steps=")
+        self._y0 = y0.detach().clone()
+        run = lambda: diffeqsolve(terms, solver, t0, t1, dt0, self._y0, args, saveat=saveat,
+                                  max_steps=max_steps, time_dtype=time_dtype)
+        # one eager solve first: lazy one-time work (function attributes, cached tables and point uploads,
+        # the caching allocator's pool) must not happen inside the capture
+        warm = torch.cuda.Stream(device=y0.device)
+        warm.wait_stream(torch.cuda.current_stream(y0.device))
+        with torch.cuda.stream(warm):
+            run()
+        torch.cuda.current_stream(y0.device).wait_stream(warm)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._sol = run()
+
+    def __call__(self, y0) -> Solution:
+        from ._tree import tree_map
+
+        if y0.shape != self._y0.shape or y0.dtype != self._y0.dtype or y0.device != self._y0.device:
+            raise ValueError(f"captured for {tuple(self._y0.shape)} {self._y0.dtype} on {self._y0.device}")
+        self._y0.copy_(y0)
+        self.graph.replay()
+        s = self._sol
+        # the graph's buffers are overwritten by the next replay: hand out copies
+        return Solution(t0=s.t0, t1=s.t1, ts=s.ts.copy(), ys=tree_map(lambda a: a.clone(), s.ys),
+                        result=s.result, stats=dict(s.stats, cuda_graph=True))
+
+
+def capture_solve(*a, **kw) -> CapturedSolve:
+    return CapturedSolve(*a, **kw)

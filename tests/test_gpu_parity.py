@@ -44,8 +44,12 @@ def test_mc_indices_golden(dev):
 @pytest.mark.parametrize("partitionable", [False, True])
 @pytest.mark.parametrize("replace", [False, True])
 def test_mc_indices_vs_oracle_ragged(dev, partitionable, replace):
-    for (P, n, t, leaf, n_leaves) in [(1, 1, 0.0, 0, 1), (2, 2, 0.3, 0, 1), (4097, 4097, -1.5, 1, 3),
-                                      ((1 << 20) + 3, 5000, 12.75, 0, 2)]:
+    # up to 16384 inputs the shuffle is one single-CTA launch (per-warp chunks: sizes around the 32 / 1024
+    # boundaries, the largest size and one past it), above that the multi-kernel radix sort
+    for (P, n, t, leaf, n_leaves) in [(1, 1, 0.0, 0, 1), (2, 2, 0.3, 0, 1), (31, 7, 0.1, 0, 1), (33, 33, 0.1, 0, 1),
+                                      (1023, 100, 0.2, 0, 1), (1025, 1025, 0.2, 0, 1), (4097, 4097, -1.5, 1, 3),
+                                      (8192, 64, 0.05, 0, 1), (12345, 12345, 0.7, 0, 1), (16384, 512, 0.0, 0, 1),
+                                      (16385, 512, 0.0, 0, 1), ((1 << 20) + 3, 5000, 12.75, 0, 2)]:
         key = jr.mc_step_key(jr.prng_key(42), t, leaf=leaf, n_leaves=n_leaves, partitionable=partitionable)
         want = jr.choice_indices(key, P, n, replace, partitionable=partitionable)
         rng = _lib.make_rng(KEY, t, leaf=leaf, n_leaves=n_leaves, partitionable=partitionable)
@@ -425,6 +429,55 @@ def test_box_step_key_column_carry(dev):
         else:
             assert all(q == "fused:box_prk_step" for q in paths), paths
     assert torch.equal(outs[True], outs[False])
+
+
+def test_captured_solve_matches_eager(dev):
+    """The whole README solve (config 1) replayed from one CUDA graph: bit-identical to the eager loop, for
+    the captured y0 and for a different y0 fed to the same graph, on both index paths."""
+    z = np.load(GOLDEN / "readme_trajectory.npz")
+    n, d = 512, 10
+    t0, dt0 = 0.0, 0.05
+    t1 = t0 + dt0 * 512
+    terms = _terms(d, (2 * np.ones(d)).astype(np.float32), (np.ones(d) / 3.0).astype(np.float32), dev)
+    for replace in (False, True):
+        tag = f"r{int(replace)}"
+        solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, replace, key=42))
+        y0 = torch.ones((n, d), device=dev)
+        solve = dfx.capture_solve(terms, solver, t0, t1, dt0, y0, saveat=dfx.SaveAt(ts=[dt0, 64 * dt0], t1=True))
+        sol = solve(y0)
+        assert sol.stats["cuda_graph"] and sol.ys.shape[0] == 3
+        assert np.array_equal(sol.ys[-1].cpu().numpy(), z[f"y_step{int(z[f'n_steps_{tag}']) - 1}_{tag}"]), tag
+        other = cuda(np.random.default_rng(9).normal(size=(n, d)).astype(np.float32), dev)
+        eager = dfx.diffeqsolve(terms, solver, t0, t1, dt0, other, saveat=dfx.SaveAt(ts=[dt0, 64 * dt0], t1=True))
+        again = solve(other)
+        assert torch.equal(again.ys, eager.ys) and np.array_equal(again.ts, eager.ts)
+        assert torch.equal(solve(y0).ys, sol.ys)           # and back: replays are independent
+
+
+def test_captured_solve_box_partition_and_table_formula(dev):
+    """Capture covers the side-stream index draw of the box + PRK step (with the key-column carry) and a
+    point-table formula (whose scaled points are uploaded once, outside the capture)."""
+    rs = np.random.default_rng(5)
+    n, d = 4096, 16
+    y0 = cuda((rs.normal(size=(n, d)) * 1.5 + 1.0).astype(np.float32), dev)
+    terms = _terms(d, np.full(d, 2.0, np.float32), np.full(d, 1.0 / 3.0, np.float32), dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+        mccube.BoxPartitionKernel(n // 16, dims=(4, 5, 6, 7), bits=2), mccube.MonteCarloKernel(16, key=7)))
+    eager = dfx.diffeqsolve(terms, solver, 0.0, 0.4, 0.05, y0, saveat=dfx.SaveAt(steps=True))
+    solve = dfx.capture_solve(terms, solver, 0.0, 0.4, 0.05, y0, saveat=dfx.SaveAt(steps=True))
+    assert solver.last_path == "fused:box_prk_step+keycols"
+    for _ in range(2):
+        assert torch.equal(solve(y0).ys, eager.ys)
+
+    d = 3
+    f = mccube.GaussianDiagDrift(np.full(d, 2.0, np.float32), np.full(d, 3.0), device=dev)
+    terms = mccube.MCCTerm(dfx.ODETerm(f), dfx.WeaklyDiagonalControlTerm(
+        lambda t, y, args: math.sqrt(2.0), mccube.LocalLinearCubaturePath(mccube.StroudSecrest63_31(mccube.GaussianRegion(d)))))
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(256, key=3))
+    y0 = cuda(rs.normal(size=(256, d)).astype(np.float32), dev)
+    eager = dfx.diffeqsolve(terms, solver, 0.0, 1.0, 0.05, y0)
+    assert torch.equal(dfx.capture_solve(terms, solver, 0.0, 1.0, 0.05, y0)(y0).ys, eager.ys)
+    assert len(solver._point_tables) <= 8                   # one upload per distinct float32 step length
 
 
 # ------------------------------------------------------------------ A11: metrics
