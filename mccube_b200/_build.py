@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MCCB200_NVCC_FLAGS", "").split()      # e.g. -DMCCB200_SS_TRACE for the debug clock stamps
 
 
 def _digest(paths) -> str:

@@ -120,28 +120,37 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t count, uint32_t* __r
 }
 
 // _shuffle for small inputs in ONE launch.  A single CTA derives the keys, then per round draws the 32-bit
-// sort keys (kept in registers, 16 per thread) and sorts by them entirely in shared memory.  The keys are
-// uniform random words, so the sort is one counting pass over their top 13 bits (8192 buckets, ~n/8192
-// elements each: shared-memory atomics hand out the slot inside the bucket) followed by an insertion sort
-// of every bucket on (key, position) -- positions are unique, which makes the order inside a bucket
-// independent of the order the atomics were served in and equal to the stable sort_key_val's.
-// One SM's issue rate bounds it: ~10 us per round at 16384 elements, mostly the threefry blocks.
+// sort keys (kept in registers, up to 16 per thread) and sorts by them entirely in shared memory.  The keys
+// are uniform random words, so the sort is a counting pass over their top 14 bits (16384 buckets, at most
+// ~1 element each on average: shared-memory atomics hand out a slot inside the bucket) after which every
+// element finds its final place as "start of its bucket + members that order before it on (key, position)".
+// Positions are unique, so the result does not depend on the order the atomics were served in and equals
+// the stable sort_key_val's.  A bucket member is one word: the key's low 18 bits above the 14-bit position.
+// The kernel is bound by one SM's issue rate (threefry) and by bank conflicts of the random shared-memory
+// accesses (~3.5 cycles per warp access): every phase is written for the fewest such accesses.
 constexpr int SMALL_SHUFFLE_MAX = 16384;
-constexpr int SS_THREADS = 1024, SS_SLOTS = SMALL_SHUFFLE_MAX / SS_THREADS, SS_BUCKETS = 8192, SS_BUCKET_SHIFT = 19;
+constexpr int SS_THREADS = 1024, SS_SLOTS = SMALL_SHUFFLE_MAX / SS_THREADS;
+constexpr int SS_BUCKET_BITS = 14, SS_BUCKETS = 1 << SS_BUCKET_BITS, SS_BUCKET_SHIFT = 32 - SS_BUCKET_BITS;
+static_assert(SMALL_SHUFFLE_MAX <= (1 << 14) && SS_BUCKET_SHIFT + 14 == 32, "a bucket member packs into 32 bits");
 
 static size_t small_shuffle_smem(uint32_t n) {
   const size_t na = ((size_t)n + 7) & ~(size_t)7;
-  return na * 10 + (size_t)SS_BUCKETS * 4;
+  return na * 8 + (size_t)SS_BUCKETS * 4;
 }
 
+#ifdef MCCB200_SS_TRACE
+__device__ long long g_ss_trace[16];
+#define SS_TRACE(k) do { if (threadIdx.x == 0 && r == 0) g_ss_trace[k] = clock64(); } while (0)
+#else
+#define SS_TRACE(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(SS_THREADS)
 small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t count, uint32_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t na = (n + 7u) & ~7u;
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(s_raw);           // [SS_BUCKETS] counts, then bucket starts
-  uint32_t* kb = cnt + SS_BUCKETS;                              // [na] keys in bucket order
-  uint16_t* pb = reinterpret_cast<uint16_t*>(kb + na);          // [na] their positions
-  uint16_t* xa = pb + na;                                       // [na] the sequence being shuffled
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(s_raw);           // [SS_BUCKETS] counts, then start | count << 16
+  uint32_t* el = cnt + SS_BUCKETS;                              // [na] bucket members: key low bits << 14 | position
+  uint16_t* xa = reinterpret_cast<uint16_t*>(el + na);          // [na] the sequence being shuffled
   uint16_t* xb = xa + na;                                       // [na] ... and its next version
   __shared__ u32x2 s_sub[MAX_ROUNDS];
   __shared__ uint32_t s_warp_tot[SS_THREADS / 32];
@@ -161,11 +170,12 @@ small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t count, ui
       key = nk;
     }
   }
-  for (uint32_t i = threadIdx.x; i < SS_BUCKETS; i += SS_THREADS) cnt[i] = 0;
+  for (uint32_t i = threadIdx.x; i < SS_BUCKETS / 4; i += SS_THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const uint32_t h = (n + 1u) >> 1;                             // original mode: block b yields elements b and b + h
   for (int r = 0; r < rounds; ++r) {
     const u32x2 sub = s_sub[r];
+    SS_TRACE(0);
     uint32_t key[SS_SLOTS], slot[SS_SLOTS];                     // slot s of this thread: element pos_of(s)
     auto pos_of = [&](int s) -> uint32_t {
       return part ? threadIdx.x + (uint32_t)s * SS_THREADS
@@ -178,69 +188,90 @@ small_shuffle_kernel(mccb200_rng rng, int rounds, uint32_t n, uint32_t count, ui
     if (part) {
 #pragma unroll
       for (int s = 0; s < SS_SLOTS; ++s) {
+        if ((uint32_t)s * SS_THREADS >= n) { key[s] = 0; continue; }       // CTA-uniform
         const u32x2 o = threefry2x32(sub.x, sub.y, 0u, pos_of(s));
         key[s] = o.x ^ o.y;
       }
     } else {
 #pragma unroll
       for (int s = 0; s < SS_SLOTS; s += 2) {
+        if ((uint32_t)(s >> 1) * SS_THREADS >= h) { key[s] = key[s + 1] = 0; continue; }   // CTA-uniform
         const uint32_t b = threadIdx.x + (uint32_t)(s >> 1) * SS_THREADS;
         const u32x2 o = threefry2x32(sub.x, sub.y, b, b + h < n ? b + h : 0u);   // the pad element counts as 0
         key[s] = o.x;
         key[s + 1] = o.y;
       }
     }
+    SS_TRACE(1);
 #pragma unroll
     for (int s = 0; s < SS_SLOTS; ++s)
       if (live_at(s)) slot[s] = atomicAdd(&cnt[key[s] >> SS_BUCKET_SHIFT], 1u);
     __syncthreads();
-    {  // exclusive scan of the bucket counts: 8 consecutive buckets per thread
-      static_assert(SS_BUCKETS == 8 * SS_THREADS, "scan layout");
-      uint32_t* mine = cnt + threadIdx.x * 8;
-      const uint4 v = *reinterpret_cast<uint4*>(mine), u = *reinterpret_cast<uint4*>(mine + 4);
-      const uint32_t sv = v.x + v.y + v.z + v.w;
-      const uint32_t sum = sv + u.x + u.y + u.z + u.w;
-      uint32_t inc = sum;
+    SS_TRACE(2);
+    {  // exclusive scan of the bucket counts; leaves start | count << 16.  Warp w owns 512 consecutive buckets,
+       // read as 4 conflict-free rows of 32 x uint4
+      static_assert(SS_BUCKETS == 16 * SS_THREADS, "scan layout");
+      uint4* mine = reinterpret_cast<uint4*>(cnt) + warp * 128 + lane;
+      uint32_t excl[4], carry = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= (uint32_t)o) inc += up;
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = mine[q * 32];
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+          if (lane >= (uint32_t)o) inc += up;
+        }
+        excl[q] = carry + inc - sum;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
       }
-      if (lane == 31) s_warp_tot[warp] = inc;
+      if (lane == 0) s_warp_tot[warp] = carry;
       __syncthreads();
-      const uint32_t base = inc - sum + __reduce_add_sync(0xFFFFFFFFu, lane < warp ? s_warp_tot[lane] : 0u);
-      *reinterpret_cast<uint4*>(mine) = make_uint4(base, base + v.x, base + v.x + v.y, base + v.x + v.y + v.z);
-      const uint32_t b2 = base + sv;
-      *reinterpret_cast<uint4*>(mine + 4) = make_uint4(b2, b2 + u.x, b2 + u.x + u.y, b2 + u.x + u.y + u.z);
+      const uint32_t wbase = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? s_warp_tot[lane] : 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = mine[q * 32];          // (re-read: conflict-free, cheaper than 16 live registers)
+        uint32_t base = wbase + excl[q];
+        uint4 w;
+        w.x = base | (v.x << 16); base += v.x;
+        w.y = base | (v.y << 16); base += v.y;
+        w.z = base | (v.z << 16); base += v.z;
+        w.w = base | (v.w << 16);
+        mine[q * 32] = w;
+      }
     }
     __syncthreads();
+    SS_TRACE(3);
 #pragma unroll
     for (int s = 0; s < SS_SLOTS; ++s)
       if (live_at(s)) {
-        const uint32_t dst = cnt[key[s] >> SS_BUCKET_SHIFT] + slot[s];
-        kb[dst] = key[s];
-        pb[dst] = (uint16_t)pos_of(s);
+        const uint32_t e = cnt[key[s] >> SS_BUCKET_SHIFT];           // start | count << 16
+        el[(e & 0xFFFFu) + slot[s]] = (key[s] << SS_BUCKET_BITS) | pos_of(s);
+        slot[s] = e;
       }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < SS_BUCKETS; j += SS_THREADS) {   // insertion sort of bucket j on (key, position)
-      const uint32_t lo = cnt[j], hi = j + 1 < SS_BUCKETS ? cnt[j + 1] : n;
-      for (uint32_t a = lo + 1; a < hi; ++a) {
-        const uint32_t ak = kb[a];
-        const uint16_t ap = pb[a];
-        uint32_t q = a;
-        while (q > lo && (kb[q - 1] > ak || (kb[q - 1] == ak && pb[q - 1] > ap))) {
-          kb[q] = kb[q - 1];
-          pb[q] = pb[q - 1];
-          --q;
+    SS_TRACE(4);
+    // final place = start of the bucket + members ordering before this one; the carried sequence moves there
+    // directly (round 0 starts from the identity)
+#pragma unroll
+    for (int s = 0; s < SS_SLOTS; ++s)
+      if (live_at(s)) {
+        const uint32_t pos = pos_of(s), members = slot[s] >> 16, me = (key[s] << SS_BUCKET_BITS) | pos;
+        uint32_t lo = slot[s] & 0xFFFFu;
+        if (members > 1) {     // (itself never counts; ~0 is no member's word below any `me`)
+          const uint32_t e0 = el[lo], e1 = el[lo + 1], e2 = members > 2 ? el[lo + 2] : ~0u, e3 = members > 3 ? el[lo + 3] : ~0u;
+          uint32_t before = (e0 < me) + (e1 < me) + (e2 < me) + (e3 < me);
+          for (uint32_t j = 4; j < members; ++j) before += el[lo + j] < me ? 1u : 0u;
+          lo += before;
         }
-        kb[q] = ak;
-        pb[q] = ap;
+        xb[lo] = r == 0 ? (uint16_t)pos : xa[pos];
       }
-    }
     __syncthreads();
-    for (uint32_t q = threadIdx.x; q < n; q += SS_THREADS) xb[q] = r == 0 ? pb[q] : xa[pb[q]];
-    for (uint32_t i = threadIdx.x; i < SS_BUCKETS; i += SS_THREADS) cnt[i] = 0;
+    SS_TRACE(5);
+    for (uint32_t i = threadIdx.x; i < SS_BUCKETS / 4; i += SS_THREADS) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    SS_TRACE(6);
     { uint16_t* t = xa; xa = xb; xb = t; }
   }
   for (uint32_t q = threadIdx.x; q < count; q += SS_THREADS) out[q] = xa[q];
@@ -278,6 +309,14 @@ static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
 }  // namespace mccb
 
 using namespace mccb;
+
+#ifdef MCCB200_SS_TRACE
+// Debug hook (not part of the C ABI): clock stamps of the first round of the last small_shuffle_kernel launch.
+extern "C" __attribute__((visibility("default"))) void mccb200_debug_ss_trace(long long* host) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, g_ss_trace, sizeof(long long) * 16);
+}
+#endif
 
 extern "C" size_t mccb200_mc_indices_workspace_bytes(uint64_t n_inputs, uint64_t count, int replace) {
   return make_idx_plan(n_inputs, count, replace).total;
