@@ -244,7 +244,17 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   MCCB_REQUIRE(bounds && n >= 1, "box_child_bounds: bad argument");
   if (!workspace || workspace_bytes < mccb200_box_bounds_workspace_bytes())
     return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "box_child_bounds: workspace too small");
-  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 6));
+  // grid-stride kernel: exactly one resident wave (6 CTAs/SM wanted, 4 fit at 58 registers: a grid of 6 per SM
+  // ran as 1.5 waves, the second one half empty)
+  static int per_sm_vec = 0, per_sm_gen = 0;
+  if (!per_sm_vec) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_vec, box_bounds_children_kernel<true>, BB_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_gen, box_bounds_children_kernel<false>, BB_THREADS, 0);
+    per_sm_vec = max(1, per_sm_vec); per_sm_gen = max(1, per_sm_gen);
+  }
+  const bool vec_path = !a.points && box_dims_vec4(s, a);
+  int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS,
+                      (uint64_t)min(BB_MAX_CTAS, sm_count() * (vec_path ? per_sm_vec : per_sm_gen)));
   cudaStream_t st = (cudaStream_t)stream;
   phase_mark("box_child_bounds", st);
   a.keycols = (!a.points && box_dims_vec4(s, a) && keycols && (((uintptr_t)keycols & 15) == 0)) ? keycols : nullptr;
