@@ -483,7 +483,9 @@ def test_captured_solve_box_partition_and_table_formula(dev):
 # ------------------------------------------------------------------ A11: metrics
 def test_moments_and_w2(dev):
     rs = np.random.default_rng(5)
-    for n, d in [(1000, 3), (50000, 10), (20000, 64), (3000, 130)]:
+    # ragged d (4-byte copies), whole float4 rows (16-byte copies), one tile and several (upper triangle + mirror),
+    # row counts that leave partial stages
+    for n, d in [(1000, 3), (50000, 10), (20000, 64), (3000, 130), (5001, 132), (40000, 256)]:
         p = (rs.normal(size=(n, d)) * rs.uniform(0.5, 2, size=d) + rs.normal(size=d) * 3).astype(np.float32)
         w = rs.uniform(0.1, 1.0, size=n).astype(np.float32)
         pt = cuda(p, dev)
