@@ -13,18 +13,39 @@ namespace mccb {
 constexpr int BB_THREADS = 256;
 constexpr int BB_MAX_CTAS = 1024;
 
-__global__ void __launch_bounds__(256)
+// One thread per row keeps the reference's left-to-right summation order (bit-exact keys), but a thread
+// walking its own 256-byte row touches 32 lines per warp load (1.1 TB/s).  So a CTA stages 256 rows x 32
+// columns at a time through shared memory with coalesced 128-byte reads, and every thread then sums its
+// row of the tile in order (pitch 33: conflict-free both ways).
+constexpr int SK_ROWS = 256, SK_COLS = 32;
+__global__ void __launch_bounds__(SK_ROWS)
 stratified_keys_kernel(const float* __restrict__ p, uint64_t n, int d, int ld, const float* __restrict__ com,
                        uint32_t* __restrict__ keys) {
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
-    const float* row = p + r * ld;
+  __shared__ float tile[SK_ROWS][SK_COLS + 1];
+  __shared__ float s_com[SK_COLS];
+  const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+  for (uint64_t rb = (uint64_t)blockIdx.x * SK_ROWS; rb < n; rb += (uint64_t)gridDim.x * SK_ROWS) {
     float acc = 0.0f;
-    for (int c = 0; c < d; ++c) {
-      float v = __fsub_rn(row[c], __ldg(com + c));
-      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    for (int cb = 0; cb < d; cb += SK_COLS) {
+      __syncthreads();                                      // the previous chunk has been consumed
+      if (threadIdx.x < SK_COLS) s_com[threadIdx.x] = cb + threadIdx.x < d ? __ldg(com + cb + threadIdx.x) : 0.0f;
+      float v[SK_ROWS / 8];
+#pragma unroll
+      for (int q = 0; q < SK_ROWS / 8; ++q) {               // warp w loads rows w, w + 8, ...: 128 contiguous bytes each
+        const uint64_t r = rb + wrow + q * 8;
+        v[q] = (r < n && cb + lane < d) ? __ldcs(p + r * ld + cb + lane) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < SK_ROWS / 8; ++q) tile[wrow + q * 8][lane] = v[q];
+      __syncthreads();
+      const int cols = min(SK_COLS, d - cb);
+      for (int c = 0; c < cols; ++c) {
+        const float x = __fsub_rn(tile[threadIdx.x][c], s_com[c]);
+        acc = __fadd_rn(acc, __fmul_rn(x, x));
+      }
     }
     // norm >= 0 (or NaN): the IEEE bit pattern of a non-negative float is order preserving.
-    keys[r] = __float_as_uint(__fsqrt_rn(acc));
+    if (rb + threadIdx.x < n) keys[rb + threadIdx.x] = __float_as_uint(__fsqrt_rn(acc));
   }
 }
 
@@ -44,18 +65,49 @@ __device__ __forceinline__ void block_minmax(float lo, float hi, float* out_lo, 
 }
 
 // partials layout: [cta][dim][2]
+// One pass over the rows for all key dims, four rows in flight per thread; VEC4: the dims are 4 consecutive
+// 16-byte aligned columns, read as one 128-bit load with a 64-byte L2 fill per row.
+template <bool VEC4>
 __global__ void __launch_bounds__(BB_THREADS)
 box_bounds_rows_kernel(const float* __restrict__ p, uint64_t n, int ld, BoxSpec spec, float* __restrict__ partials) {
-  for (int q = 0; q < spec.n_dims; ++q) {
-    float lo = INFINITY, hi = -INFINITY;
-    const int c = spec.dims[q];
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
-      float v = p[r * ld + c];
-      lo = fminf(lo, v); hi = fmaxf(hi, v);
+  float lo[MCCB200_BOX_MAX_DIMS], hi[MCCB200_BOX_MAX_DIMS];
+#pragma unroll
+  for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q) { lo[q] = INFINITY; hi[q] = -INFINITY; }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += 4 * stride) {
+    if (VEC4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t ru = r + (uint64_t)u * stride;
+        v[u] = ld_strided4(p + (ru < n ? ru : r) * ld + spec.dims[0]);   // past the end: repeat row r
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        lo[0] = fminf(lo[0], v[u].x); hi[0] = fmaxf(hi[0], v[u].x);
+        lo[1] = fminf(lo[1], v[u].y); hi[1] = fmaxf(hi[1], v[u].y);
+        lo[2] = fminf(lo[2], v[u].z); hi[2] = fmaxf(hi[2], v[u].z);
+        lo[3] = fminf(lo[3], v[u].w); hi[3] = fmaxf(hi[3], v[u].w);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t ru = r + (uint64_t)u * stride;
+        const float* row = p + (ru < n ? ru : r) * ld;
+#pragma unroll
+        for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q)
+          if (q < spec.n_dims) {
+            const float x = ld_strided(row + spec.dims[q]);
+            lo[q] = fminf(lo[q], x); hi[q] = fmaxf(hi[q], x);
+          }
+      }
     }
-    block_minmax(lo, hi, partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
-                 partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
   }
+#pragma unroll
+  for (int q = 0; q < MCCB200_BOX_MAX_DIMS; ++q)
+    if (q < spec.n_dims)
+      block_minmax(lo[q], hi[q], partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2,
+                   partials + ((size_t)blockIdx.x * spec.n_dims + q) * 2 + 1);
 }
 
 template <bool VEC4>
@@ -196,8 +248,8 @@ extern "C" int mccb200_stratified_keys(const float* p, uint64_t n, int d, int ld
                                        void* stream) {
   MCCB_REQUIRE(p && com && keys && d >= 1 && ld >= d, "stratified_keys: bad argument");
   if (n == 0) return MCCB200_OK;
-  int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
-  stratified_keys_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, n, d, ld, com, keys);
+  int grid = (int)min((n + SK_ROWS - 1) / SK_ROWS, (uint64_t)sm_count() * 6);
+  stratified_keys_kernel<<<grid, SK_ROWS, 0, (cudaStream_t)stream>>>(p, n, d, ld, com, keys);
   count_launches(1);
   return check_launch("stratified_keys");
 }
@@ -212,7 +264,10 @@ extern "C" int mccb200_box_bounds(const float* p, uint64_t n, int ld, const int3
     return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "box_bounds: workspace too small");
   int grid = (int)min((n + BB_THREADS - 1) / BB_THREADS, (uint64_t)min(BB_MAX_CTAS, sm_count() * 4));
   cudaStream_t st = (cudaStream_t)stream;
-  box_bounds_rows_kernel<<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
+  bool vec4 = s.n_dims == 4 && (s.dims[0] & 3) == 0 && (ld & 3) == 0 && (((uintptr_t)p) & 15) == 0;
+  for (int q = 1; q < 4 && vec4; ++q) vec4 = s.dims[q] == s.dims[0] + q;
+  if (vec4) box_bounds_rows_kernel<true><<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
+  else box_bounds_rows_kernel<false><<<grid, BB_THREADS, 0, st>>>(p, n, ld, s, (float*)workspace);
   box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);
   count_launches(2);
   return check_launch("box_bounds");
