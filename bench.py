@@ -35,6 +35,18 @@ from pathlib import Path
 
 import numpy as np
 
+# stdout carries exactly one JSON line.  Libraries write there too (with NCCL_DEBUG=VERSION, as set on the GPU
+# boxes, NCCL prints "NCCL version ..." to stdout at the first collective), so file descriptor 1 is pointed
+# at stderr for everything else and the result line goes to a private copy of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -161,7 +173,7 @@ def reference_arm(a):
         "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -675,7 +687,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
