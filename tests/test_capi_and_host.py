@@ -200,3 +200,24 @@ def test_cubature_registry_search_and_permutations():
     assert np.array_equal(rr, [[-3, -3, -3], [-3, -3, 3], [-3, 3, -3], [-3, 3, 3], [3, -3, -3], [3, -3, 3], [3, 3, -3], [3, 3, 3]])
     with pytest.raises(ValueError):
         _generate_point_permutations(np.ones(2), "X")
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the oracle on the host cores) needs no GPU; stdout is exactly one JSON
+    line with the contract's keys, whatever else the process prints (that goes to stderr)."""
+    import json
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "particle_steps_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config"):
+        assert key in line, key
