@@ -350,6 +350,33 @@ def extra_workloads(dev, peak_gbs):
     except Exception as e:  # noqa: BLE001
         out["config4_fullcov_n2^20_d512"] = {"error": repr(e)}
     torch.cuda.empty_cache()
+    try:   # config 1 (README): n = 512, d = 10, 512 steps, y0 = ones: the whole solve, eager loop vs one CUDA graph
+        n, d, n_steps = 512, 10, 512
+        terms, solver = mc_problem(n, d, False, mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev))
+        y0 = torch.ones((n, d), device=dev)
+        t1 = DT0 * n_steps
+
+        def wall(fn, reps):
+            fn(); torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(reps):
+                r = fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t) / reps * 1e3, r
+
+        eager_ms, sol = wall(lambda: dfx.diffeqsolve(terms, solver, 0.0, t1, DT0, y0), 2)
+        solve = dfx.capture_solve(terms, solver, 0.0, t1, DT0, y0)
+        graph_ms, sol_g = wall(lambda: solve(y0), 5)
+        mean, cov = mccube.mean_and_cov(sol_g.ys[-1])
+        w2 = mccube.gaussian_wasserstein_metric((np.full(d, TARGET_MEAN), mean), (TARGET_VAR * np.eye(d), cov))
+        out["config1_readme_n512_d10_512steps"] = {
+            "solve_ms_eager": eager_ms, "solve_ms_cuda_graph": graph_ms, "us_per_step_cuda_graph": graph_ms * 1e3 / n_steps,
+            "particle_steps_per_sec": n * n_steps / graph_ms * 1e3, "graph_equals_eager": bool(torch.equal(sol.ys, sol_g.ys)),
+            "w2_to_target": float(w2.real),
+            "note": "wall clock per whole solve, result left on the device; launch-latency bound: per step one single-CTA "
+                    "shuffle of n*k = 16384 ids (bit-exact jax.random permutation) + one fused expand+select"}
+    except Exception as e:  # noqa: BLE001
+        out["config1_readme_n512_d10_512steps"] = {"error": repr(e)}
     return out
 
 
@@ -481,7 +508,7 @@ def main():
     n, d = 1 << a.n_log2, a.d
     terms, solver, y = build_problem(a, dev)
     K, W = a.steps, max(a.warmup, 3)
-    times = dfx.step_times(0.0, DT0 * (K + W + 8), DT0, np.float32)
+    times = dfx.step_times(0.0, DT0 * (2 * K + W + 16), DT0, np.float32)
 
     def barrier():
         torch.cuda.synchronize()
@@ -499,24 +526,56 @@ def main():
     path = solver.last_path
     barrier()
 
-    # ---- timed region (device-resident state; 4 GiB per state >> 126 MB L2, no flush needed)
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if rank == 0:
-        sampler.mark()
-    ev0.record()
-    for i in range(W, W + K):
-        y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region (device-resident state; 4 GiB per state >> 126 MB L2, no flush needed):
+    # exactly K steps between two events, barrier + synchronize on both sides, max over ranks
+    def timed_block(first):
+        nonlocal y, state
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if rank == 0:
+            sampler.mark()
+        ev0.record()
+        for i in range(first, first + K):
+            y, _, _, state, _ = solver.step(terms, times[i][0], times[i][1], y, None, state, False)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count() - launches0
+
+    def phase_profile(first, reps):
+        """Per-phase times of the same step (library events on the launching stream), ms per step."""
+        _lib.profile_enable(True)
+        yy, st2 = y, state
+        for i in range(first, first + reps):
+            yy, _, _, st2, _ = solver.step(terms, times[i][0], times[i][1], yy, None, st2, False)
+        got = {}
+        for name, ms in _lib.profile_read():
+            got.setdefault(name, []).append(ms)
+        _lib.profile_enable(False)
+        return {k_: float(np.mean(v)) * (len(v) / reps) for k_, v in got.items()}
+
+    ms_total, launches = timed_block(W)
+    reps = min(K, 5)
+    phase_ms = phase_profile(W + K, reps)
+    # A timed block far above the sum of its own kernels was stalled from outside (seen once in ~20 runs on the
+    # shared boxes: 3.6 instead of 2.4 ms/step, the kernels unchanged): like a throttled run it is measured again,
+    # once, and the first figure is kept in the line.
+    remeasured = None
+    main_phases = sum(v for k_, v in phase_ms.items() if k_ != "mc_indices")     # the draw runs on a side stream
+    force = os.environ.get("MCCB200_BENCH_FORCE_REMEASURE") == "1"          # exercises this path in a test run
+    stalled = torch.tensor([1.0 if (force or (main_phases > 0 and ms_total / K > 1.3 * main_phases)) else 0.0], device=dev)
     if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        dist.all_reduce(stalled, op=dist.ReduceOp.MAX)
+    if stalled.item() > 0:
+        remeasured = {"first_ms_per_step": ms_total / K, "sum_of_kernels_ms": main_phases,
+                      "reason": "first timed block exceeded 1.3x the sum of its kernels (external stall); measured again once"}
+        ms_total, launches = timed_block(W + K + reps)
+    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
     value = world * n * K / (ms_total * 1e-3)
 
@@ -531,21 +590,6 @@ def main():
             w2_final = float(np.real(w2))
         except Exception as e:  # noqa: BLE001
             w2_final = repr(e)
-
-    # ---- per-phase timing of the same step (library events on the launching stream)
-    phases = {}
-    if rank == 0:
-        _lib.profile_enable(True)
-        reps = min(K, 5)
-        yy = y
-        st2 = state
-        for i in range(W + K, W + K + reps):
-            yy, _, _, st2, _ = solver.step(terms, times[i][0], times[i][1], yy, None, st2, False)
-        for name, ms in _lib.profile_read():
-            phases.setdefault(name, []).append(ms)
-        _lib.profile_enable(False)
-        del yy
-    phase_ms = {k_: float(np.mean(v)) * (len(v) / min(K, 5)) for k_, v in phases.items()}  # ms per step
 
     # ---- end to end through the public API with host buffers
     e2e = None
@@ -683,7 +727,8 @@ def main():
         "config": {"workload": workload_name(a), "path": path, "n_per_gpu": n, "d": d,
                    "l2": "state is 4 GiB per array (>> 126 MB L2): no flush between iterations",
                    "threefry_partitionable": False, "phase_ms_per_step": phase_ms,
-                   "w2_to_target_after_timed_steps": w2_final, "t_final": float(times[W + K - 1][1])},
+                   "w2_to_target_after_timed_steps": w2_final, "t_final": float(times[W + K - 1][1]),
+                   "remeasured": remeasured},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }
