@@ -246,8 +246,15 @@ class CapturedSolve:
             run()
         torch.cuda.current_stream(y0.device).wait_stream(warm)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._sol = run()
+        try:
+            with torch.cuda.graph(self.graph):
+                self._sol = run()
+        except RuntimeError as e:
+            # a step that synchronises with the host or copies from pageable memory (the generic path with a
+            # host-side partitioner, a drift / diffusion callable that calls .item() or .cpu(), ...) cannot be recorded
+            torch.cuda.synchronize(y0.device)
+            raise ValueError("capture_solve: this solve cannot be recorded as a CUDA graph (a step synchronises with "
+                             f"the host or uploads from pageable memory); use diffeqsolve instead [{e}]") from e
 
     def __call__(self, y0) -> Solution:
         from ._tree import tree_map

@@ -894,3 +894,24 @@ def test_edge_cases_new_entry_points(dev):
     want2 = ref.mcc_step(want, t1, np.float32(0.1), lambda q: ref.gaussian_diag_drift(q, mean, inv_var),
                          ref.hadamard_points(dd), ref.hadamard_weights(dd), SQRT2, okern)
     assert solver.last_path == "fused:box_prk_step+keycols" and np.array_equal(got2.cpu().numpy(), want2)
+
+
+def test_captured_solve_generic_path_and_refusal(dev):
+    """The generic (materialising) path with a device-side partitioner is capturable as well; a solve whose
+    step synchronises with the host (BinaryTree: sklearn callback) is refused with a ValueError and leaves
+    the device usable."""
+    n, d = 256, 4
+    terms = _terms(d, np.full(d, 2.0, np.float32), np.full(d, 1.0 / 3.0, np.float32), dev)
+    y0 = cuda(np.random.default_rng(2).normal(size=(n, d)).astype(np.float32), dev)
+    strat = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+        mccube.StratifiedPartitioningKernel(16), mccube.MonteCarloKernel(16, key=1)))
+    eager = dfx.diffeqsolve(terms, strat, 0.0, 0.2, 0.05, y0).ys
+    assert strat.last_path == "generic:expand_all+kernel"
+    assert torch.equal(dfx.capture_solve(terms, strat, 0.0, 0.2, 0.05, y0)(y0).ys, eager)
+    tree = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+        mccube.BinaryTreePartitioningKernel(16), mccube.MonteCarloKernel(16, key=1)))
+    with pytest.raises(ValueError, match="cannot be recorded as a CUDA graph"):
+        dfx.capture_solve(terms, tree, 0.0, 0.2, 0.05, y0)
+    plain = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=1))
+    assert torch.equal(dfx.capture_solve(terms, plain, 0.0, 0.2, 0.05, y0)(y0).ys,
+                       dfx.diffeqsolve(terms, plain, 0.0, 0.2, 0.05, y0).ys)
