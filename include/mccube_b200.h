@@ -191,6 +191,12 @@ MCCB200_API int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int
 MCCB200_API int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
                            const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
                            const float* bounds, uint32_t* keys, void* stream);
+/* minmax[q] = min, minmax[n_dims + q] = max of key dim q over the implicit children (what a partition over several
+ * shards reduces across devices before forming bounds = (min, 2^bits / (max - min)) in float32). */
+MCCB200_API int mccb200_box_child_minmax(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
+                             const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                             const float* keycols /* optional */, float* minmax, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* Fused BoxPartitionKernel + PartitioningRecombinationKernel + MonteCarloKernel step on
  * the implicit children (Hadamard cubature only): counting-sort ranks of all n*k
@@ -235,6 +241,20 @@ MCCB200_API int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, 
                                             uint64_t out_per_part, uint64_t in_per_part, const void* tables,
                                             const void* sel, float* y1, float* keycols_out /* optional */,
                                             void* workspace, size_t workspace_bytes, void* stream);
+/* Pass B alone, for particles sharded over several devices with ONE global partition -- what the reference's
+ * PartitioningRecombinationKernel computes on the concatenated state (mccube/_kernels/base.py:152-177).
+ * `key_start[key]` is the GLOBAL sorted position of this shard's first child with that key, so ranks, partitions
+ * and output slots are global; the LOCAL id (parent * k + point) of every selected child of this shard is
+ * written to idx_slots[global slot] (pre-filled with 0xFFFFFFFF by the caller, one entry per global output row).
+ * `mccb200_box_prk_key_start_offset` locates the LOCAL key starts in the workspace mccb200_box_prk_count filled
+ * ((size_t)-1: unsupported shape). */
+MCCB200_API int mccb200_box_prk_rank_global(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                            const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                                            uint64_t out_per_part, uint64_t in_per_part, const void* tables,
+                                            const void* sel, const uint32_t* key_start, uint32_t* idx_slots,
+                                            void* workspace, size_t workspace_bytes, void* stream);
+MCCB200_API size_t mccb200_box_prk_key_start_offset(uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
+                                                    uint64_t out_per_part, uint32_t* n_keys);
 
 /* ------------------------------------------------------------------ A11: moments
  * One pass each: sums[d] (+ weight sum) and centred second moments [d, d] in fp64:
@@ -318,6 +338,16 @@ MCCB200_API int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, in
                                              const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
                                              const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
                                              float* const* peer_out, void* stream);
+/* The same kernel driven by a list of global output slots (global Box partition over shards): idx_slots[slot] is
+ * the LOCAL child id this rank contributes to `slot`, slot_list the slots it contributes to (any order),
+ * counts[rank * n_ranks + 0..] their number (other rows zero).  mccb200_compact_slots builds slot_list / the count
+ * from idx_slots on the device (entries != 0xFFFFFFFF; *cursor is zeroed by the caller; a full list traps). */
+MCCB200_API int mccb200_expand_scatter_slots(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                                             const mccb200_cubature* cub, const uint32_t* idx_slots,
+                                             const uint32_t* slot_list, const uint32_t* counts, int rank, int n_ranks,
+                                             uint64_t rows_per_rank, float* const* peer_out, void* stream);
+MCCB200_API int mccb200_compact_slots(const uint32_t* idx_slots, uint64_t n_slots, uint32_t* list, uint64_t capacity,
+                                      uint32_t* cursor, void* stream);
 
 #ifdef __cplusplus
 }

@@ -333,3 +333,143 @@ class ShardedMonteCarloStep:
             if recv.shape[0]:
                 y1[keep:keep + recv.shape[0]] = recv
         return y1, slot_map
+
+
+class ShardedBoxStep:
+    """One MCCSolver step with `PartitioningRecombinationKernel(BoxPartitionKernel, MonteCarloKernel)` over
+    row-sharded particles and ONE GLOBAL partition: what the reference computes on the concatenated state
+    (mccube/_kernels/base.py:152-177), shards bit-identical to the single-device step.
+
+    The global stable sort by box key never happens.  Per rank: the min / max of the implicit children (one
+    all-reduce of 2 * dims floats), the per-key child counts of its own parents (`box_prk_count`; one all-gather of
+    n_keys integers tells every rank where its children of each key start in the global order), the ranking pass
+    with those global key starts (`box_prk_rank_global`: the shard's hits land in a sparse [n_tot] slot array),
+    an on-device compaction of the hit slots, and the fused expand + scatter kernel that writes every selected
+    child straight into the shard of the rank storing its output row (NVLink peer stores).  No sort, no row
+    buffer, no host synchronisation; the data path has no collective.  `BoxPartitionKernel.partition_count` and
+    `MonteCarloKernel.recombination_count` are the GLOBAL partition count and the per-partition output count.
+
+    The phases are separate methods so that tests can emulate the ranks on one device."""
+
+    def __init__(self, solver, terms, n_ranks: int):
+        from ._kernels import BoxPartitionKernel, MonteCarloKernel, PartitioningRecombinationKernel
+
+        kernel = solver.recombination_kernel
+        if (type(kernel) is not PartitioningRecombinationKernel or type(kernel.partitioning_kernel) is not BoxPartitionKernel
+                or type(kernel.recombination_kernel) is not MonteCarloKernel or solver.weighted or solver.n_substeps != 1):
+            raise NotImplementedError("sharded Box step: unweighted Box + PRK + MonteCarloKernel with n_substeps=1 only")
+        self.solver, self.terms, self.n_ranks = solver, terms, n_ranks
+
+    # ---- shapes shared by all phases
+    def _plan(self, t0, t1, y_shard):
+        from . import _lib
+
+        solver = self.solver
+        part = solver.recombination_kernel.partitioning_kernel
+        mc = solver.recombination_kernel.recombination_kernel
+        n_loc, d = y_shard.shape
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        n_tot = n_loc * self.n_ranks
+        m = part.partition_count
+        if (n_tot * k) % m:
+            raise ValueError(f"partition_count {m} does not divide the {n_tot * k} expanded particles")
+        in_per_part, out_per_part = n_tot * k // m, mc.recombination_count
+        if m * out_per_part != n_tot:
+            raise ValueError(f"partition_count * recombination_count = {m * out_per_part} must equal the global particle count {n_tot}")
+        if n_tot * k > 2 ** 32:
+            raise ValueError("sharded Box step: more than 2^32 children in total (32-bit sorted positions)")
+        dims = part.resolve_dims(d)
+        if not _lib.box_prk_supported(n_loc, d, cub, dims, part.bits, in_per_part):
+            raise NotImplementedError("sharded Box step: shape not supported by the fused Box kernel")
+        return dict(part=part, mc=mc, drift=drift, cub=cub, dt=dt, k=k, d=d, n_loc=n_loc, n_tot=n_tot,
+                    in_per_part=in_per_part, out_per_part=out_per_part, dims=dims, bits=part.bits)
+
+    def local_minmax(self, t0, t1, y_shard):
+        """Phase 1: [min..., max...] of the key dims over this shard's implicit children (None with fixed bounds)."""
+        from . import _lib
+
+        pl = self._plan(t0, t1, y_shard)
+        if pl["part"].fixed_bounds(pl["dims"], y_shard.device) is not None:
+            return None
+        return _lib.box_child_minmax(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], pl["dims"], pl["bits"])
+
+    def bounds_from(self, t0, t1, y_shard, minmax):
+        """Bounds of the global partition from the reduced min / max: (lo, 2^bits / (hi - lo)) in float32, the
+        arithmetic of the single-device bounds kernel."""
+        pl = self._plan(t0, t1, y_shard)
+        fixed = pl["part"].fixed_bounds(pl["dims"], y_shard.device)
+        if fixed is not None:
+            return fixed
+        nd = len(pl["dims"])
+        lo, hi = minmax[:nd], minmax[nd:]
+        rng = hi - lo
+        cells = torch.full_like(rng, float(1 << pl["bits"]))
+        inv_h = torch.where(rng > 0, cells / rng, torch.zeros_like(rng))
+        return torch.cat([lo, inv_h]).contiguous()
+
+    def count(self, t0, t1, y_shard, bounds):
+        """Phase 2: counting pass over this shard; returns (workspace for phase 3, per-key child counts [n_keys])."""
+        from . import _lib
+
+        pl = self._plan(t0, t1, y_shard)
+        tables = _lib.box_prk_tables(pl["k"], pl["dims"], pl["bits"], y_shard.device)
+        ws = _lib.box_prk_count(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], pl["dims"], pl["bits"], bounds,
+                                pl["in_per_part"], tables)
+        starts = _lib.box_prk_local_key_starts(ws, pl["n_loc"], pl["k"], len(pl["dims"]), pl["bits"], pl["in_per_part"],
+                                               pl["out_per_part"]).to(torch.int64) & 0xFFFFFFFF
+        ends = torch.cat([starts[1:], starts.new_tensor([pl["n_loc"] * pl["k"]])])
+        return ws, (ends - starts)
+
+    @staticmethod
+    def key_starts_for(rank: int, totals_all: torch.Tensor) -> torch.Tensor:
+        """Global sorted position of rank's first child of every key from the [n_ranks, n_keys] count matrix:
+        children of smaller keys on all ranks + children of the same key on lower ranks (uint32 bit patterns)."""
+        per_key = totals_all.sum(0)
+        key_base = torch.cumsum(per_key, 0) - per_key
+        below = totals_all[:rank].sum(0)
+        v = (key_base + below) & 0xFFFFFFFF
+        return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+    def rank_and_scatter(self, t0, t1, y_shard, rank: int, ws, key_start, peer_ptrs):
+        """Phase 3: global ranks -> this shard's hits -> fused expand + scatter into the owners' shards."""
+        from . import _lib
+
+        pl = self._plan(t0, t1, y_shard)
+        dev = y_shard.device
+        tables = _lib.box_prk_tables(pl["k"], pl["dims"], pl["bits"], dev)
+        idx_local = pl["mc"].indices(t0, pl["in_per_part"], pl["out_per_part"], dev)
+        sel = _lib.box_prk_selection(idx_local, pl["in_per_part"])
+        idx_slots = torch.full((pl["n_tot"],), -1, dtype=torch.int32, device=dev)
+        _lib.box_prk_rank_global(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], pl["dims"], pl["bits"],
+                                 pl["out_per_part"], pl["in_per_part"], tables, sel, ws, key_start, idx_slots)
+        G, n_loc = self.n_ranks, pl["n_loc"]
+        counts = torch.zeros(G * G, dtype=torch.int32, device=dev)
+        slot_list = torch.empty(n_loc + n_loc // 8 + 1024, dtype=torch.int32, device=dev)
+        _lib.compact_slots(idx_slots, slot_list, counts[rank * G:rank * G + 1])
+        _lib.expand_scatter_slots(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], idx_slots, slot_list, counts,
+                                  rank, G, n_loc, peer_ptrs)
+
+    def step(self, t0, t1, rank: int, shards: PeerShards, group=None) -> torch.Tensor:
+        """The state lives in `shards` (load it once with `shards.load`); returns this rank's next shard."""
+        cur, nxt = shards.turn, shards.turn ^ 1
+        y_in, y_out = shards.local[cur], shards.local[nxt]
+        mm = self.local_minmax(t0, t1, y_in)
+        if mm is not None and self.n_ranks > 1:
+            nd = mm.numel() // 2
+            lo, hi = mm[:nd].clone(), mm[nd:].clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            mm = torch.cat([lo, hi])
+        bounds = self.bounds_from(t0, t1, y_in, mm)
+        ws, totals = self.count(t0, t1, y_in, bounds)
+        if self.n_ranks > 1:
+            gathered = [torch.empty_like(totals) for _ in range(self.n_ranks)]
+            dist.all_gather(gathered, totals.contiguous(), group=group)
+            totals_all = torch.stack(gathered)
+        else:
+            totals_all = totals[None]
+        key_start = self.key_starts_for(rank, totals_all)
+        self.rank_and_scatter(t0, t1, y_in, rank, ws, key_start, shards.ptrs[nxt])
+        shards.barrier()          # every rank's rows have landed (and nobody still reads the other buffer)
+        shards.turn = nxt
+        return y_out

@@ -73,6 +73,10 @@ _SIGNATURES = {
     "mccb200_expand_scatter_peers": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
                                                C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_expand_scatter_slots": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                               C.POINTER(Cubature), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_compact_slots": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
     "mccb200_mc_indices_slice": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                            C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -100,6 +104,9 @@ _SIGNATURES = {
     "mccb200_box_child_bounds": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                            C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_box_child_minmax": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
+                                           C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_box_child_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(Drift), C.c_float,
                                          C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
@@ -120,6 +127,12 @@ _SIGNATURES = {
                                               C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_uint64,
                                               C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_size_t, C.c_void_p]),
+    "mccb200_box_prk_rank_global": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                              C.POINTER(Cubature), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_uint64,
+                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_size_t, C.c_void_p]),
+    "mccb200_box_prk_key_start_offset": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                                      C.POINTER(C.c_uint32)]),
     "mccb200_moments_sum": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "mccb200_moments_m2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
@@ -557,6 +570,64 @@ def box_prk_count(y0, d, drift, dt, cub, dims, bits, bounds, in_per_part, tables
                                      tables.data_ptr(), _ptr(keycols), ws.data_ptr(), ws.numel(), _stream()),
            "box_prk_count")
     return ws
+
+
+def box_child_minmax(y0, d, drift, dt, cub, dims, bits, keycols=None):
+    """[min..., max...] of every key dim over the implicit children (2 * len(dims) float32)."""
+    lib = load()
+    _require_cuda(y0, keycols)
+    _f32c(y0)
+    out = torch.empty(2 * len(dims), dtype=torch.float32, device=y0.device)
+    ws = workspace(lib.mccb200_box_bounds_workspace_bytes(), y0.device)
+    _check(lib.mccb200_box_child_minmax(y0.data_ptr(), y0.shape[0], d, y0.shape[1], C.byref(drift),
+                                        float(np.float32(dt)), C.byref(cub), _dims_array(dims), len(dims), bits,
+                                        _ptr(keycols), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+           "box_child_minmax")
+    return out
+
+
+def box_prk_local_key_starts(ws, n, k, n_dims, bits, in_per_part, out_per_part):
+    """View (int32 bit patterns of uint32) of the local sorted position of every key's first child inside the
+    workspace `box_prk_count` returned."""
+    lib = load()
+    n_keys = C.c_uint32(0)
+    off = lib.mccb200_box_prk_key_start_offset(n, k, n_dims, bits, in_per_part, out_per_part, C.byref(n_keys))
+    if off == C.c_size_t(-1).value:
+        raise MccubeB200Error("box_prk_local_key_starts: unsupported shape")
+    return ws[off:off + 4 * n_keys.value].view(torch.int32)
+
+
+def box_prk_rank_global(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_part, tables, sel, ws, key_start,
+                        idx_slots):
+    """Ranking pass with global key starts: fills idx_slots[global slot] = local child id for this shard's hits."""
+    lib = load()
+    _require_cuda(y0, tables, sel, ws, key_start, idx_slots)
+    _check(lib.mccb200_box_prk_rank_global(y0.data_ptr(), y0.shape[0], d, C.byref(drift), float(np.float32(dt)),
+                                           C.byref(cub), _dims_array(dims), len(dims), bits, out_per_part, in_per_part,
+                                           tables.data_ptr(), sel.data_ptr(), key_start.data_ptr(), idx_slots.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream()), "box_prk_rank_global")
+    return idx_slots
+
+
+def compact_slots(idx_slots, slot_list, cursor):
+    """slot_list[: cursor] = the slots s with idx_slots[s] != -1 (any order); cursor: 1-element int32 view, zeroed."""
+    lib = load()
+    _require_cuda(idx_slots, slot_list, cursor)
+    _check(lib.mccb200_compact_slots(idx_slots.data_ptr(), idx_slots.numel(), slot_list.data_ptr(), slot_list.numel(),
+                                     cursor.data_ptr(), _stream()), "compact_slots")
+
+
+def expand_scatter_slots(y0, d, drift: Drift, dt, cub: Cubature, idx_slots, slot_list, counts, rank, n_ranks,
+                         rows_per_rank, peer_ptrs):
+    """Fused expand + exchange driven by a slot list: child idx_slots[s] of this rank's parents goes to row
+    s % rows_per_rank of shard s // rows_per_rank."""
+    lib = load()
+    _require_cuda(y0, idx_slots, slot_list, counts, peer_ptrs)
+    _f32c(y0)
+    _check(lib.mccb200_expand_scatter_slots(y0.data_ptr(), y0.shape[0], d, C.byref(drift), float(np.float32(dt)),
+                                            C.byref(cub), idx_slots.data_ptr(), slot_list.data_ptr(), counts.data_ptr(),
+                                            int(rank), int(n_ranks), int(rows_per_rank), peer_ptrs.data_ptr(), _stream()),
+           "expand_scatter_slots")
 
 
 def box_prk_rank_gather(y0, d, drift, dt, cub, dims, bits, out_per_part, in_per_part, tables, sel, ws, out=None,

@@ -803,7 +803,7 @@ static int launch_count(BoxPrkParams& p, const PrkPlan& pl, cudaStream_t st) {
   return check_launch("box_prk_count");
 }
 
-static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cudaStream_t st) {
+static int launch_rank(BoxPrkParams& p, const PrkPlan& pl, cudaStream_t st) {
   phase_mark("box_prk.rank", st);
 #define MCCB_FLAT2(PS, MS, P2)                                                                                          \
   do {                                                                                                                  \
@@ -821,6 +821,13 @@ static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cud
   else MCCB_FLAT(false, false);
 #undef MCCB_FLAT
 #undef MCCB_FLAT2
+  count_launches(1);
+  return check_launch("box_prk_rank");
+}
+
+static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cudaStream_t st) {
+  int rc0 = launch_rank(p, pl, st);
+  if (rc0) return rc0;
   // gather: the HBM-bound fused expand+select materialises the selected children
   ExpandArgs g = p.a;
   g.keycols = nullptr;
@@ -919,6 +926,44 @@ extern "C" int mccb200_box_prk_rank_gather(const float* y0, uint64_t n, int d, c
     return fail(MCCB200_ERR_UNSUPPORTED, "box_prk_rank_gather: keycols_out needs 4 consecutive 16-byte aligned key columns");
   }
   return launch_rank_gather(p, pl, y1, (cudaStream_t)stream);
+}
+
+/* Pass B alone, for particles sharded over several devices with ONE global partition (the reference's):
+ * `key_start[key]` is the GLOBAL sorted position of this shard's first child with that key (start of the key
+ * over all shards + children of lower-ranked shards with the same key), so ranks, partitions and output slots
+ * are global; every selected child's LOCAL id (parent * k + point) is written to `idx_slots[global slot]`,
+ * which the caller pre-fills with 0xFFFFFFFF and sizes for all partitions.  No gather. */
+extern "C" int mccb200_box_prk_rank_global(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                           const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                                           uint64_t out_per_part, uint64_t in_per_part, const void* tables,
+                                           const void* sel, const uint32_t* key_start, uint32_t* idx_slots,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  BoxPrkParams p{};
+  PrkPlan pl;
+  int rc = setup_params(p, pl, y0, n, d, drift, dt, cub, dims_host, n_dims, bits, out_per_part, in_per_part, workspace,
+                        workspace_bytes, "box_prk_rank_global");
+  if (rc) return rc;
+  MCCB_REQUIRE(tables && sel && key_start && idx_slots, "box_prk_rank_global: NULL argument");
+  if (n == 0) return MCCB200_OK;
+  SelLayout sl;
+  make_sel_layout(sl, in_per_part, out_per_part);
+  bind_tables(p, pl.tl, tables);
+  p.pre = (const uint32_t*)((const char*)sel + sl.off_pre);
+  p.sp = (const uint2*)((const char*)sel + sl.off_sp);
+  p.sel_ext = sl.ext;
+  p.key_start = key_start;
+  p.idx_out = idx_slots;
+  return launch_rank(p, pl, (cudaStream_t)stream);
+}
+
+/* Byte offset, inside the workspace `mccb200_box_prk_count` filled, of the uint32 array with the LOCAL sorted
+ * position of the first child of every key (n_keys entries, ascending; the last key ends at n * k). */
+extern "C" size_t mccb200_box_prk_key_start_offset(uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
+                                                   uint64_t out_per_part, uint32_t* n_keys) {
+  PrkPlan pl;
+  if (!make_prk_plan(pl, n, (uint32_t)k, n_dims, bits, in_per_part, out_per_part)) return (size_t)-1;
+  if (n_keys) *n_keys = pl.n_keys;
+  return pl.off_table + (size_t)pl.n_segments * pl.n_keys * sizeof(uint32_t);
 }
 
 extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,

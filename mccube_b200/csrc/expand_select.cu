@@ -347,10 +347,10 @@ extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int wei
   return run_expand(a, (cudaStream_t)stream);
 }
 
-extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
-                                            const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
-                                            const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
-                                            float* const* peer_out, void* stream) {
+static int scatter_peers_impl(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                              const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
+                              const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
+                              float* const* peer_out, void* stream, bool local_ids) {
   ExpandArgs a{};
   int rc = fill_expand_args(a, y0, n_loc, d, 0, drift, dt, cub);
   if (rc) return rc;
@@ -363,10 +363,30 @@ extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int
   a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
   a.sc_order = order; a.sc_counts = counts; a.sc_peers = peer_out;
   a.sc_rank = (uint32_t)rank; a.sc_G = (uint32_t)n_ranks;
-  a.sc_rows_per_rank = rows_per_rank; a.sc_child_offset = (uint64_t)rank * n_loc * (uint64_t)cub->k;
+  a.sc_rows_per_rank = rows_per_rank;
+  a.sc_child_offset = local_ids ? 0 : (uint64_t)rank * n_loc * (uint64_t)cub->k;
   a.n_out = rows_per_rank + rows_per_rank / 8 + 1024;   // grid sizing only: the true count is read on the device
   a.y1 = const_cast<float*>(y0);                        // alignment probe only (never written in this form)
   return run_expand(a, (cudaStream_t)stream);
+}
+
+extern "C" int mccb200_expand_scatter_peers(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                                            const mccb200_cubature* cub, const uint32_t* idx, const uint32_t* order,
+                                            const uint32_t* counts, int rank, int n_ranks, uint64_t rows_per_rank,
+                                            float* const* peer_out, void* stream) {
+  return scatter_peers_impl(y0, n_loc, d, drift, dt, cub, idx, order, counts, rank, n_ranks, rows_per_rank, peer_out,
+                            stream, false);
+}
+
+/* The same kernel for a list of global output slots: `idx_slots[slot]` holds the LOCAL child id (parent * k +
+ * point) this rank contributes to `slot`, `slot_list` the slots it contributes to (any order), and
+ * `counts[rank * n_ranks + 0..]` their number (summed; other rows of `counts` must be zero). */
+extern "C" int mccb200_expand_scatter_slots(const float* y0, uint64_t n_loc, int d, const mccb200_drift* drift, float dt,
+                                            const mccb200_cubature* cub, const uint32_t* idx_slots,
+                                            const uint32_t* slot_list, const uint32_t* counts, int rank, int n_ranks,
+                                            uint64_t rows_per_rank, float* const* peer_out, void* stream) {
+  return scatter_peers_impl(y0, n_loc, d, drift, dt, cub, idx_slots, slot_list, counts, rank, n_ranks, rows_per_rank,
+                            peer_out, stream, true);
 }
 
 extern "C" int mccb200_expand_gather_peers(float* const* peer_in, int n_ranks, uint64_t rows_per_rank, int d,

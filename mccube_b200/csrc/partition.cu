@@ -167,8 +167,9 @@ box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ parti
 }
 
 // one warp per key dim: lanes stride over the CTA partials, shuffle-reduce
+// raw: write (lo, hi) instead of (lo, cells / range) -- for the cross-device min / max of a global partition
 __global__ void box_bounds_final_kernel(const float* __restrict__ partials, int n_ctas, BoxSpec spec,
-                                        float* __restrict__ bounds) {
+                                        float* __restrict__ bounds, int raw = 0) {
   const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (q >= spec.n_dims) return;
   float lo = INFINITY, hi = -INFINITY;
@@ -183,7 +184,7 @@ __global__ void box_bounds_final_kernel(const float* __restrict__ partials, int 
   if (lane == 0) {
     float rng = __fsub_rn(hi, lo);
     bounds[q] = lo;
-    bounds[spec.n_dims + q] = rng > 0.0f ? __fdiv_rn((float)(1 << spec.bits), rng) : 0.0f;
+    bounds[spec.n_dims + q] = raw ? hi : (rng > 0.0f ? __fdiv_rn((float)(1 << spec.bits), rng) : 0.0f);
   }
 }
 
@@ -286,10 +287,10 @@ extern "C" int mccb200_box_keys(const float* p, uint64_t n, int ld, const int32_
   return check_launch("box_keys");
 }
 
-extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
-                                        float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
-                                        int bits, const float* keycols, float* bounds, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+static int child_bounds_impl(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift, float dt,
+                             const mccb200_cubature* cub, const int32_t* dims_host, int n_dims, int bits,
+                             const float* keycols, float* bounds, void* workspace, size_t workspace_bytes, void* stream,
+                             int raw) {
   BoxSpec s;
   int rc = make_box_spec(s, dims_host, n_dims, bits, d);
   if (rc) return rc;
@@ -315,10 +316,28 @@ extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int 
   a.keycols = (!a.points && box_dims_vec4(s, a) && keycols && (((uintptr_t)keycols & 15) == 0)) ? keycols : nullptr;
   if (!a.points && box_dims_vec4(s, a)) box_bounds_children_kernel<true><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
   else box_bounds_children_kernel<false><<<grid, BB_THREADS, 0, st>>>(a, s, (float*)workspace);
-  box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds);
+  box_bounds_final_kernel<<<1, 32 * MCCB200_BOX_MAX_DIMS, 0, st>>>((const float*)workspace, grid, s, bounds, raw);
   phase_mark("end", st);
   count_launches(2);
   return check_launch("box_child_bounds");
+}
+
+extern "C" int mccb200_box_child_bounds(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
+                                        float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
+                                        int bits, const float* keycols, float* bounds, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return child_bounds_impl(y0, n, d, ld, drift, dt, cub, dims_host, n_dims, bits, keycols, bounds, workspace,
+                           workspace_bytes, stream, 0);
+}
+
+/* minmax[q] = min, minmax[n_dims + q] = max of key dim q over the implicit children: what a global partition over
+ * several shards reduces across devices before forming the cell width (float32: 2^bits / (max - min)). */
+extern "C" int mccb200_box_child_minmax(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,
+                                        float dt, const mccb200_cubature* cub, const int32_t* dims_host, int n_dims,
+                                        int bits, const float* keycols, float* minmax, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return child_bounds_impl(y0, n, d, ld, drift, dt, cub, dims_host, n_dims, bits, keycols, minmax, workspace,
+                           workspace_bytes, stream, 1);
 }
 
 extern "C" int mccb200_box_child_keys(const float* y0, uint64_t n, int d, int ld, const mccb200_drift* drift,

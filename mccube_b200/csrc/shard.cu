@@ -51,9 +51,44 @@ scatter_rows_kernel(const float* __restrict__ in, int ld, const uint32_t* __rest
   }
 }
 
+// list[cursor++] = s for every slot s a rank fills (idx_slots[s] != 0xFFFFFFFF): warp-aggregated append, any order
+__global__ void __launch_bounds__(256)
+compact_slots_kernel(const uint32_t* __restrict__ idx_slots, uint64_t n_slots, uint32_t* __restrict__ list,
+                     uint32_t capacity, uint32_t* __restrict__ cursor) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t rounds = (n_slots + stride - 1) / stride;
+  for (uint64_t it = 0; it < rounds; ++it) {
+    const uint64_t s = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = s < n_slots && __ldcs(idx_slots + s) != 0xFFFFFFFFu;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (m == 0u) continue;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (mine) {
+      const uint32_t at = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (at >= capacity) __trap();                        // loud: the caller sized the list too small
+      list[at] = (uint32_t)s;
+    }
+  }
+}
+
 }  // namespace mccb
 
 using namespace mccb;
+
+/* Appends to `list` (capacity entries) every slot s < n_slots with idx_slots[s] != 0xFFFFFFFF and adds their
+ * number to *cursor (device; the caller zeroes it).  Order is arbitrary; a full list traps. */
+extern "C" int mccb200_compact_slots(const uint32_t* idx_slots, uint64_t n_slots, uint32_t* list, uint64_t capacity,
+                                     uint32_t* cursor, void* stream) {
+  MCCB_REQUIRE(idx_slots && list && cursor && capacity < 0xFFFFFFFFull, "compact_slots: bad argument");
+  if (n_slots == 0) return MCCB200_OK;
+  const int grid = (int)min((n_slots + 255) / 256, (uint64_t)sm_count() * 8);
+  compact_slots_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx_slots, n_slots, list, (uint32_t)capacity, cursor);
+  count_launches(1);
+  return check_launch("compact_slots");
+}
 
 // ---- peer shards: plain cudaMalloc buffers shared between the ranks of one node through CUDA IPC.
 // The importer opens a handle with ITS device current and cudaIpcMemLazyEnablePeerAccess, which maps

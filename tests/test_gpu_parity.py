@@ -667,6 +667,49 @@ def test_sharded_p2p_scatter_emulated_ranks(dev, replace):
     assert torch.equal(torch.cat(shards), want)
 
 
+@pytest.mark.parametrize("G,n_loc,d,dims,bits,m_div,fixed", [
+    (4, 1024, 16, (4, 5, 6, 7), 2, 16, False),      # vectorised key columns, k = 32
+    (2, 2048, 64, (0, 1, 2, 3), 3, 64, False),      # config-3 family: k = 128, 8192 children per partition
+    (3, 1024, 10, (0, 3, 9), 2, 8, True),           # odd rank count, scalar key columns, fixed bounds
+])
+def test_sharded_box_step_emulated_ranks(dev, G, n_loc, d, dims, bits, m_div, fixed):
+    """Global Box + PRK partition over row-sharded particles (ranks emulated on one GPU, "peer" shards are local
+    tensors, the two collectives done by hand): the shards written by all ranks together equal the single-device
+    step on the concatenated state bit for bit, over several steps."""
+    from mccube_b200._distributed import ShardedBoxStep
+
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=31)
+    terms = _terms(d, mean, inv_var, dev)
+    kw = dict(bounds=(np.full(len(dims), -8.0), np.full(len(dims), 12.0))) if fixed else {}
+    out_per = m_div
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+        mccube.BoxPartitionKernel(n_tot // out_per, dims=dims, bits=bits, **kw), mccube.MonteCarloKernel(out_per, key=11)))
+    sh = ShardedBoxStep(solver, terms, G)
+    times = dfx.step_times(0.0, 0.15, 0.05, np.float32)
+    want = cuda(y, dev)
+    cur = [want[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
+    for (a, b) in times:
+        want, *_ = solver.step(terms, a, b, want, None, None, False)
+        assert solver.last_path.startswith("fused:box_prk_step")
+        nxt = [torch.full((n_loc, d), float("nan"), device=dev) for _ in range(G)]
+        ptrs = torch.tensor([s_.data_ptr() for s_ in nxt], dtype=torch.int64, device=dev)
+        mms = [sh.local_minmax(a, b, cur[r]) for r in range(G)]
+        if mms[0] is None:
+            mm = None
+        else:
+            nd = len(dims)
+            mm = torch.cat([torch.stack([q[:nd] for q in mms]).min(0).values, torch.stack([q[nd:] for q in mms]).max(0).values])
+        bounds = sh.bounds_from(a, b, cur[0], mm)
+        totals_all = torch.stack([sh.count(a, b, cur[r], bounds)[1].clone() for r in range(G)])
+        assert int(totals_all.sum()) == n_tot * solver._describe(terms, cur[0], a, b, None)[3]
+        for r in range(G):
+            ws, _ = sh.count(a, b, cur[r], bounds)          # (one device, one scratch buffer: count again per rank)
+            sh.rank_and_scatter(a, b, cur[r], r, ws, sh.key_starts_for(r, totals_all), ptrs)
+        assert torch.equal(torch.cat(nxt), want), (a, b)
+        cur = nxt
+
+
 def test_sharded_pull_gather_emulated_ranks(dev):
     """Pull form (with_replacement=True): every rank draws only its own slice of the index vector and reads
     the parents from the owners' shards; ranks emulated on one GPU.  Also checks the index slices."""
