@@ -431,6 +431,33 @@ def sharded_global_mc(dev, rank, world, steps=5):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[name] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3)}
         del ys
+    # the headline kernel pair with ONE global partition over all ranks' particles (the reference's partition of
+    # the concatenated state; the headline value uses a partition per rank): counts + ranks per rank, two tiny
+    # collectives, fused expand + scatter into the owners' shards over NVLink
+    try:
+        from mccube_b200._distributed import ShardedBoxStep
+
+        shb = ShardedBoxStep(mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+            mccube.BoxPartitionKernel(n_tot >> 6, dims=(0, 1, 2, 3), bits=3), mccube.MonteCarloKernel(1 << 6, key=42))),
+            terms, world)
+        gen.manual_seed(11 + rank)
+        shards.load(torch.randn((n_loc, d), generator=gen, device=dev) * 1.5 + TARGET_MEAN)
+        for i in range(3):
+            shb.step(times[i][0], times[i][1], rank, shards)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(3, 3 + steps):
+            shb.step(times[i][0], times[i][1], rank, shards)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out["global_box_prk_step"] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3),
+                                      "note": "BoxPartitionKernel(n_tot/2^6) + PRK(MonteCarloKernel(2^6)) with one global "
+                                              "partition over all shards, shards bit-identical to the single-device step"}
+    except Exception as e:  # noqa: BLE001
+        out["global_box_prk_step"] = {"error": repr(e)}
     shards.close()
     del shards
     torch.cuda.empty_cache()

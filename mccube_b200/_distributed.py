@@ -437,8 +437,7 @@ class ShardedBoxStep:
         pl = self._plan(t0, t1, y_shard)
         dev = y_shard.device
         tables = _lib.box_prk_tables(pl["k"], pl["dims"], pl["bits"], dev)
-        idx_local = pl["mc"].indices(t0, pl["in_per_part"], pl["out_per_part"], dev)
-        sel = _lib.box_prk_selection(idx_local, pl["in_per_part"])
+        sel = self._selection(t0, pl, dev)
         idx_slots = torch.full((pl["n_tot"],), -1, dtype=torch.int32, device=dev)
         _lib.box_prk_rank_global(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], pl["dims"], pl["bits"],
                                  pl["out_per_part"], pl["in_per_part"], tables, sel, ws, key_start, idx_slots)
@@ -449,17 +448,40 @@ class ShardedBoxStep:
         _lib.expand_scatter_slots(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], idx_slots, slot_list, counts,
                                   rank, G, n_loc, peer_ptrs)
 
+    def _selection(self, t0, pl, dev):
+        """The shared local index vector and its selection tables (a function of (key, t0) only); `step` draws
+        them on a side stream ahead of time."""
+        from . import _lib
+
+        ready = getattr(self, "_sel_ready", None)
+        if ready is not None and ready[0] == (float(t0), pl["in_per_part"], pl["out_per_part"]):
+            self._sel_ready = None
+            torch.cuda.current_stream(dev).wait_stream(ready[3])
+            ready[1].record_stream(torch.cuda.current_stream(dev))
+            ready[2].record_stream(torch.cuda.current_stream(dev))
+            return ready[2]
+        idx_local = pl["mc"].indices(t0, pl["in_per_part"], pl["out_per_part"], dev)
+        return _lib.box_prk_selection(idx_local, pl["in_per_part"])
+
     def step(self, t0, t1, rank: int, shards: PeerShards, group=None) -> torch.Tensor:
         """The state lives in `shards` (load it once with `shards.load`); returns this rank's next shard."""
+        from . import _lib
+        from ._solvers import _side_stream
+
         cur, nxt = shards.turn, shards.turn ^ 1
         y_in, y_out = shards.local[cur], shards.local[nxt]
+        pl = self._plan(t0, t1, y_in)
+        side = _side_stream(y_in.device)
+        with torch.cuda.stream(side):                            # overlaps the bounds / counting passes
+            idx_local = pl["mc"].indices(t0, pl["in_per_part"], pl["out_per_part"], y_in.device)
+            sel = _lib.box_prk_selection(idx_local, pl["in_per_part"])
+        self._sel_ready = ((float(t0), pl["in_per_part"], pl["out_per_part"]), idx_local, sel, side)
         mm = self.local_minmax(t0, t1, y_in)
         if mm is not None and self.n_ranks > 1:
             nd = mm.numel() // 2
-            lo, hi = mm[:nd].clone(), mm[nd:].clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-            mm = torch.cat([lo, hi])
+            both = torch.cat([mm[:nd], -mm[nd:]])                 # one collective: min of (lo, -hi)
+            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
+            mm = torch.cat([both[:nd], -both[nd:]])
         bounds = self.bounds_from(t0, t1, y_in, mm)
         ws, totals = self.count(t0, t1, y_in, bounds)
         if self.n_ranks > 1:

@@ -16,7 +16,7 @@ import torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import mccube_b200 as mccube  # noqa: E402
 from mccube_b200 import diffrax_compat as dfx  # noqa: E402
-from mccube_b200._distributed import PeerShards, ShardedMonteCarloStep  # noqa: E402
+from mccube_b200._distributed import PeerShards, ShardedBoxStep, ShardedMonteCarloStep  # noqa: E402
 
 
 def terms_for(d, dev):
@@ -86,6 +86,28 @@ def main():
     got, slot_map = sh.step_owner(t0, t1, y[rank * n_loc:(rank + 1) * n_loc].contiguous(), rank)
     assert torch.equal(got, want[slot_map.to(torch.int64) & 0xFFFFFFFF]), f"rank {rank}: owner-computes mismatch"
     dist.barrier()
+    # global Box + PRK partition over the shards (two all-reduces of 8 floats, one all-gather of the key counts,
+    # fused expand + scatter over peer memory): three steps, shards equal the single-device trajectory
+    n_box, d_box = 4096, 16
+
+    def box_solver(n_all):
+        return mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+            mccube.BoxPartitionKernel(n_all // 16, dims=(4, 5, 6, 7), bits=2), mccube.MonteCarloKernel(16, key=7)))
+
+    gen.manual_seed(13)
+    yb = torch.randn((n_box * world, d_box), generator=gen, device=dev) * 1.5 + 1.0
+    terms_b = terms_for(d_box, dev)
+    shb = ShardedBoxStep(box_solver(n_box * world), terms_b, world)
+    shards = PeerShards(n_box, d_box, rank, world, dev)
+    shards.load(yb[rank * n_box:(rank + 1) * n_box])
+    single, want = box_solver(n_box * world), yb
+    for (ta, tb) in dfx.step_times(0.0, 0.15, 0.05, np.float32):
+        want, *_ = single.step(terms_b, ta, tb, want, None, None, False)
+        got = shb.step(ta, tb, rank, shards)
+        assert torch.equal(got, want[rank * n_box:(rank + 1) * n_box]), f"rank {rank}: sharded Box step != single at t={ta}"
+    del got
+    shards.close()
+    dist.barrier()
 
     # ---- timing at n_loc = 2^n_log2 per rank
     n_loc, d = 1 << a.n_log2, a.d
@@ -147,6 +169,27 @@ def main():
     torch.cuda.synchronize(); dist.barrier()
     ms_q = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms_q, op=dist.ReduceOp.MAX)
+    # global Box + PRK partition timing (2^6 outputs per partition of 2^13 children, as in the headline config)
+    shards.close()
+    shb = ShardedBoxStep(mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+        mccube.BoxPartitionKernel(n_tot // 64, dims=(0, 1, 2, 3), bits=3), mccube.MonteCarloKernel(64, key=42))), terms, world)
+    shards = PeerShards(n_loc, d, rank, world, dev)
+    gen.manual_seed(11 + rank)
+    shards.load(torch.randn((n_loc, d), generator=gen, device=dev) * 1.5 + 2.0)
+    for i in range(3):
+        shb.step(times[i][0], times[i][1], rank, shards)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for i in range(3, 3 + a.steps):
+        shb.step(times[i][0], times[i][1], rank, shards)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms_b = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms_b, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"variant": "global Box + PRK partition over the shards (fused expand + peer scatter), bit-exact shards",
+                          "n_gpus": world, "n_per_gpu": n_loc, "d": d, "ms_per_step": float(ms_b) / a.steps,
+                          "particle_steps_per_sec": n_tot * a.steps / (float(ms_b) * 1e-3)}))
     if rank == 0:
         print(json.dumps({"variant": "pull: own index slice + gather from the owners' shards over peer memory, bit-exact shards",
                           "n_gpus": world, "n_per_gpu": n_loc, "d": d, "ms_per_step": float(ms_q) / a.steps,

@@ -134,3 +134,31 @@ def test_plan_rebalance_is_consistent():
             assert np.array_equal(per - tr.sum(1) + tr.sum(0), np.full(G, n_loc))   # everybody ends with n_loc
             assert np.array_equal(tr.sum(1), np.maximum(per - n_loc, 0))            # only the surplus moves
             assert (np.diag(tr) == 0).all()
+
+
+def test_global_key_starts_match_a_global_stable_sort():
+    """Host logic of the sharded Box step: from the per-rank per-key child counts, rank r's first child of key q
+    sits at (children of smaller keys on all ranks) + (children of key q on lower ranks) in the global stable
+    order -- checked against an explicit stable sort of (key, rank-major child id), including 32-bit wrap."""
+    import torch
+
+    from mccube_b200._distributed import ShardedBoxStep
+
+    rs = np.random.default_rng(0)
+    G, n_keys, per_rank = 3, 17, 500
+    keys = [rs.integers(0, n_keys, size=per_rank) for _ in range(G)]
+    totals = torch.tensor(np.stack([np.bincount(k_, minlength=n_keys) for k_ in keys]), dtype=torch.int64)
+    allk = np.concatenate(keys)
+    order = np.argsort(allk, kind="stable")                       # global sorted position -> global child id
+    pos = np.empty_like(order); pos[order] = np.arange(order.size)
+    for r in range(G):
+        got = ShardedBoxStep.key_starts_for(r, totals).numpy().astype(np.int64) & 0xFFFFFFFF
+        for q in range(n_keys):
+            mine = np.nonzero(keys[r] == q)[0]
+            if mine.size:
+                assert got[q] == pos[r * per_rank + mine[0]], (r, q)
+    # positions are taken modulo 2^32 (uint32 bit patterns in an int32 tensor)
+    big = torch.tensor([[2 ** 31, 2 ** 31 - 5, 7], [1, 2, 3]], dtype=torch.int64)
+    got = ShardedBoxStep.key_starts_for(1, big)
+    assert got.dtype == torch.int32
+    assert (got.to(torch.int64) & 0xFFFFFFFF).tolist() == [2 ** 31, (2 ** 31 + 1 + 2 ** 31 - 5) % 2 ** 32, (2 ** 32 - 2 + 7) % 2 ** 32]
