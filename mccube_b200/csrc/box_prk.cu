@@ -834,9 +834,8 @@ static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cud
   const uint64_t total = p.a.n * (uint64_t)p.a.k;
   g.idx = p.idx_out; g.perm = nullptr; g.out_per_part = 1; g.in_per_part = 1;
   g.n_out = total / p.in_per_part * p.out_per_part; g.y1 = y1;
-  int rc = run_expand_select(g, st);
+  int rc = run_expand_select(g, st);               // (counts its own launch, launch_rank counted the ranking kernel)
   if (rc) return rc;
-  count_launches(1);
   return check_launch("box_prk_rank_gather");
 }
 
