@@ -126,6 +126,9 @@ class LocalLinearInterpolation:
         return tree_map(lambda a, b: a + coeff * (b - a), self.y0, self.y1)
 
 
+Euler.interpolation_cls = LocalLinearInterpolation        # as diffrax.Euler (defined above the interpolation class)
+
+
 @dataclass
 class SaveAt:
     t0: bool = False

@@ -221,3 +221,41 @@ def test_bench_reference_arm_prints_one_json_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config"):
         assert key in line, key
+
+
+def test_diffeqsolve_protocol_on_cpu():
+    """The constant-step driver (stand-in for diffrax.diffeqsolve, diffrax is not installable here) with the
+    plain Euler solver on CPU tensors: step count and float32 time accumulation, SaveAt(t0 / t1 / steps / ts /
+    dense), linear interpolation inside a step, max_steps."""
+    f = lambda t, y, args: -y                                               # noqa: E731
+    term = dfx.ODETerm(f)
+    y0 = torch.tensor([[1.0, 2.0]])
+    dt = 0.1
+    sol = dfx.diffeqsolve(term, dfx.Euler(), 0.0, 1.0, dt, y0, saveat=dfx.SaveAt(t0=True, steps=True))
+    times = dfx.step_times(0.0, 1.0, dt, np.float32)
+    assert sol.stats["num_steps"] == len(times) == 10 and sol.result == dfx.RESULTS.successful
+    assert sol.ys.shape == (11, 1, 2) and np.isclose(sol.ts[-1], 1.0)
+    want = y0.clone()
+    for (a, b) in times:
+        want = want + (-want) * float(np.float32(b) - np.float32(a))
+    assert torch.allclose(sol.ys[-1], want, rtol=1e-6)
+    # ts inside steps are linear interpolations of the step's end points; ts at step boundaries are exact
+    sol_ts = dfx.diffeqsolve(term, dfx.Euler(), 0.0, 1.0, dt, y0, saveat=dfx.SaveAt(ts=[0.0, 0.25, 0.5, 1.0]))
+    assert sol_ts.ys.shape[0] == 4 and torch.equal(sol_ts.ys[0], y0)
+    i25 = [i for i, (a, b) in enumerate(times) if a <= np.float32(0.25) <= b][0]
+    a, b = times[i25]
+    lo, hi = sol.ys[i25], sol.ys[i25 + 1]
+    w = (float(np.float32(0.25)) - float(a)) / (float(b) - float(a))
+    assert torch.allclose(sol_ts.ys[1], lo + w * (hi - lo), rtol=1e-6)
+    assert torch.allclose(sol_ts.ys[-1], sol.ys[-1])
+    # dense output evaluates anywhere; without it evaluate() raises
+    dense = dfx.diffeqsolve(term, dfx.Euler(), 0.0, 1.0, dt, y0, saveat=dfx.SaveAt(dense=True))
+    assert torch.allclose(dense.evaluate(0.25), sol_ts.ys[1], rtol=1e-6)
+    with pytest.raises(ValueError):
+        sol.evaluate(0.25)
+    # max_steps
+    short = dfx.diffeqsolve(term, dfx.Euler(), 0.0, 1.0, dt, y0, max_steps=4)
+    assert short.result == dfx.RESULTS.max_steps_reached and short.stats["num_steps"] == 4
+    # capture_solve refuses CPU states
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        dfx.capture_solve(term, dfx.Euler(), 0.0, 1.0, dt, y0)
