@@ -1,6 +1,7 @@
 """CPU-only checks: the C-ABI library builds, loads and exports every symbol that
 include/mccube_b200.h declares (no compute calls), and the host-side mirror of the reference
 API behaves like the reference's own tests expect."""
+import math
 import re
 import warnings
 from pathlib import Path
@@ -259,3 +260,37 @@ def test_diffeqsolve_protocol_on_cpu():
     # capture_solve refuses CPU states
     with pytest.raises(ValueError, match="CUDA tensor"):
         dfx.capture_solve(term, dfx.Euler(), 0.0, 1.0, dt, y0)
+
+
+def test_pairwise_metric_reference_expectation():
+    """/root/reference/tests/test_metrics.py:37-45 (host-side helper, plain torch)."""
+    y0 = torch.tensor([[0.0, 0.0], [3.0, 4.0], [5.0, 12.0]])
+    dist = mccube.pairwise_metric(y0, y0)
+    want = torch.tensor([[0.0, 5.0, 13.0], [5.0, 0.0, math.sqrt(68)], [13.0, math.sqrt(68), 0.0]])
+    assert torch.allclose(dist, want, rtol=1e-6)
+    # result[j, i] = metric(xs[i], ys[j]) for different inputs (_metrics.py:63-76)
+    xs, ys = torch.tensor([[0.0, 0.0], [1.0, 0.0]]), torch.tensor([[0.0, 2.0], [0.0, 0.0], [3.0, 4.0]])
+    got = mccube.pairwise_metric(xs, ys)
+    assert got.shape == (3, 2) and torch.allclose(got[2], torch.tensor([5.0, math.sqrt(20.0)]))
+
+
+def test_key_words_and_tree_helpers():
+    """Host-side plumbing: PRNG key forms (jr.key(seed) = (seed >> 32, seed & 0xffffffff))
+    and the PyTree helpers with jax.tree_util's leaf order (dict keys sorted)."""
+    from mccube_b200._kernels.random import key_words
+    from mccube_b200._tree import tree_leaves, tree_map, tree_map_with_index
+
+    assert key_words(42) == (0, 42) and key_words((1 << 35) + 7) == (8, 7)
+    assert key_words((3, 4)) == (3, 4) and key_words(torch.tensor([5, 6])) == (5, 6)
+    assert key_words(np.array([2 ** 32 + 1, -1])) == (1, 0xFFFFFFFF)
+    tree = {"b": [torch.ones(2), (torch.zeros(1), torch.full((1,), 2.0))], "a": torch.full((3,), 7.0)}
+    leaves = tree_leaves(tree)
+    assert [int(x.numel()) for x in leaves] == [3, 2, 1, 1]                 # "a" before "b"
+    doubled = tree_map(lambda x: 2 * x, tree)
+    assert isinstance(doubled["b"][1], tuple) and float(doubled["a"][0]) == 14.0
+    # a bare leaf as the second tree broadcasts (a prefix tree), like the reference's integer counts
+    summed = tree_map(lambda x, c: x + c, tree, 1.0)
+    assert float(summed["b"][1][1][0]) == 3.0
+    seen = []
+    tree_map_with_index(lambda i, n, leaf: seen.append((i, n, int(leaf.numel()))), tree)
+    assert seen == [(0, 4, 3), (1, 4, 2), (2, 4, 1), (3, 4, 1)]
