@@ -420,6 +420,22 @@ class ShardedBoxStep:
         ends = torch.cat([starts[1:], starts.new_tensor([pl["n_loc"] * pl["k"]])])
         return ws, (ends - starts)
 
+    # ---- the two collectives of a step (tiny: 2 * dims floats, n_keys integers); no data path collective
+    @staticmethod
+    def reduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
+        """Global [min..., max...] from every rank's local one with ONE all-reduce: min over (lo, -hi)."""
+        nd = minmax.numel() // 2
+        both = torch.cat([minmax[:nd], -minmax[nd:]])
+        dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
+        return torch.cat([both[:nd], -both[nd:]])
+
+    @staticmethod
+    def gather_totals(totals: torch.Tensor, n_ranks: int, group=None) -> torch.Tensor:
+        """[n_ranks, n_keys] matrix of every rank's per-key child counts."""
+        gathered = [torch.empty_like(totals) for _ in range(n_ranks)]
+        dist.all_gather(gathered, totals.contiguous(), group=group)
+        return torch.stack(gathered)
+
     @staticmethod
     def key_starts_for(rank: int, totals_all: torch.Tensor) -> torch.Tensor:
         """Global sorted position of rank's first child of every key from the [n_ranks, n_keys] count matrix:
@@ -478,18 +494,10 @@ class ShardedBoxStep:
         self._sel_ready = ((float(t0), pl["in_per_part"], pl["out_per_part"]), idx_local, sel, side)
         mm = self.local_minmax(t0, t1, y_in)
         if mm is not None and self.n_ranks > 1:
-            nd = mm.numel() // 2
-            both = torch.cat([mm[:nd], -mm[nd:]])                 # one collective: min of (lo, -hi)
-            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
-            mm = torch.cat([both[:nd], -both[nd:]])
+            mm = self.reduce_minmax(mm, group)
         bounds = self.bounds_from(t0, t1, y_in, mm)
         ws, totals = self.count(t0, t1, y_in, bounds)
-        if self.n_ranks > 1:
-            gathered = [torch.empty_like(totals) for _ in range(self.n_ranks)]
-            dist.all_gather(gathered, totals.contiguous(), group=group)
-            totals_all = torch.stack(gathered)
-        else:
-            totals_all = totals[None]
+        totals_all = self.gather_totals(totals, self.n_ranks, group) if self.n_ranks > 1 else totals[None]
         key_start = self.key_starts_for(rank, totals_all)
         self.rank_and_scatter(t0, t1, y_in, rank, ws, key_start, shards.ptrs[nxt])
         shards.barrier()          # every rank's rows have landed (and nobody still reads the other buffer)

@@ -162,3 +162,41 @@ def test_global_key_starts_match_a_global_stable_sort():
     got = ShardedBoxStep.key_starts_for(1, big)
     assert got.dtype == torch.int32
     assert (got.to(torch.int64) & 0xFFFFFFFF).tolist() == [2 ** 31, (2 ** 31 + 1 + 2 ** 31 - 5) % 2 ** 32, (2 ** 32 - 2 + 7) % 2 ** 32]
+
+
+def _box_worker(rank, world, port, out):
+    """The two collectives of ShardedBoxStep on CPU tensors over gloo: global min / max from one all-reduce and
+    the per-rank key-count matrix, then every rank's global key starts."""
+    from mccube_b200._distributed import ShardedBoxStep
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.default_rng(100 + rank)
+        lo, hi = rs.normal(size=3).astype(np.float32) - 2.0, rs.normal(size=3).astype(np.float32) + 2.0
+        mm = ShardedBoxStep.reduce_minmax(torch.tensor(np.concatenate([lo, hi])))
+        totals = torch.tensor(rs.integers(0, 50, size=11), dtype=torch.int64)
+        totals_all = ShardedBoxStep.gather_totals(totals, world)
+        starts = ShardedBoxStep.key_starts_for(rank, totals_all)
+        out[rank] = (mm.numpy(), totals.numpy(), starts.numpy(), lo, hi)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_box_collectives_two_ranks_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_box_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        got = {r: out[r] for r in range(world)}
+    lo = np.minimum(got[0][3], got[1][3])
+    hi = np.maximum(got[0][4], got[1][4])
+    for r in range(world):
+        assert np.array_equal(got[r][0], np.concatenate([lo, hi]))              # exact: min / max only
+    t0, t1 = got[0][1], got[1][1]
+    per_key = t0 + t1
+    base = np.cumsum(per_key) - per_key
+    assert np.array_equal(got[0][2].astype(np.int64), base)                     # rank 0 starts each key's run
+    assert np.array_equal(got[1][2].astype(np.int64), base + t0)                # rank 1 follows rank 0's children
