@@ -364,6 +364,23 @@ class ShardedBoxStep:
     def _plan(self, t0, t1, y_shard):
         from . import _lib
 
+        from ._drift import GaussianDiagDrift
+
+        # the phases of one step share one description; only when the drift is the analytic one (an array drift is
+        # evaluated on the shard's current contents, which a raw-pointer kernel may have rewritten in place)
+        if not isinstance(self.terms.ode.vector_field, GaussianDiagDrift):
+            return self._plan_uncached(t0, t1, y_shard)
+        tag = (float(t0), float(t1), y_shard.data_ptr(), tuple(y_shard.shape))
+        cached = getattr(self, "_plan_cache", None)
+        if cached is not None and cached[0] == tag:
+            return cached[1]
+        pl = self._plan_uncached(t0, t1, y_shard)
+        self._plan_cache = (tag, pl)
+        return pl
+
+    def _plan_uncached(self, t0, t1, y_shard):
+        from . import _lib
+
         solver = self.solver
         part = solver.recombination_kernel.partitioning_kernel
         mc = solver.recombination_kernel.recombination_kernel
@@ -417,7 +434,7 @@ class ShardedBoxStep:
                                 pl["in_per_part"], tables)
         starts = _lib.box_prk_local_key_starts(ws, pl["n_loc"], pl["k"], len(pl["dims"]), pl["bits"], pl["in_per_part"],
                                                pl["out_per_part"]).to(torch.int64) & 0xFFFFFFFF
-        ends = torch.cat([starts[1:], starts.new_tensor([pl["n_loc"] * pl["k"]])])
+        ends = torch.cat([starts[1:], torch.full((1,), pl["n_loc"] * pl["k"], dtype=torch.int64, device=starts.device)])
         return ws, (ends - starts)
 
     # ---- the two collectives of a step (tiny: 2 * dims floats, n_keys integers); no data path collective
