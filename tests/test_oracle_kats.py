@@ -160,3 +160,47 @@ def test_randint64_structure():
         if not part:
             bits = jr.random_bits(k2, 32, 200)
             assert np.array_equal(lo, (bits[:100].astype(np.uint64) << np.uint64(32)) | bits[100:].astype(np.uint64))
+
+
+# ------------------------------------------------------------------ property tests of the restated jax.random chain
+def test_oracle_random_properties():
+    """Size-independent properties of the restatement, over random keys / sizes (hypothesis): a shuffle is a
+    permutation, draws stay in range, a slice of the counter-based draws equals the slice of the full draw in
+    partitionable mode, `split` and `fold_in` agree where JAX defines them to, and everything is a pure function
+    of its arguments."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2 ** 63 - 1), size=st.integers(1, 300), part=st.booleans(), data=st.integers(0, 2 ** 32 - 1))
+    def run(seed, size, part, data):
+        key = jr.fold_in(jr.prng_key(seed), data)
+        perm = jr.shuffle_perm(key, size, partitionable=part)
+        assert sorted(perm.tolist()) == list(range(size))
+        assert np.array_equal(perm, jr.shuffle_perm(key, size, partitionable=part))           # deterministic
+        n_draws = max(1, size // 3)
+        idx = jr.choice_indices(key, size, n_draws, False, partitionable=part)
+        assert np.array_equal(idx, perm[:n_draws])                                             # choice = permutation prefix
+        rep = jr.choice_indices(key, size, 2 * size, True, partitionable=part)
+        assert rep.min() >= 0 and rep.max() < size and rep.shape == (2 * size,)
+        bits = jr.random_bits(key, 32, size, partitionable=part)
+        assert bits.dtype == np.uint32 and bits.shape == (size,)
+        if part:
+            # counter based: element i depends on (key, i) only, so a longer draw extends a shorter one
+            longer = jr.random_bits(key, 32, size + 7, partitionable=True)
+            assert np.array_equal(longer[:size], bits)
+            ks = jr.split(key, 3, partitionable=True)
+            for i in range(3):
+                assert tuple(int(v) for v in ks[i]) == tuple(int(v) for v in jr.fold_in(key, i))
+        else:
+            # original mode hashes iota(size) in two halves: the first ceil(size/2) words of a draw of `size`
+            # are the x0 outputs of blocks (i, i + h)
+            h = (size + 1) // 2
+            x1 = np.arange(h, 2 * h, dtype=np.uint32)
+            x1[x1 >= size] = 0
+            o0, o1 = jr.threefry2x32(key, np.arange(h, dtype=np.uint32), x1)
+            assert np.array_equal(bits[:h], o0) and np.array_equal(bits[h:], o1[:size - h])
+        u = jr.uniform(key, size, partitionable=part)
+        assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
+
+    run()
