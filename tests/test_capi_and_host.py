@@ -294,3 +294,36 @@ def test_key_words_and_tree_helpers():
     seen = []
     tree_map_with_index(lambda i, n, leaf: seen.append((i, n, int(leaf.numel()))), tree)
     assert seen == [(0, 4, 3), (1, 4, 2), (2, 4, 1), (3, 4, 1)]
+
+
+def test_c_abi_argument_errors_without_a_gpu(lib):
+    """every entry point validates before it touches the device and reports through a
+    status code + thread-local message (what the XLA-FFI shim turns into ffi::Error); size queries are pure host
+    functions.  None of this needs a GPU."""
+    import ctypes as C
+
+    lib.mccb200_last_error.restype = C.c_char_p
+    rng = _lib.make_rng((0, 42), 0.0)
+    assert lib.mccb200_mc_indices(C.byref(rng), 10, 20, 0, None, None, 0, None) != 0
+    assert b"NULL argument" in lib.mccb200_last_error()
+    fake = C.c_void_p(64)       # non-NULL, never dereferenced: validation fails first
+    assert lib.mccb200_mc_indices(C.byref(rng), 10, 20, 0, fake, fake, 1 << 30, None) != 0
+    assert b"without replacement" in lib.mccb200_last_error()
+    assert lib.mccb200_mc_indices(C.byref(rng), 1 << 20, 1 << 10, 0, fake, fake, 16, None) != 0
+    assert b"workspace" in lib.mccb200_last_error()
+    assert lib.mccb200_compact_slots(None, 10, None, 10, None, None) != 0
+    assert b"compact_slots" in lib.mccb200_last_error()
+    # workspace sizes: pure functions, monotone in the problem size, zero-replace draw needs no sort scratch
+    small = lib.mccb200_mc_indices_workspace_bytes(16384, 512, 0)
+    big = lib.mccb200_mc_indices_workspace_bytes(1 << 25, 1 << 20, 0)
+    assert 0 < small < big and lib.mccb200_mc_indices_workspace_bytes(1 << 25, 1 << 20, 1) < small
+    assert lib.mccb200_sort_pairs_workspace_bytes(1 << 20) >= 3 * 4 * (1 << 20)
+    n_keys = C.c_uint32(0)
+    off = lib.mccb200_box_prk_key_start_offset(1 << 20, 128, 4, 3, 8192, 64, C.byref(n_keys))
+    assert n_keys.value == 1 << 12 and off % 4 == 0
+    assert off < lib.mccb200_box_prk_step_workspace_bytes(1 << 20, 128, 4, 3, 8192)
+    assert lib.mccb200_box_prk_key_start_offset(1 << 20, 128, 6, 6, 8192, 64, C.byref(n_keys)) == C.c_size_t(-1).value
+    # tensor-core drift: multiples of 32 columns, 16-byte aligned rows
+    assert lib.mccb200_gaussian_full_drift_tc_supported(1 << 20, 512, 512) == 1
+    assert lib.mccb200_gaussian_full_drift_tc_supported(100, 48, 48) == 0
+    assert lib.mccb200_gaussian_full_drift_tc_supported(100, 64, 66) == 0
