@@ -38,9 +38,12 @@ import numpy as np
 # stdout carries exactly one JSON line.  Libraries write there too (with NCCL_DEBUG=VERSION, as set on the GPU
 # boxes, NCCL prints "NCCL version ..." to stdout at the first collective), so file descriptor 1 is pointed
 # at stderr for everything else and the result line goes to a private copy of the original stdout.
-_RESULT_OUT = os.fdopen(os.dup(1), "w")
-sys.stdout.flush()
-os.dup2(2, 1)
+if __name__ == "__main__":
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+else:                                   # imported (experiments/): leave the importer's stdout alone
+    _RESULT_OUT = sys.stdout
 
 
 def emit(line: dict):
@@ -711,6 +714,7 @@ def main():
     nd = a.box_dims
     alg = {
         "expand_select": 2.0 * n * d * 4,              # read n selected parent rows + write n rows
+        "box_prk.rank_gather": 2.0 * n * d * 4,        # fused ranking + gather kernel: the same rows (+ 4 B/parent in)
         "box_prk.rank": n * (4 + 4.0),                 # packed parent descriptor in, selected child id out
         "box_prk.count": n * (nd * 4 + 4.0),           # key dims in, packed descriptor out
         "box_child_bounds": n * nd * 4.0,              # key dims in
@@ -723,12 +727,18 @@ def main():
         dom_name = max(timed, key=timed.get)
         dur_ms = timed[dom_name]
         achieved = alg[dom_name] / (dur_ms * 1e-3) / 1e9
-        traffic = None
-        tfile = ROOT / "profiles" / "traffic_r1.json"   # dram__bytes_read+write per launch from `ncu --set full`
-        if tfile.exists():
-            traffic = json.loads(tfile.read_text()).get(dom_name)
+        # dram__bytes_read + write per launch of that kernel, from the newest committed `ncu --set full` capture
+        # (profiles/traffic_r*.json names the .csv it was read from); null when no capture covers the kernel
+        traffic, traffic_src = None, None
+        for tfile in sorted((ROOT / "profiles").glob("traffic_r*.json"), reverse=True):
+            rec = json.loads(tfile.read_text())
+            if dom_name in rec:
+                traffic, traffic_src = rec[dom_name], f"{tfile.name} ({rec.get('source', 'ncu --set full')})"
+                break
+        step_gbs = 2.0 * n * d * 4 / (ms_step * 1e-3) / 1e9     # the step's algorithmic bytes over the whole step
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "achieved_step": step_gbs, "frac_step": step_gbs / peak,
                     "algorithmic_bytes_per_launch": alg[dom_name], "kernel_ms": dur_ms,
                     "share_of_step": dur_ms / max(sum(phase_ms.values()), 1e-9), "all_kernels": kernels}
 

@@ -625,6 +625,396 @@ box_rank_flat_kernel(const BoxPrkParams p) {
   if (q_count) drain(q_count);
 }
 
+// ------------------------------------------------------------------ pass B + gather, fused (warp-specialised)
+// One persistent CTA per SM.  Warps 0 .. RW-1 run the ranking walk of box_rank_flat_kernel unchanged, but a
+// selected child is not written out as an id: it becomes a ROW JOB (child id, output row) in the warp's
+// shared-memory ring.  The remaining TW warps materialise the jobs: 32 at a time, every lane asks the TMA
+// engine for one parent row (cp.async.bulk global -> shared, 256 bytes at d = 64, completion counted on an
+// mbarrier), two stages deep, so the bytes in flight cost no registers and no issue slots; when a stage has
+// landed the warp applies drift + signed noise in the reference's fp32 op order to 128-bit chunks read from
+// shared memory and streams the child rows (and their packed key columns) to their final slots.  The 64 MB
+// index vector and the separate HBM-bound gather pass disappear, a parent row selected twice is fetched from
+// L2 the second time, and the ranking warps' dependent chains fill the issue slots the copy does not need.
+// Ring protocol (shared memory, one ring per ranking warp): the producer publishes `tail` after writing the
+// jobs, the consumer publishes `head` after it has materialised them, `done` closes the ring.
+constexpr int FZ_MAX_THREADS = 1024;
+constexpr int FZ_JQ = 128;      // row-job ring entries per ranking warp
+constexpr int FZ_STAGES = 2;    // TMA stages per transform warp (32 parent rows each)
+constexpr int FZ_MAX_RINGS = 4; // rings served by one transform warp
+
+struct FusedOut {
+  float* y1;
+  float* keycols_out;        // optional [n_out, 4]
+  int keycol0;
+  int vpr;                   // 128-bit chunks per row (d / 4 <= 32)
+  int lpr_shift;             // log2(lanes per row) = log2(pow2 >= vpr)
+  int rank_warps;            // warps 0 .. rank_warps-1 rank, the others materialise rows
+  uint32_t row_bytes;        // d * 4
+  uint32_t xform_words;      // shared-memory words of one transform warp (stages + barriers)
+  uint32_t spin_ns;          // back-off of the ring waits
+  float one, neg_one, neg_zero;   // 1, -1, -0 as RUNTIME values: ptxas must not fold the exact-rounding fmas (see f2_fma)
+};
+
+__device__ __forceinline__ uint32_t fz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_vol(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+__device__ __forceinline__ void fz_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spins on the phase parity; traps instead of hanging the GPU if a phase never completes.
+__device__ __forceinline__ void fz_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+// one row: global -> shared through the TMA engine (addresses and size multiples of 16 bytes)
+__device__ __forceinline__ void fz_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Packed fp32 pairs (Blackwell FFMA2).  Every step of the reference's fp32 op order is ONE rounding, written as
+// an fma whose extra operand makes it that rounding exactly -- a * b = fma(a, b, -0), a + b = fma(a, 1, b),
+// m - y = fma(y, -1, m) -- with the constants 1, -1, -0 passed in as kernel arguments: given literal constants
+// ptxas rewrites the fmas into mul.f32x2 / add.f32x2 and then CONTRACTS dt * f + noise into one FFMA2 (seen in
+// SASS), which is a different rounding.  With runtime operands every step stays its own FFMA2 and the results are
+// bit-identical to __fmul_rn / __fadd_rn / __fsub_rn (checked against the scalar kernels by the parity tests).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+struct ChildConst {       // per-lane constants of its 128-bit column chunk
+  uint64_t mean01, mean23, ivar01, ivar23, dt2, one2, mone2, nzero2;
+  uint32_t cmask, top_shift, scale_bits;
+};
+
+// One 128-bit chunk of a child row in the reference's fp32 op order: y + (dt * f + noise), f = (mean - y) * inv_var,
+// the noise being +-scale with the Hadamard sign of point j in columns col .. col+3 (col % 4 == 0):
+// parity(j & col) ^ block ^ {0, j0, j1, j0 ^ j1}, applied to the sign bit of scale.
+template <int DRIFT>
+__device__ __forceinline__ float4 fz_child4(const ChildConst& c, const float4& y, uint32_t j, uint32_t half_mask) {
+  const uint32_t jm = j & half_mask;
+  const uint32_t s0 = c.scale_bits ^ (((uint32_t)__popc(jm & c.cmask) + (j >> c.top_shift)) << 31);
+  const uint32_t b0 = jm << 31, b1 = (jm >> 1) << 31;
+  const uint64_t n01 = f2_pack(__uint_as_float(s0), __uint_as_float(s0 ^ b0));
+  const uint64_t n23 = f2_pack(__uint_as_float(s0 ^ b1), __uint_as_float(s0 ^ b0 ^ b1));
+  const uint64_t y01 = f2_pack(y.x, y.y), y23 = f2_pack(y.z, y.w);
+  uint64_t st01, st23;
+  if (DRIFT == 2) {
+    const uint64_t f01 = f2_fma(f2_fma(y01, c.mone2, c.mean01), c.ivar01, c.nzero2);   // (mean - y) * inv_var
+    const uint64_t f23 = f2_fma(f2_fma(y23, c.mone2, c.mean23), c.ivar23, c.nzero2);
+    st01 = f2_fma(f01, c.dt2, c.nzero2);                                              // dt * f
+    st23 = f2_fma(f23, c.dt2, c.nzero2);
+  } else {
+    st01 = st23 = f2_fma(f2_pack(0.f, 0.f), c.dt2, c.nzero2);
+  }
+  const uint64_t o01 = f2_fma(f2_fma(st01, c.one2, n01), c.one2, y01);                 // y + (dt * f + noise)
+  const uint64_t o23 = f2_fma(f2_fma(st23, c.one2, n23), c.one2, y23);
+  float4 out;
+  f2_unpack(o01, out.x, out.y);
+  f2_unpack(o23, out.z, out.w);
+  return out;
+}
+
+template <int DRIFT, bool D64>
+__global__ void __launch_bounds__(FZ_MAX_THREADS, 1)
+box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
+  extern __shared__ uint32_t smem[];
+  const ExpandArgs& a = p.a;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int RW = o.rank_warps, TW = (int)(blockDim.x >> 5) - RW;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // ---- CTA-wide tables (as box_rank_flat_kernel<true, true, true>)
+  uint32_t* cursor = smem;
+  const uint32_t cls_pad = 1u << p.cls_pad_log2;
+  uint32_t* s_tab = cursor; cursor += p.n_sets * cls_pad;
+  uint32_t* s_cnt = cursor; cursor += p.n_sets;
+  cursor += ((cursor - smem) & 1u);
+  uint2* s_sp = reinterpret_cast<uint2*>(cursor); cursor += 4u * p.out_per_part;
+  uint16_t* s_pre16 = reinterpret_cast<uint16_t*>(cursor); cursor += ((p.in_per_part + p.sel_ext + 4u) & ~3u) / 2u;
+  uint16_t* s_mem = reinterpret_cast<uint16_t*>(cursor); cursor += (p.n_sets * a.k + 1u) / 2u;
+  cursor += (4u - ((uint32_t)(cursor - smem) & 3u)) & 3u;          // 16-byte alignment of what follows
+  for (uint32_t i = threadIdx.x; i < p.n_sets * cls_pad; i += blockDim.x) s_tab[i] = p.cls_packed[i];
+  for (uint32_t i = threadIdx.x; i < p.n_sets; i += blockDim.x) s_cnt[i] = p.cls_count[i];
+  for (uint32_t i = threadIdx.x; i <= p.in_per_part + p.sel_ext; i += blockDim.x) s_pre16[i] = (uint16_t)p.pre[i];
+  for (uint32_t i = threadIdx.x; i < 2u * p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
+  for (uint32_t i = threadIdx.x; i < p.n_sets * a.k; i += blockDim.x) s_mem[i] = p.members[i];
+  // ---- per ranking warp: hit-record ring (FQ_CAP x 16 B) | job ring (FZ_JQ x 8 B) | control (4 words)
+  constexpr uint32_t RANK_WORDS = FQ_CAP * 4 + FZ_JQ * 2 + 4;
+  auto rank_block = [&](int w) { return cursor + (size_t)w * RANK_WORDS; };
+  // ---- per transform warp: FZ_STAGES x 32 rows | FZ_STAGES mbarriers
+  uint32_t* xbase = cursor + (size_t)RW * RANK_WORDS;
+  if (warp < RW) {
+    if (lane < 4) rank_block(warp)[FQ_CAP * 4 + FZ_JQ * 2 + lane] = 0u;
+  } else if (lane == 0) {
+    uint32_t* xb = xbase + (size_t)(warp - RW) * o.xform_words;
+    for (int s = 0; s < FZ_STAGES; ++s) fz_mbar_init(fz_smem_u32(xb + FZ_STAGES * 8u * o.row_bytes + 2 * s), 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int logk = __ffs(a.k) - 1;
+
+  if (warp >= RW) {
+    // ================= transform warps
+    const int tw = warp - RW;
+    uint32_t* xb = xbase + (size_t)tw * o.xform_words;
+    const uint32_t stage_bytes = 32u * o.row_bytes;
+    const uint32_t buf0 = fz_smem_u32(xb), bar0 = fz_smem_u32(xb + FZ_STAGES * 8u * o.row_bytes);
+    const int lpr_shift = D64 ? 4 : o.lpr_shift;
+    const int sub = lane & ((1 << lpr_shift) - 1), rs = lane >> lpr_shift, rpp = 32 >> lpr_shift;
+    const int vpr = D64 ? 16 : o.vpr;
+    const uint32_t ld = D64 ? 64u : (uint32_t)a.ld;
+    const uint32_t col = (uint32_t)sub * 4u;
+    ChildConst cc;
+    {
+      float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), ivar = mean;
+      if (DRIFT == 2 && sub < vpr) {
+        mean = __ldg(reinterpret_cast<const float4*>(a.mean + col));
+        ivar = __ldg(reinterpret_cast<const float4*>(a.inv_var + col));
+      }
+      cc.mean01 = f2_pack(mean.x, mean.y); cc.mean23 = f2_pack(mean.z, mean.w);
+      cc.ivar01 = f2_pack(ivar.x, ivar.y); cc.ivar23 = f2_pack(ivar.z, ivar.w);
+      cc.dt2 = f2_pack(a.dt, a.dt); cc.one2 = f2_pack(o.one, o.one); cc.mone2 = f2_pack(o.neg_one, o.neg_one);
+      cc.nzero2 = f2_pack(o.neg_zero, o.neg_zero);
+      cc.cmask = col & a.half_mask; cc.top_shift = (uint32_t)logk - 1u; cc.scale_bits = __float_as_uint(a.scale);
+    }
+    uint32_t fetch[FZ_MAX_RINGS] = {0u, 0u, 0u, 0u};   // jobs handed to the TMA engine, per served ring
+    uint32_t st_ring[FZ_STAGES] = {0u, 0u}, st_head[FZ_STAGES] = {0u, 0u}, st_cnt[FZ_STAGES] = {0u, 0u};
+    uint32_t phase_bits = 0;                            // parity of each stage's barrier
+    int in_flight = 0, next_load = 0, next_use = 0, rr = 0;
+    uint32_t idle_spins = 0;
+    long long idle_t0 = 0;
+    for (;;) {
+      // ---- hand the next block of 32 jobs to the TMA engine if a stage is free
+      bool issued = false, all_done = true;
+      if (in_flight < FZ_STAGES) {
+#pragma unroll
+        for (int qq = 0; qq < FZ_MAX_RINGS; ++qq) {
+          const int q = (rr + qq) & (FZ_MAX_RINGS - 1);
+          const int r = tw + q * TW;
+          if (r >= RW || issued) continue;
+          uint32_t* ctrl = rank_block(r) + FQ_CAP * 4 + FZ_JQ * 2;
+          uint32_t done = 0, tail = 0;
+          if (lane == 0) { done = ld_vol(ctrl + 2); tail = ld_vol(ctrl); }   // done first: a set flag means tail is final
+          done = __shfl_sync(0xffffffffu, done, 0);
+          tail = __shfl_sync(0xffffffffu, tail, 0);
+          const uint32_t avail = tail - fetch[q];
+          if (avail >= 32u || (done && avail)) {
+            const uint32_t cnt = avail < 32u ? avail : 32u;
+            __threadfence_block();
+            const uint2* jq = reinterpret_cast<const uint2*>(rank_block(r) + FQ_CAP * 4);
+            const uint32_t bar = bar0 + 8u * (uint32_t)next_load;
+            if (lane == 0) fz_mbar_expect_tx(bar, cnt * o.row_bytes);
+            __syncwarp();
+            if ((uint32_t)lane < cnt) {
+              const uint32_t child = jq[(fetch[q] + (uint32_t)lane) & (FZ_JQ - 1)].x;
+              fz_bulk_row(buf0 + (uint32_t)next_load * stage_bytes + (uint32_t)lane * o.row_bytes,
+                          a.y0 + (uint64_t)(child >> logk) * ld, o.row_bytes, bar);
+            }
+            st_ring[next_load] = (uint32_t)r; st_head[next_load] = fetch[q]; st_cnt[next_load] = cnt;
+            fetch[q] += cnt;
+            next_load ^= 1;
+            ++in_flight;
+            issued = true;
+            rr = (q + 1) & (FZ_MAX_RINGS - 1);
+          }
+          if (!(done && tail == fetch[q])) all_done = false;
+        }
+      } else {
+        all_done = false;
+      }
+      // ---- materialise the oldest stage when both are busy or nothing new could be issued
+      if (in_flight == FZ_STAGES || (!issued && in_flight > 0)) {
+        const int s = next_use;
+        fz_mbar_wait(bar0 + 8u * (uint32_t)s, (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+        uint32_t* rb = rank_block((int)st_ring[s]);
+        const uint2* jq = reinterpret_cast<const uint2*>(rb + FQ_CAP * 4);
+        const uint32_t head = st_head[s], cnt = st_cnt[s];
+        const char* buf = reinterpret_cast<const char*>(xb) + (size_t)s * stage_bytes;
+        if (sub < vpr) {
+#pragma unroll 4
+          for (uint32_t t = (uint32_t)rs; t < cnt; t += (uint32_t)rpp) {
+            const uint2 job = jq[(head + t) & (FZ_JQ - 1)];
+            const float4 y = *reinterpret_cast<const float4*>(buf + t * o.row_bytes + col * 4u);
+            const float4 out = fz_child4<DRIFT>(cc, y, job.x & (a.k - 1u), a.half_mask);
+            st_stream4(o.y1 + ((uint64_t)job.y * ld + col), out);
+            if (o.keycols_out != nullptr && (int)col == o.keycol0) st_stream4(o.keycols_out + (uint64_t)job.y * 4u, out);
+          }
+        }
+        __syncwarp();                                       // all reads of the stage are done before it is refilled
+        if (lane == 0) st_vol(rb + FQ_CAP * 4 + FZ_JQ * 2 + 1, head + cnt);   // frees the ring slots
+        next_use ^= 1;
+        --in_flight;
+        continue;
+      }
+      if (issued) continue;
+      if (all_done) break;
+      __nanosleep(o.spin_ns);
+      if ((++idle_spins & 4095u) == 0u) {                     // a protocol bug must trap, not hang the GPU
+        if (idle_t0 == 0) idle_t0 = clock64();
+        else if (clock64() - idle_t0 > 8000000000ll) __trap();
+      }
+    }
+    return;
+  }
+
+  // ================= ranking warps (the walk of box_rank_flat_kernel; see there)
+  uint32_t* wb = rank_block(warp);
+  uint4* hq = reinterpret_cast<uint4*>(wb);                  // (rank0, first, n_hit | moff << 11, child0)
+  uint2* jq = reinterpret_cast<uint2*>(wb + FQ_CAP * 4);
+  uint32_t* ctrl = wb + FQ_CAP * 4 + FZ_JQ * 2;
+  const uint32_t* s_tab_biased = s_tab - FLAT_TOFF_BIAS;
+  const uint32_t Pm = p.in_per_part, nm = p.out_per_part;
+  const uint32_t ushift = (uint32_t)logk - p.cls_pad_log2;   // log2(unit)
+  uint32_t q_head = 0, q_count = 0;                          // hit-record ring (warp-uniform)
+  uint32_t j_tail = 0;                                       // jobs published so far (warp-uniform)
+
+  auto wait_space = [&](uint32_t cnt) {                      // until the transform warp has freed cnt ring slots
+    if (lane == 0) {
+      long long t0 = 0;
+      for (uint32_t spin = 0; j_tail + cnt - ld_vol(ctrl + 1) > (uint32_t)FZ_JQ; ++spin) {
+        __nanosleep(o.spin_ns);
+        if ((spin & 4095u) == 4095u) {                        // a protocol bug must trap, not hang the GPU
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+      }
+    }
+    __syncwarp();
+  };
+  auto publish = [&](uint32_t cnt) {
+    j_tail += cnt;
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); st_vol(ctrl, j_tail); }
+  };
+  // turn cnt (<= 32) queued hit records into row jobs
+  auto drain = [&](uint32_t cnt) {
+    uint32_t first = 0, n_hit = 0, child0 = 0, slot0 = 0, midx = 0;
+    if ((uint32_t)lane < cnt) {
+      const uint4 e4 = hq[(q_head + (uint32_t)lane) & (FQ_CAP - 1)];
+      slot0 = (e4.x >> p.in_shift) * nm;
+      midx = (e4.z >> 11) - (e4.x & (Pm - 1u));              // + position = index into the class's member list
+      first = e4.y; n_hit = e4.z & 0x7FFu; child0 = e4.w;
+    }
+    q_head = (q_head + cnt) & (FQ_CAP - 1);
+    q_count -= cnt;
+    uint32_t hx = n_hit;                                     // inclusive scan: every lane's ring slots
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, hx, sft);
+      if (lane >= sft) hx += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, hx, 31);
+    if (total <= 64u) {
+      wait_space(total);
+      uint32_t at = j_tail + hx - n_hit;
+      for (uint32_t it = 0; it < n_hit; ++it, ++at) {
+        const uint2 pl = s_sp[first + it];                  // (position, output slot l), extended past one wrap
+        jq[at & (FZ_JQ - 1)] = make_uint2(child0 + s_mem[midx + pl.x], slot0 + pl.y);
+      }
+      publish(total);
+    } else {                                                 // (rare: one job per lane and trip)
+      for (uint32_t it = 0;; ++it) {
+        const bool more = it < n_hit;
+        const uint32_t mm = __ballot_sync(0xffffffffu, more);
+        if (mm == 0u) break;
+        wait_space(32u);
+        if (more) {
+          const uint2 pl = s_sp[first + it];
+          jq[(j_tail + (uint32_t)__popc(mm & lt_mask)) & (FZ_JQ - 1)] = make_uint2(child0 + s_mem[midx + pl.x], slot0 + pl.y);
+        }
+        publish((uint32_t)__popc(mm));
+      }
+    }
+  };
+
+  const uint32_t total_warps = gridDim.x * (uint32_t)RW;
+  for (uint32_t seg = blockIdx.x * (uint32_t)RW + (uint32_t)warp; seg < p.n_segments; seg += total_warps) {
+    uint32_t* row = p.table + (uint64_t)seg * p.n_keys;    // same key, earlier segments (relative ranks)
+    const uint64_t i0 = (uint64_t)seg * p.parents_per_seg;
+    const uint64_t i1 = min(a.n, i0 + p.parents_per_seg);
+    auto front = [&](const FlatBatch& b, uint64_t base, uint32_t r0, FlatRound& fr) {
+      const FlatRecord rec = flat_record(b, r0, lane, s_tab_biased);
+      const uint32_t peers = __match_any_sync(0xffffffffu, rec.key);
+      uint32_t exu, totu;
+      peer_units(peers, rec.e, p.cls_pad_log2, lt_mask, exu, totu);
+      fr.leader = __ffs(peers) - 1;
+      fr.st = 0;
+      if (rec.valid && lane == fr.leader) fr.st = atomicAdd(row + rec.key, totu << ushift);
+      fr.valid = rec.valid; fr.key = rec.key; fr.exu = exu; fr.e = rec.e;
+      fr.child0 = ((uint32_t)base + (uint32_t)(rec.owner & 31)) << logk;   // child ids are uint32 (n * k <= 2^32)
+      fr.moff = (rec.S << logk) + (rec.ent >> 22);
+    };
+    auto back = [&](const FlatRound& fr) {
+      const uint32_t st = __shfl_sync(0xffffffffu, fr.st, fr.leader);
+      uint32_t n_hit = 0, rank0 = 0, first = 0;
+      if (fr.valid) {
+        rank0 = st + __ldg(p.key_start + fr.key) + (fr.exu << ushift);
+        const uint32_t pos0 = rank0 & (Pm - 1u);
+        first = s_pre16[pos0];
+        n_hit = (uint32_t)s_pre16[pos0 + ((1u << fr.e) << ushift)] - first;   // size <= k <= Pm: the extended table covers the wrap
+      }
+      const uint32_t hm = __ballot_sync(0xffffffffu, n_hit != 0u);
+      if (hm) {
+        if (n_hit) {
+          const uint32_t at = (q_head + q_count + (uint32_t)__popc(hm & lt_mask)) & (FQ_CAP - 1);
+          hq[at] = make_uint4(rank0, first, n_hit | (fr.moff << 11), fr.child0);
+        }
+        q_count += (uint32_t)__popc(hm);
+        __syncwarp();
+        if (q_count >= 32u) drain(32u);
+      }
+    };
+    FlatRound cur, nxt;
+    bool have_cur = false;
+    uint32_t ndesc = i0 + lane < i1 ? __ldcs(p.pdesc + i0 + lane) : 0u;
+    for (uint64_t base = i0; base < i1; base += 32) {
+      const uint32_t desc = ndesc;
+      const bool have = base + lane < i1;
+      if (base + 32 + lane < i1) ndesc = __ldcs(p.pdesc + base + 32 + lane);   // next batch (coalesced)
+      const FlatBatch b = flat_batch(desc, have ? s_cnt[desc >> 24] : 0u, lane, p.cls_pad_log2);
+      for (uint32_t r0 = 0; r0 < b.R; r0 += 32) {
+        __syncwarp();   // order this round's atomics after the previous round's (same-key runs)
+        front(b, base, r0, nxt);
+        if (have_cur) back(cur);
+        cur = nxt;
+        have_cur = true;
+      }
+    }
+    if (have_cur) back(cur);
+    if (q_count) drain(q_count);
+  }
+  __syncwarp();
+  if (lane == 0) { __threadfence_block(); st_vol(ctrl + 2, 1u); }
+}
+
 // ------------------------------------------------------------------ host side: layouts
 struct TablesLayout {
   TableSpec t;
@@ -669,19 +1059,66 @@ static bool make_sel_layout(SelLayout& L, uint64_t in_per_part, uint64_t out_per
   return true;
 }
 
+static int max_optin_smem() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+  return v;
+}
+
+// Launch geometry of box_rank_fused_kernel (one CTA per SM): ranking warps, transform warps, shared memory.
+struct FusedGeom { int rank_warps, xform_warps; size_t smem, xform_words; };
+
+static bool fused_geometry(uint32_t n_sets, uint32_t cls_pad_log2, uint32_t k, uint64_t in_per_part, uint64_t sel_ext,
+                           uint64_t out_per_part, uint32_t row_bytes, FusedGeom& g) {
+  size_t words = ((size_t)n_sets << cls_pad_log2) + (size_t)n_sets;
+  words += words & 1;
+  words += 4 * (size_t)out_per_part;
+  words += (((size_t)in_per_part + sel_ext + 4) & ~(size_t)3) / 2;
+  words += ((size_t)n_sets * k + 1) / 2;
+  words = (words + 3) & ~(size_t)3;
+  const size_t rank_words = (size_t)FQ_CAP * 4 + (size_t)FZ_JQ * 2 + 4;
+  g.xform_words = (size_t)FZ_STAGES * 8 * row_bytes + 2 * FZ_STAGES + 2;   // stages (32 rows each) + mbarriers
+  g.xform_words = (g.xform_words + 3) & ~(size_t)3;
+  const size_t cap = (size_t)max_optin_smem();
+  int rw = env_int("MCCB200_FUSED_WARPS", 24), tw = env_int("MCCB200_FUSED_TWARPS", 8);
+  if (rw < 1) rw = 1;
+  if (tw < 1) tw = 1;
+  if (rw + tw > FZ_MAX_THREADS / 32) rw = FZ_MAX_THREADS / 32 - tw;
+  while (tw > 1 && (words + (size_t)rw * rank_words + (size_t)tw * g.xform_words) * 4 > cap) --tw;
+  if (rw > FZ_MAX_RINGS * tw) rw = FZ_MAX_RINGS * tw;
+  if (rw < 1 || (words + (size_t)rw * rank_words + (size_t)tw * g.xform_words) * 4 > cap) return false;
+  g.rank_warps = rw;
+  g.xform_warps = tw;
+  g.smem = (words + (size_t)rw * rank_words + (size_t)tw * g.xform_words) * 4;
+  return true;
+}
+
+// What the fused kernel needs of the SHAPE (known to the counting and the ranking call alike, so that both cut
+// the same segments); pointers and the selection size are checked again at launch (fused_plan).
+static bool fused_shape_ok(int k, uint64_t in_per_part, int d, int ld, int drift_kind, int weighted) {
+  if (env_int("MCCB200_BOX_FUSED", 1) == 0) return false;
+  if (k > 256 || (in_per_part & (in_per_part - 1)) != 0) return false;
+  if (weighted || (d & 3) || ld != d || d > 128 || drift_kind == 1) return false;
+  const size_t pre_bytes_128 = ((size_t)((in_per_part + BP_MAX_K + 4) & ~3ull)) * 2 + (size_t)128 * 16;
+  return pre_bytes_128 <= 28 * 1024;
+}
+
 struct PrkPlan {
   TablesLayout tl;
   uint32_t n_keys, n_segments;
   int warps_per_cta, ctas_per_sm, grid_b, pre_in_smem, mem_in_smem;
   uint64_t parents_per_seg;
   size_t smem_a, smem_b;
-  size_t off_pdesc, off_table, off_idx, off_tables, off_sel, total;
+  size_t off_pdesc, off_keytot, off_table, off_idx, off_tables, off_sel, total;
 };
 
 // Workspace: [pdesc | table (+ key totals) | idx_out | class tables | selection tables]; the last
 // two regions are only used by the all-in-one mccb200_box_prk_step.
+// fused: 1 = segments for the fused rank + gather kernel (one per ranking warp), 0 = one per warp of the 4 resident
+// CTAs of box_rank_flat_kernel, -1 = unknown (workspace query: sized for the larger of the two).
 static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, uint64_t in_per_part,
-                          uint64_t out_per_part_max) {
+                          uint64_t out_per_part_max, int fused = 0) {
   if (!make_tables_layout(pl.tl, k, n_dims, bits)) return false;
   if (in_per_part >= 0x40000000ull || in_per_part < (uint64_t)k) return false;  // a class run wraps at most once
   if (out_per_part_max >= 0x40000000ull || out_per_part_max < 1) return false;
@@ -698,8 +1135,17 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   pl.warps_per_cta = 8;
   // 4 resident pass-B CTAs per SM.  Measured: 5 / 6 CTAs (48 / 40 registers) leave pass B at 0.75 / 0.83 ms
   // (it is issue-bound, not latency-bound) and push the counter table past L2 (scan 0.09 -> 0.20 / 0.28 ms).
-  pl.ctas_per_sm = 4;
+  pl.ctas_per_sm = env_int("MCCB200_RANK_CTAS", 4);
   uint64_t segs = (uint64_t)sm_count() * pl.warps_per_cta * pl.ctas_per_sm;   // one warp per segment
+  if (fused != 0 && pl.mem_in_smem) {
+    FusedGeom g;
+    if (fused_geometry(t.n_sets, t.cls_pad_log2, (uint32_t)k, in_per_part, BP_MAX_K, 128, 256, g)) {
+      int spw = env_int("MCCB200_FUSED_SPW", 1);
+      if (spw < 1) spw = 1;
+      const uint64_t fsegs = (uint64_t)sm_count() * g.rank_warps * spw;
+      segs = fused > 0 ? fsegs : (fsegs > segs ? fsegs : segs);
+    }
+  }
   if (segs > n) segs = n ? n : 1;
   pl.parents_per_seg = (n + segs - 1) / segs;
   pl.n_segments = (uint32_t)((n + pl.parents_per_seg - 1) / pl.parents_per_seg);
@@ -713,7 +1159,8 @@ static bool make_prk_plan(PrkPlan& pl, uint64_t n, int k, int n_dims, int bits, 
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t o = cur; cur += align_up(bytes, 256); return o; };
   pl.off_pdesc = take((size_t)n * 4);
-  pl.off_table = take(((size_t)pl.n_segments + 1) * row);
+  pl.off_keytot = take(row);                             // key starts: before the table, so that their offset
+  pl.off_table = take((size_t)pl.n_segments * row);      // does not depend on the segment count
   pl.off_idx = take((size_t)n_out_max * 4);
   pl.off_tables = take(pl.tl.total);
   pl.off_sel = take(sl.total);
@@ -766,7 +1213,8 @@ static int setup_params(BoxPrkParams& p, PrkPlan& pl, const float* y0, uint64_t 
   MCCB_REQUIRE(in_per_part >= 1 && total % in_per_part == 0, "%s: in_per_part=%llu does not divide n*k=%llu", who,
                (unsigned long long)in_per_part, (unsigned long long)total);
   MCCB_REQUIRE(out_per_part >= 1, "%s: bad out_per_part", who);
-  if (!make_prk_plan(pl, n, cub->k, n_dims, bits, in_per_part, out_per_part))
+  const int fused_hint = fused_shape_ok(cub->k, in_per_part, p.a.d, p.a.ld, p.a.drift_kind, p.a.weighted) ? 1 : 0;
+  if (!make_prk_plan(pl, n, cub->k, n_dims, bits, in_per_part, out_per_part, fused_hint))
     return fail(MCCB200_ERR_UNSUPPORTED, "%s: shape unsupported (key bits %d > %d, k > %d or in_per_part < k)", who,
                 n_dims * bits, BP_MAX_KEY_BITS, BP_MAX_K);
   if (workspace_bytes < pl.total)
@@ -774,7 +1222,7 @@ static int setup_params(BoxPrkParams& p, PrkPlan& pl, const float* y0, uint64_t 
   char* w = (char*)workspace;
   p.pdesc = (uint32_t*)(w + pl.off_pdesc);
   p.table = (uint32_t*)(w + pl.off_table);
-  p.key_start = p.table + (uint64_t)pl.n_segments * pl.n_keys;
+  p.key_start = (const uint32_t*)(w + pl.off_keytot);
   p.idx_out = (uint32_t*)(w + pl.off_idx);
   p.n_keys = pl.n_keys;
   p.n_segments = pl.n_segments;
@@ -792,7 +1240,7 @@ static int launch_count(BoxPrkParams& p, const PrkPlan& pl, cudaStream_t st) {
   if (box_dims_vec4(p.spec, p.a)) box_count_flat_kernel<true><<<pl.n_segments, 256, pl.smem_a, st>>>(p);
   else box_count_flat_kernel<false><<<pl.n_segments, 256, pl.smem_a, st>>>(p);
   phase_mark("box_prk.scan", st);
-  uint32_t* key_tot = p.table + (uint64_t)pl.n_segments * pl.n_keys;
+  uint32_t* key_tot = const_cast<uint32_t*>(p.key_start);
   if (pl.n_keys % 4 == 0)
     box_scan_columns_kernel<4><<<(pl.n_keys / 4 + SC_KQ - 1) / SC_KQ, SC_KQ * SC_CY, 0, st>>>(p.table, pl.n_segments, pl.n_keys, key_tot);
   else
@@ -825,7 +1273,59 @@ static int launch_rank(BoxPrkParams& p, const PrkPlan& pl, cudaStream_t st) {
   return check_launch("box_prk_rank");
 }
 
+// Shape / alignment conditions of box_rank_fused_kernel; fills the launch geometry.
+struct FusedLaunch { FusedOut o; int warps, grid; size_t smem; };
+
+static bool fused_plan(const BoxPrkParams& p, const PrkPlan& pl, float* y1, float* keycols_out, FusedLaunch& fl) {
+  const ExpandArgs& a = p.a;
+  if (!fused_shape_ok((int)a.k, p.in_per_part, a.d, a.ld, a.drift_kind, a.weighted)) return false;
+  if (!pl.pre_in_smem || !pl.mem_in_smem || p.in_shift == 0xFFFFFFFFu) return false;
+  if ((((uintptr_t)a.y0 | (uintptr_t)y1) & 15) != 0) return false;
+  if (a.drift_kind == 2 && (((uintptr_t)a.mean | (uintptr_t)a.inv_var) & 15) != 0) return false;
+  if (keycols_out && (((uintptr_t)keycols_out & 15) != 0)) return false;
+  FusedGeom g;
+  if (!fused_geometry(p.n_sets, p.cls_pad_log2, a.k, p.in_per_part, p.sel_ext, p.out_per_part, (uint32_t)a.d * 4u, g))
+    return false;
+  if ((uint32_t)g.rank_warps > p.n_segments) g.rank_warps = (int)p.n_segments;
+  fl.warps = g.rank_warps + g.xform_warps;
+  fl.smem = g.smem;
+  fl.grid = (int)min((uint64_t)sm_count(), ((uint64_t)p.n_segments + g.rank_warps - 1) / g.rank_warps);
+  fl.o.y1 = y1;
+  fl.o.keycols_out = keycols_out;
+  fl.o.keycol0 = p.a.keycol0;
+  fl.o.vpr = a.d / 4;
+  fl.o.lpr_shift = 0;
+  while ((1 << fl.o.lpr_shift) < fl.o.vpr) ++fl.o.lpr_shift;
+  fl.o.rank_warps = g.rank_warps;
+  fl.o.row_bytes = (uint32_t)a.d * 4u;
+  fl.o.xform_words = (uint32_t)g.xform_words;
+  fl.o.spin_ns = (uint32_t)env_int("MCCB200_FUSED_SPIN_NS", 200);
+  fl.o.one = 1.0f; fl.o.neg_one = -1.0f; fl.o.neg_zero = -0.0f;
+  return true;
+}
+
+template <int DRIFT, bool D64>
+static void launch_fused_k(const BoxPrkParams& p, const FusedLaunch& fl, cudaStream_t st) {
+  cudaFuncSetAttribute(box_rank_fused_kernel<DRIFT, D64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fl.smem);
+  box_rank_fused_kernel<DRIFT, D64><<<fl.grid, fl.warps * 32, fl.smem, st>>>(p, fl.o);
+}
+
+template <int DRIFT>
+static void launch_fused_d(const BoxPrkParams& p, const FusedLaunch& fl, cudaStream_t st) {
+  if (p.a.d == 64) launch_fused_k<DRIFT, true>(p, fl, st);
+  else launch_fused_k<DRIFT, false>(p, fl, st);
+}
+
 static int launch_rank_gather(BoxPrkParams& p, const PrkPlan& pl, float* y1, cudaStream_t st) {
+  FusedLaunch fl;
+  if (fused_plan(p, pl, y1, p.a.keycols_out, fl)) {
+    phase_mark("box_prk.rank_gather", st);
+    if (p.a.drift_kind == 2) launch_fused_d<2>(p, fl, st);
+    else launch_fused_d<0>(p, fl, st);
+    phase_mark("end", st);
+    count_launches(1);
+    return check_launch("box_prk_rank_gather(fused)");
+  }
   int rc0 = launch_rank(p, pl, st);
   if (rc0) return rc0;
   // gather: the HBM-bound fused expand+select materialises the selected children
@@ -879,7 +1379,7 @@ extern "C" size_t mccb200_box_prk_step_workspace_bytes(uint64_t n, int k, int n_
                                                        uint64_t in_per_part) {
   PrkPlan pl;
   // 0 = unsupported shape.  Sized for out_per_part <= in_per_part.
-  if (!make_prk_plan(pl, n, k, n_dims, bits, in_per_part, in_per_part)) return 0;
+  if (!make_prk_plan(pl, n, k, n_dims, bits, in_per_part, in_per_part, -1)) return 0;
   return pl.total;
 }
 
@@ -962,7 +1462,7 @@ extern "C" size_t mccb200_box_prk_key_start_offset(uint64_t n, int k, int n_dims
   PrkPlan pl;
   if (!make_prk_plan(pl, n, (uint32_t)k, n_dims, bits, in_per_part, out_per_part)) return (size_t)-1;
   if (n_keys) *n_keys = pl.n_keys;
-  return pl.off_table + (size_t)pl.n_segments * pl.n_keys * sizeof(uint32_t);
+  return pl.off_keytot;
 }
 
 extern "C" int mccb200_box_prk_step(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,

@@ -1,6 +1,7 @@
 // Library-level plumbing of the C ABI: version, thread-local error text, device queries.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -50,6 +51,11 @@ void phase_mark(const char* name, cudaStream_t st) {
 
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 int sm_count() {
   static thread_local int cached_dev = -1;

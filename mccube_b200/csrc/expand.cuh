@@ -65,6 +65,19 @@ __device__ __forceinline__ float4 ld_strided4(const float* p) {  // p 16-byte al
   return v;
 }
 
+// Streaming 128-bit row accesses (read once / written once: no L1 allocation).
+__device__ __forceinline__ float4 ld_stream4(const float* p) {  // p 16-byte aligned
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {  // p 16-byte aligned
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // Drift value f_col(y0[i, :]) of parent i (evaluated on PARENTS only, _term.py:58-63).
 __device__ __forceinline__ float drift_value(const ExpandArgs& a, uint64_t i, int col, float y) {
   if (a.drift_kind == 2) return __fmul_rn(__fsub_rn(__ldg(a.mean + col), y), __ldg(a.inv_var + col));

@@ -245,7 +245,7 @@ static int pick_vec(int d, int ld, const void* p0, const void* p1) {
 }
 
 template <int VEC>
-static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
+static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st, int pad_smem = 0) {
   const bool table = a.points != nullptr;
   if (a.sc_peers && a.sc_order == nullptr) {   // pull form: Hadamard, drift kinds 0 / 2
     if (a.drift_kind == 2) expand_kernel<VEC, 2, false, 3><<<grid, EX_THREADS, 0, st>>>(a);
@@ -264,6 +264,11 @@ static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st) {
     return;
   }
 #define MCCB_LAUNCH(D, T) expand_kernel<VEC, D, T><<<grid, EX_THREADS, 0, st>>>(a)
+  if (a.drift_kind == 2 && !table && pad_smem > 0) {   // residency cap (co-scheduling experiments)
+    cudaFuncSetAttribute(expand_kernel<VEC, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem);
+    expand_kernel<VEC, 2, false><<<grid, EX_THREADS, pad_smem, st>>>(a);
+    return;
+  }
   if (a.drift_kind == 2) { if (table) MCCB_LAUNCH(2, true); else MCCB_LAUNCH(2, false); }
   else if (a.drift_kind == 1) { if (table) MCCB_LAUNCH(1, true); else MCCB_LAUNCH(1, false); }
   else { if (table) MCCB_LAUNCH(0, true); else MCCB_LAUNCH(0, false); }
@@ -318,9 +323,11 @@ int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
   a.rows_per_iter = EX_THREADS / a.vpr;
   uint64_t rows_per_cta = (uint64_t)a.rows_per_iter * EX_UNROLL;
   uint64_t want = (a.n_out + rows_per_cta - 1) / rows_per_cta;
-  int grid = (int)min(want, (uint64_t)sm_count() * 8);
+  const int ctas_per_sm = env_int("MCCB200_EXPAND_CTAS", 8);
+  const int pad_smem = env_int("MCCB200_EXPAND_SMEM_PAD", 0);
+  int grid = (int)min(want, (uint64_t)sm_count() * ctas_per_sm);
   phase_mark(a.idx ? "expand_select" : "expand_all", st);
-  if (vec == 4) launch_expand<4>(a, grid, st);
+  if (vec == 4) launch_expand<4>(a, grid, st, pad_smem);
   else if (vec == 2) launch_expand<2>(a, grid, st);
   else launch_expand<1>(a, grid, st);
   phase_mark("end", st);
