@@ -38,29 +38,38 @@ def global_mean(local_sums: torch.Tensor, group=None):
 
 
 def global_cov(local_m2: torch.Tensor, local_sums: torch.Tensor, centre: torch.Tensor, mean: torch.Tensor,
-               wtot: torch.Tensor, ddof: int = 1, group=None):
+               wtot: torch.Tensor, ddof: int = 1, group=None, local_w2=None):
     """local_m2 = sum_r w_r (x_r - centre)(x_r - centre)^T over this rank's shard with a centre
     COMMON to all ranks (fp64).  One all-reduce, then the exact shift to the global mean:
-    sum w (x-m)(x-m)^T = sum w (x-c)(x-c)^T - W (m-c)(m-c)^T."""
+    sum w (x-m)(x-m)^T = sum w (x-c)(x-c)^T - W (m-c)(m-c)^T.
+    Normalisation as numpy / jnp.cov: `wtot - ddof` without weights, `wtot - ddof * sum(w^2) / wtot`
+    with aweights (`local_w2` = this rank's sum of squared weights, reduced in the same all-reduce)."""
     del local_sums
-    m2 = all_reduce_sum_(local_m2.clone(), group)
+    d = local_m2.shape[0]
+    packed = torch.cat([local_m2.reshape(-1), (local_w2 if local_w2 is not None else local_m2.new_zeros(())).reshape(1)])
+    packed = all_reduce_sum_(packed, group)
+    m2 = packed[:-1].reshape(d, d)
     delta = mean - centre.to(mean.dtype)
     m2 = m2 - wtot * torch.outer(delta, delta)
-    return m2 / (wtot - ddof)
+    fact = wtot - ddof if local_w2 is None else wtot - ddof * packed[-1] / wtot
+    return m2 / fact
 
 
 def distributed_mean_and_cov(particles: torch.Tensor, weights=None, ddof: int = 1, group=None):
-    """jnp.mean / jnp.cov of the GLOBAL particle set from per-rank shards: two GPU reductions
-    (mccb200_moments_sum, mccb200_moments_m2) and two tiny all-reduces."""
+    """jnp.mean / jnp.cov(aweights=weights, ddof=ddof) of the GLOBAL particle set from per-rank shards: two GPU
+    reductions (mccb200_moments_sum, mccb200_moments_m2) and two tiny all-reduces."""
     from . import _lib
 
     d = particles.shape[1]
+    if weights is not None:
+        weights = torch.as_tensor(weights, device=particles.device).to(torch.float32)   # the kernels read float32
     mean_local, wtot_local = _lib.column_means(particles.contiguous(), d, weights)
     sums = torch.cat([mean_local * wtot_local, wtot_local.reshape(1)])
     mean, wtot = global_mean(sums, group)
     centre = mean.to(torch.float32).contiguous()
     m2 = _lib.second_moment(particles.contiguous(), d, centre, weights)
-    cov = global_cov(m2, sums, centre, mean, wtot, ddof, group)
+    w2 = None if weights is None else (weights.double() * weights.double()).sum()
+    cov = global_cov(m2, sums, centre, mean, wtot, ddof, group, local_w2=w2)
     return mean, cov
 
 
@@ -476,7 +485,9 @@ class ShardedBoxStep:
                                  pl["out_per_part"], pl["in_per_part"], tables, sel, ws, key_start, idx_slots)
         G, n_loc = self.n_ranks, pl["n_loc"]
         counts = torch.zeros(G * G, dtype=torch.int32, device=dev)
-        slot_list = torch.empty(n_loc + n_loc // 8 + 1024, dtype=torch.int32, device=dev)
+        # hard bound on this shard's hits (every output slot, or every local child): the compaction kernel traps on
+        # overflow, and the per-rank hit counts are correlated (all partitions share one local index vector)
+        slot_list = torch.empty(min(pl["n_tot"], n_loc * pl["k"]), dtype=torch.int32, device=dev)
         _lib.compact_slots(idx_slots, slot_list, counts[rank * G:rank * G + 1])
         _lib.expand_scatter_slots(y_shard, pl["d"], pl["drift"], pl["dt"], pl["cub"], idx_slots, slot_list, counts,
                                   rank, G, n_loc, peer_ptrs)

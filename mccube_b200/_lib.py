@@ -160,6 +160,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("MCCB200_LIB"):          # experiments: a library built with other -D flags
+        LIB_PATH = Path(os.environ["MCCB200_LIB"])
     if not LIB_PATH.exists():
         raise MccubeB200Error(
             f"{LIB_PATH} is missing: build it with `python -m mccube_b200._build` "
@@ -209,9 +212,36 @@ def _ptr(t):
 
 
 def _require_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: the wrappers launch on its current stream and the
+    workspace cache is keyed by it (use `with torch.cuda.device(t.device):` around calls for another GPU)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None or isinstance(t, _DevicePtr):
+            continue
+        if not t.is_cuda:
             raise MccubeB200Error("mccube_b200 kernels need CUDA tensors (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise MccubeB200Error(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                                  "wrap the call in `with torch.cuda.device(tensor.device)`")
+
+
+def _i32c(t, what="index"):
+    """Index / permutation / slot vectors are read as 32-bit words (uint32 bit patterns)."""
+    if t is not None and (t.dtype not in (torch.int32, torch.uint32) or not t.is_contiguous()):
+        raise MccubeB200Error(f"{what}: expected a contiguous int32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+def _f32w(t, n=None):
+    """Optional weight vector: 1-D float32, any stride (the kernels read 4-byte words `stride` apart)."""
+    if t is not None:
+        if t.dtype != torch.float32 or t.dim() != 1:
+            raise MccubeB200Error(f"weights: expected a 1-D float32 tensor, got {t.dtype} with {t.dim()} dims")
+        if n is not None and t.numel() != n:
+            raise MccubeB200Error(f"weights: expected {n} entries, got {t.numel()}")
+    return t
 
 
 def _f32c(t):
@@ -321,6 +351,7 @@ def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=No
     lib = load()
     _require_cuda(y0, idx, perm)
     _f32c(y0)
+    _i32c(idx, "expand_select idx"); _i32c(perm, "expand_select perm")
     n, ld = y0.shape
     n_out = idx.numel() if n_out is None else n_out
     out = torch.empty((n_out, ld), dtype=torch.float32, device=y0.device) if out is None else out
@@ -429,6 +460,7 @@ def gather_rows(p, idx):
     lib = load()
     _require_cuda(p, idx)
     _f32c(p)
+    _i32c(idx, "gather_rows idx")
     out = torch.empty((idx.numel(), p.shape[1]), dtype=torch.float32, device=p.device)
     _check(lib.mccb200_gather_rows(p.data_ptr(), p.shape[1], idx.data_ptr(), idx.numel(), out.data_ptr(), _stream()),
            "gather_rows")
@@ -652,6 +684,7 @@ def column_means(p, d, weights=None):
     _require_cuda(p, weights)
     _f32c(p)
     n, ld = p.shape
+    _f32w(weights, n)
     sums = torch.zeros(d + 1, dtype=torch.float64, device=p.device)
     ws = 1 if weights is None else weights.stride(0)
     _check(lib.mccb200_moments_sum(p.data_ptr(), n, d, ld, _ptr(weights), ws, sums.data_ptr(), _stream()),
@@ -663,8 +696,9 @@ def second_moment(p, d, centre, weights=None):
     """sum_r w_r (p_r - centre)(p_r - centre)^T as float64 [d, d] (accumulated on the GPU)."""
     lib = load()
     _require_cuda(p, weights, centre)
-    _f32c(p)
+    _f32c(p); _f32c(centre)
     n, ld = p.shape
+    _f32w(weights, n)
     w_stride = 1 if weights is None else weights.stride(0)
     m2 = torch.zeros((d, d), dtype=torch.float64, device=p.device)
     _check(lib.mccb200_moments_m2(p.data_ptr(), n, d, ld, _ptr(weights), w_stride, centre.data_ptr(), m2.data_ptr(),
@@ -678,6 +712,7 @@ def moments(p, d, weights=None):
     _require_cuda(p, weights)
     _f32c(p)
     n, ld = p.shape
+    _f32w(weights, n)
     w_stride = 1 if weights is None else weights.stride(0)
     sums = torch.zeros(d + 1, dtype=torch.float64, device=p.device)
     _check(lib.mccb200_moments_sum(p.data_ptr(), n, d, ld, _ptr(weights), w_stride, sums.data_ptr(), _stream()),
@@ -754,6 +789,7 @@ def scatter_rows_(out, rows, slots, slot_offset=0):
     lib = load()
     _require_cuda(out, rows, slots)
     _f32c(rows); _f32c(out)
+    _i32c(slots, "scatter_rows slots")
     _check(lib.mccb200_scatter_rows(rows.data_ptr(), rows.shape[1], slots.data_ptr(), slot_offset, rows.shape[0],
                                     out.data_ptr(), _stream()), "scatter_rows")
     return out

@@ -60,6 +60,8 @@ def mean_and_cov(particles: torch.Tensor, weights=None, ddof: int = 1):
     (/root/reference/README.md:85-86; docs/quickstart.md:98-101 uses ddof=0 and aweights),
     as float64 tensors, from one sum pass and one centred second-moment pass on the GPU."""
     d = particles.shape[1]
+    if weights is not None:
+        weights = torch.as_tensor(weights, device=particles.device).to(torch.float32)   # the kernels read float32
     mean, wtot, m2 = _lib.moments(particles.contiguous(), d, weights)
     if weights is None:
         cov = m2 / (wtot - ddof)

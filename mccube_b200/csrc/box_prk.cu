@@ -635,8 +635,12 @@ box_rank_flat_kernel(const BoxPrkParams p) {
 // shared memory and streams the child rows (and their packed key columns) to their final slots.  The 64 MB
 // index vector and the separate HBM-bound gather pass disappear, a parent row selected twice is fetched from
 // L2 the second time, and the ranking warps' dependent chains fill the issue slots the copy does not need.
-// Ring protocol (shared memory, one ring per ranking warp): the producer publishes `tail` after writing the
-// jobs, the consumer publishes `head` after it has materialised them, `done` closes the ring.
+// Ring protocol (shared memory, one ring of 4 x 32 jobs per ranking warp): the producer publishes `tail` after
+// writing the jobs and `done` when it has finished; the consumer takes the jobs in blocks of 32 and, once a block
+// is materialised, arrives on that quarter's `empty` mbarrier.  A producer entering a quarter for the n-th time
+// waits for the (n-1)-th completion of its barrier with mbarrier.try_wait, which suspends the warp in hardware: a
+// polling loop here (tried first, volatile loads + nanosleep, which returns after ~20 ns whatever it is asked for)
+// took a third of the SM's issue slots from the transform warps.
 constexpr int FZ_MAX_THREADS = 1024;
 constexpr int FZ_JQ = 128;      // row-job ring entries per ranking warp
 constexpr int FZ_STAGES = 2;    // TMA stages per transform warp (32 parent rows each)
@@ -661,6 +665,9 @@ __device__ __forceinline__ void st_vol(uint32_t* p, uint32_t v) { *reinterpret_c
 __device__ __forceinline__ void fz_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void fz_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -682,10 +689,31 @@ __device__ __forceinline__ void fz_mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// L2 residency: the counter table (tens of MB, hit by one atomic per record) must stay in L2 while 8 GB of rows
+// stream through it; without hints the stream evicts the table and every atomic becomes a DRAM round trip.
+__device__ __forceinline__ uint64_t fz_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t fz_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // one row: global -> shared through the TMA engine (addresses and size multiples of 16 bytes)
-__device__ __forceinline__ void fz_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void fz_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fz_st_stream4(float* p, const float4& v, uint64_t pol) {  // p 16-byte aligned
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t fz_atom_add(uint32_t* p, uint32_t v, uint64_t pol) {
+  uint32_t old;
+  asm volatile("atom.global.add.L2::cache_hint.u32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(v), "l"(pol) : "memory");
+  return old;
 }
 
 // Packed fp32 pairs (Blackwell FFMA2).  Every step of the reference's fp32 op order is ONE rounding, written as
@@ -766,12 +794,16 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
   for (uint32_t i = threadIdx.x; i < 2u * p.out_per_part; i += blockDim.x) s_sp[i] = p.sp[i];
   for (uint32_t i = threadIdx.x; i < p.n_sets * a.k; i += blockDim.x) s_mem[i] = p.members[i];
   // ---- per ranking warp: hit-record ring (FQ_CAP x 16 B) | job ring (FZ_JQ x 8 B) | control (4 words)
-  constexpr uint32_t RANK_WORDS = FQ_CAP * 4 + FZ_JQ * 2 + 4;
+  constexpr uint32_t RANK_WORDS = FQ_CAP * 4 + FZ_JQ * 2 + 4 + 8;   // ... | control (4 words) | 4 `empty` mbarriers
   auto rank_block = [&](int w) { return cursor + (size_t)w * RANK_WORDS; };
   // ---- per transform warp: FZ_STAGES x 32 rows | FZ_STAGES mbarriers
   uint32_t* xbase = cursor + (size_t)RW * RANK_WORDS;
   if (warp < RW) {
-    if (lane < 4) rank_block(warp)[FQ_CAP * 4 + FZ_JQ * 2 + lane] = 0u;
+    if (lane < 4) {
+      rank_block(warp)[FQ_CAP * 4 + FZ_JQ * 2 + lane] = 0u;
+      fz_mbar_init(fz_smem_u32(rank_block(warp) + FQ_CAP * 4 + FZ_JQ * 2 + 4 + 2 * lane), 1u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (lane == 0) {
     uint32_t* xb = xbase + (size_t)(warp - RW) * o.xform_words;
     for (int s = 0; s < FZ_STAGES; ++s) fz_mbar_init(fz_smem_u32(xb + FZ_STAGES * 8u * o.row_bytes + 2 * s), 1u);
@@ -804,6 +836,7 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
       cc.nzero2 = f2_pack(o.neg_zero, o.neg_zero);
       cc.cmask = col & a.half_mask; cc.top_shift = (uint32_t)logk - 1u; cc.scale_bits = __float_as_uint(a.scale);
     }
+    const uint64_t pol_stream = fz_policy_evict_first();
     uint32_t fetch[FZ_MAX_RINGS] = {0u, 0u, 0u, 0u};   // jobs handed to the TMA engine, per served ring
     uint32_t st_ring[FZ_STAGES] = {0u, 0u}, st_head[FZ_STAGES] = {0u, 0u}, st_cnt[FZ_STAGES] = {0u, 0u};
     uint32_t phase_bits = 0;                            // parity of each stage's barrier
@@ -835,7 +868,7 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
             if ((uint32_t)lane < cnt) {
               const uint32_t child = jq[(fetch[q] + (uint32_t)lane) & (FZ_JQ - 1)].x;
               fz_bulk_row(buf0 + (uint32_t)next_load * stage_bytes + (uint32_t)lane * o.row_bytes,
-                          a.y0 + (uint64_t)(child >> logk) * ld, o.row_bytes, bar);
+                          a.y0 + (uint64_t)(child >> logk) * ld, o.row_bytes, bar, pol_stream);
             }
             st_ring[next_load] = (uint32_t)r; st_head[next_load] = fetch[q]; st_cnt[next_load] = cnt;
             fetch[q] += cnt;
@@ -864,12 +897,18 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
             const uint2 job = jq[(head + t) & (FZ_JQ - 1)];
             const float4 y = *reinterpret_cast<const float4*>(buf + t * o.row_bytes + col * 4u);
             const float4 out = fz_child4<DRIFT>(cc, y, job.x & (a.k - 1u), a.half_mask);
-            st_stream4(o.y1 + ((uint64_t)job.y * ld + col), out);
-            if (o.keycols_out != nullptr && (int)col == o.keycol0) st_stream4(o.keycols_out + (uint64_t)job.y * 4u, out);
+#if defined(FZ_EXP) && FZ_EXP == 1   /* timing experiment: compute, no stores */
+            if (out.x == 123.456f) st_stream4(o.y1, out);
+#elif defined(FZ_EXP) && FZ_EXP == 3 /* timing experiment: stores into a 16 MB window (L2 resident) */
+            st_stream4(o.y1 + ((uint64_t)(job.y & 0xFFFFu) * ld + col), out);
+#else
+            fz_st_stream4(o.y1 + ((uint64_t)job.y * ld + col), out, pol_stream);
+            if (o.keycols_out != nullptr && (int)col == o.keycol0) fz_st_stream4(o.keycols_out + (uint64_t)job.y * 4u, out, pol_stream);
+#endif
           }
         }
         __syncwarp();                                       // all reads of the stage are done before it is refilled
-        if (lane == 0) st_vol(rb + FQ_CAP * 4 + FZ_JQ * 2 + 1, head + cnt);   // frees the ring slots
+        if (lane == 0) fz_mbar_arrive(fz_smem_u32(rb + FQ_CAP * 4 + FZ_JQ * 2 + 4 + 2 * ((head >> 5) & 3u)));   // frees the quarter
         next_use ^= 1;
         --in_flight;
         continue;
@@ -895,19 +934,17 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
   const uint32_t ushift = (uint32_t)logk - p.cls_pad_log2;   // log2(unit)
   uint32_t q_head = 0, q_count = 0;                          // hit-record ring (warp-uniform)
   uint32_t j_tail = 0;                                       // jobs published so far (warp-uniform)
+  const uint64_t pol_keep = fz_policy_evict_last();
 
-  auto wait_space = [&](uint32_t cnt) {                      // until the transform warp has freed cnt ring slots
-    if (lane == 0) {
-      long long t0 = 0;
-      for (uint32_t spin = 0; j_tail + cnt - ld_vol(ctrl + 1) > (uint32_t)FZ_JQ; ++spin) {
-        __nanosleep(o.spin_ns);
-        if ((spin & 4095u) == 4095u) {                        // a protocol bug must trap, not hang the GPU
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > 8000000000ll) __trap();
-        }
-      }
+  const uint32_t empty0 = fz_smem_u32(ctrl + 4);
+  uint32_t ready_block = 3;                                  // highest 32-job block of the ring known to be free
+  auto wait_space = [&](uint32_t cnt) {                      // until the quarters of jobs [j_tail, j_tail + cnt) are free
+    if (cnt == 0u) return;
+    const uint32_t last = (j_tail + cnt - 1u) >> 5;
+    while (ready_block < last) {
+      ++ready_block;                                         // block b re-uses the quarter of block b - 4
+      fz_mbar_wait(empty0 + 8u * (ready_block & 3u), ((ready_block >> 2) - 1u) & 1u);
     }
-    __syncwarp();
   };
   auto publish = [&](uint32_t cnt) {
     j_tail += cnt;
@@ -967,7 +1004,7 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
       peer_units(peers, rec.e, p.cls_pad_log2, lt_mask, exu, totu);
       fr.leader = __ffs(peers) - 1;
       fr.st = 0;
-      if (rec.valid && lane == fr.leader) fr.st = atomicAdd(row + rec.key, totu << ushift);
+      if (rec.valid && lane == fr.leader) fr.st = fz_atom_add(row + rec.key, totu << ushift, pol_keep);
       fr.valid = rec.valid; fr.key = rec.key; fr.exu = exu; fr.e = rec.e;
       fr.child0 = ((uint32_t)base + (uint32_t)(rec.owner & 31)) << logk;   // child ids are uint32 (n * k <= 2^32)
       fr.moff = (rec.S << logk) + (rec.ent >> 22);
@@ -992,8 +1029,10 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
         if (q_count >= 32u) drain(32u);
       }
     };
-    FlatRound cur, nxt;
-    bool have_cur = false;
+    // The atomic of a round is consumed TWO rounds later (box_rank_flat_kernel waits one): this kernel's own
+    // gather keeps HBM busy, which stretches the L2 round trip the ranking chain waits for.
+    FlatRound old, cur, nxt;
+    int pending = 0;
     uint32_t ndesc = i0 + lane < i1 ? __ldcs(p.pdesc + i0 + lane) : 0u;
     for (uint64_t base = i0; base < i1; base += 32) {
       const uint32_t desc = ndesc;
@@ -1003,12 +1042,14 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
       for (uint32_t r0 = 0; r0 < b.R; r0 += 32) {
         __syncwarp();   // order this round's atomics after the previous round's (same-key runs)
         front(b, base, r0, nxt);
-        if (have_cur) back(cur);
+        if (pending == 2) { back(old); --pending; }
+        old = cur;
         cur = nxt;
-        have_cur = true;
+        ++pending;
       }
     }
-    if (have_cur) back(cur);
+    if (pending == 2) back(old);
+    if (pending >= 1) back(cur);
     if (q_count) drain(q_count);
   }
   __syncwarp();
@@ -1077,7 +1118,7 @@ static bool fused_geometry(uint32_t n_sets, uint32_t cls_pad_log2, uint32_t k, u
   words += (((size_t)in_per_part + sel_ext + 4) & ~(size_t)3) / 2;
   words += ((size_t)n_sets * k + 1) / 2;
   words = (words + 3) & ~(size_t)3;
-  const size_t rank_words = (size_t)FQ_CAP * 4 + (size_t)FZ_JQ * 2 + 4;
+  const size_t rank_words = (size_t)FQ_CAP * 4 + (size_t)FZ_JQ * 2 + 4 + 8;
   g.xform_words = (size_t)FZ_STAGES * 8 * row_bytes + 2 * FZ_STAGES + 2;   // stages (32 rows each) + mbarriers
   g.xform_words = (g.xform_words + 3) & ~(size_t)3;
   const size_t cap = (size_t)max_optin_smem();

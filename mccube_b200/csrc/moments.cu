@@ -354,11 +354,8 @@ extern "C" int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, con
   rows_per_cta = (rows_per_cta + M2_ROWS - 1) / M2_ROWS * M2_ROWS;
   dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)pairs);
   const size_t smem = m2_smem_bytes(tiles > 1, w != nullptr);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m2_smem_bytes(true, true));
-    attr_set = true;
-  }
+  // (a per-DEVICE attribute: set on every call)
+  cudaFuncSetAttribute(moments_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m2_smem_bytes(true, true));
   moments_m2_kernel<<<grid, M2_THREADS, smem, (cudaStream_t)stream>>>(p, n, d, ld, w, w_stride, centre, rows_per_cta, m2_out);
   count_launches(1);
   return check_launch("moments_m2");

@@ -339,12 +339,9 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
   if (count == 0) return MCCB200_OK;
   if (!replace && p.rounds > 0 && n_inputs <= (uint64_t)SMALL_SHUFFLE_MAX) {
     const size_t smem = small_shuffle_smem((uint32_t)n_inputs);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(small_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)small_shuffle_smem(SMALL_SHUFFLE_MAX));
-      attr_set = true;
-    }
+    // (a per-DEVICE attribute: set on every call, a process-wide flag would leave other devices at 48 KB)
+    cudaFuncSetAttribute(small_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)small_shuffle_smem(SMALL_SHUFFLE_MAX));
     phase_mark("mc_indices", st);
     small_shuffle_kernel<<<1, SS_THREADS, smem, st>>>(*rng, p.rounds, (uint32_t)n_inputs, (uint32_t)count, idx_out);
     phase_mark("end", st);

@@ -33,12 +33,25 @@ def _worker(rank, world, port, n, d, out):
         centre = mean.to(torch.float32)
         c64 = centre.double().numpy()
         m2 = torch.tensor(((xs - c64) * ws[:, None]).T @ (xs - c64))
-        cov = global_cov(m2, sums, centre, mean, wtot, ddof=0)
+        w2 = torch.tensor((ws * ws).sum())
+        cov = global_cov(m2, sums, centre, mean, wtot, ddof=0, local_w2=w2)
+        cov1 = global_cov(m2, sums, centre, mean, wtot, ddof=1, local_w2=w2)     # weighted, ddof = 1 (jnp.cov default)
+        # normalised weights (what pack_particles produces): sum(w) = 1, so `wtot - ddof` would divide by zero
+        wn = w / w.sum()
+        wsn = wn[lo:hi]
+        sums_n = torch.tensor(np.concatenate([(wsn[:, None] * xs).sum(0), [wsn.sum()]]))
+        mean_n, wtot_n = global_mean(sums_n)
+        m2n = torch.tensor(((xs - c64) * wsn[:, None]).T @ (xs - c64))
+        cov1n = global_cov(m2n, sums_n, centre, mean_n, wtot_n, ddof=1, local_w2=torch.tensor((wsn * wsn).sum()))
         if rank == 0:
             out["mean"] = mean.numpy()
             out["cov"] = cov.numpy()
+            out["cov1"] = cov1.numpy()
+            out["cov1n"] = cov1n.numpy()
             out["want_mean"] = np.average(x, axis=0, weights=w)
             out["want_cov"] = np.cov(x, rowvar=False, ddof=0, aweights=w)
+            out["want_cov1"] = np.cov(x, rowvar=False, ddof=1, aweights=w)
+            out["want_cov1n"] = np.cov(x, rowvar=False, ddof=1, aweights=wn)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -60,6 +73,8 @@ def test_global_moments_two_ranks_gloo():
         mp.spawn(_worker, args=(world, _free_port(), n, d, out), nprocs=world, join=True)
         np.testing.assert_allclose(out["mean"], out["want_mean"], rtol=1e-12)
         np.testing.assert_allclose(out["cov"], out["want_cov"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out["cov1"], out["want_cov1"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out["cov1n"], out["want_cov1n"], rtol=1e-9, atol=1e-12)
 
 
 def test_plan_blocks_matches_bruteforce():
