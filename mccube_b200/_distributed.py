@@ -344,6 +344,89 @@ class ShardedMonteCarloStep:
         return y1, slot_map
 
 
+    # ---- id exchange + owner-computes: O(n_loc) memory per rank, 64-bit child ids, no row leaves its owner
+    def owner_ids_bucket(self, t0, y_shard: torch.Tensor, rank: int):
+        """Phase 1 (local): this rank draws ONLY the index slice of the output slots [rank * n_loc, (rank+1) * n_loc)
+        (`with_replacement=True`: the draws are counter based) and groups the (slot, LOCAL child id) pairs by the
+        rank that owns the selected parent, stably (ascending slot inside a group).
+        Returns (pairs [n_loc, 2] int32 grouped by owner, per-owner counts as a device tensor [G])."""
+        import math
+
+        from . import _lib
+
+        kernel = self.solver.recombination_kernel
+        if not kernel.with_replacement:
+            raise ValueError("step_owner_ids needs with_replacement=True (the shuffle is not sliceable)")
+        n_loc, _ = y_shard.shape
+        G = self.n_ranks
+        n_tot = n_loc * G
+        k = self.terms.cde.control.gaussian_cubature.point_count
+        if n_loc * k > 2 ** 32:
+            raise ValueError("step_owner_ids: a shard's children need 32-bit local ids (n_loc * k <= 2^32)")
+        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, y_shard.device)
+        return _lib.shard_bucket_ids(idx, rank * n_loc, n_loc, k, G)
+
+    def owner_ids_materialise(self, t0, t1, y_shard: torch.Tensor, rank: int, recv_pairs: torch.Tensor, counts):
+        """Phase 2 (local, after the id exchange): `recv_pairs` = the (slot, local child id) pairs of every output
+        slot whose selected parent lives on this rank, in sender order; `counts[src][owner]` = the replicated
+        matrix of pair counts.  Materialises the first n_loc of them into this rank's next shard and the surplus
+        into a send buffer for the ranks with a deficit (`plan_rebalance`, O(sqrt(n_loc)) rows).
+        Returns (y1 [n_loc, d] with rows [:keep] filled, slots [keep], send_rows, send_slots, send_splits,
+        recv_splits, keep)."""
+        import numpy as np
+
+        from . import _lib
+
+        solver = self.solver
+        n_loc, d = y_shard.shape
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        counts = np.asarray(counts, dtype=np.int64)
+        per_owner = counts.sum(axis=0)                       # rows every rank materialises
+        transfers = plan_rebalance(per_owner, n_loc)
+        total = int(per_owner[rank])
+        assert recv_pairs.shape[0] == total
+        keep = min(total, n_loc)
+        slots = recv_pairs[:, 0].contiguous()
+        ids = recv_pairs[:, 1].contiguous()
+        y1 = torch.empty((n_loc, d), dtype=torch.float32, device=y_shard.device)
+        if keep:
+            _lib.expand_select(y_shard, d, False, drift, dt, cub, ids[:keep], n_out=keep, out=y1[:keep])
+        n_give = total - keep
+        send_rows = (_lib.expand_select(y_shard, d, False, drift, dt, cub, ids[keep:].contiguous(), n_out=n_give)
+                     if n_give else y1.new_empty((0, d)))
+        return (y1, slots[:keep], send_rows, slots[keep:].contiguous(), [int(c) for c in transfers[rank]],
+                [int(c) for c in transfers[:, rank]], keep)
+
+    def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None):
+        """One step with a GLOBAL `MonteCarloKernel(with_replacement=True)` resample in which no parent row and
+        (up to the binomial imbalance) no child row crosses the link: ranks exchange 8 bytes per output row --
+        (slot, child id) -- and every rank materialises the selected children of its OWN parents with the local
+        fused gather.  Works with 64-bit global child ids (`kernel.x64`, BASELINE config 5: 2^34 children) in
+        O(n_loc) memory per rank.  Returns (y1_shard, slot_map): y1_shard[q] is row slot_map[q] of the
+        single-device step on the concatenated state (same multiset, known permutation)."""
+        G = self.n_ranks
+        pairs, counts_dev = self.owner_ids_bucket(t0, y_shard.contiguous(), rank)
+        if G == 1:
+            counts = counts_dev.cpu().numpy().reshape(1, 1)
+            recv_pairs = pairs
+        else:
+            allc = [torch.empty_like(counts_dev) for _ in range(G)]
+            dist.all_gather(allc, counts_dev, group=group)
+            counts = torch.stack(allc).cpu().numpy()          # counts[src][owner]: the step's one host synchronisation
+            recv_pairs = exchange_rows(pairs, [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]], group)
+        y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
+            t0, t1, y_shard, rank, recv_pairs, counts)
+        slot_map = torch.empty(y_shard.shape[0], dtype=torch.int32, device=y_shard.device)
+        slot_map[:keep] = slots
+        if G > 1 and (sum(send_splits) or sum(recv_splits)):
+            rows = exchange_rows(send_rows, send_splits, recv_splits, group)
+            got = exchange_rows(send_slots.reshape(-1, 1), send_splits, recv_splits, group).reshape(-1)
+            if rows.shape[0]:
+                y1[keep:keep + rows.shape[0]] = rows
+                slot_map[keep:keep + rows.shape[0]] = got
+        return y1, slot_map
+
+
 class ShardedBoxStep:
     """One MCCSolver step with `PartitioningRecombinationKernel(BoxPartitionKernel, MonteCarloKernel)` over
     row-sharded particles and ONE GLOBAL partition: what the reference computes on the concatenated state

@@ -737,6 +737,74 @@ def test_sharded_pull_gather_emulated_ranks(dev):
         mccube.MonteCarloKernel(n_tot, False, key=42).indices_slice(t0, n_tot * k, n_tot, 0, n_loc, dev)
 
 
+@pytest.mark.parametrize("G,n_loc,d,x64", [(4, 250, 12, False), (3, 333, 8, True), (8, 64, 64, True), (1, 100, 4, False)])
+def test_sharded_owner_ids_emulated_ranks(dev, G, n_loc, d, x64):
+    """Id exchange + owner-computes (`step_owner_ids`): every rank draws only its own index slice, the ranks
+    exchange (slot, child id) pairs and each materialises the children of its OWN parents.  Ranks emulated on one
+    GPU, the two all-to-alls done by hand: row q of rank r's shard equals row slot_map[q] of the single-device
+    step on the concatenated state, every output slot appears exactly once, and every shard has n_loc rows."""
+    from mccube_b200._distributed import ShardedMonteCarloStep
+
+    n_tot = G * n_loc
+    y, mean, inv_var = _setup(n_tot, d, seed=41)
+    terms = _terms(d, mean, inv_var, dev)
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    yt = cuda(y, dev)
+
+    def make():
+        kern = mccube.MonteCarloKernel(n_tot, True, key=42)
+        kern.x64 = x64
+        return mccube.MCCSolver(dfx.Euler(), kern)
+
+    want, *_ = make().step(terms, t0, t1, yt, None, None, False) if not x64 else (None,)
+    if x64:   # the single-device step draws 32-bit ids; build the x64 reference from the x64 index vector
+        solver = make()
+        drift, cub, dt, k, _ = solver._describe(terms, yt, *solver.substep_times(t0, t1)[0], None)
+        idx = solver.recombination_kernel.indices_slice(t0, n_tot * k, n_tot, 0, n_tot, dev)
+        ptrs = torch.tensor([yt.data_ptr()], dtype=torch.int64, device=dev)
+        want = _lib.expand_gather_peers(ptrs, 1, n_tot, d, drift, dt, cub, idx, torch.empty_like(yt))
+    sh = ShardedMonteCarloStep(make(), terms, G)
+    shards = [yt[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
+    bucketed = [sh.owner_ids_bucket(t0, shards[r], r) for r in range(G)]
+    counts = torch.stack([c for _, c in bucketed]).cpu().numpy()           # counts[src][owner]
+    assert counts.sum() == n_tot and (counts.sum(1) == n_loc).all()
+    mats = []
+    for r in range(G):
+        parts = []
+        for src in range(G):
+            off = int(counts[src, :r].sum())
+            parts.append(bucketed[src][0][off:off + int(counts[src, r])])
+        mats.append(sh.owner_ids_materialise(t0, t1, shards[r], r, torch.cat(parts), counts))
+    outs, maps = [], []
+    for r in range(G):
+        y1, slots, _, _, _, recv_splits, keep = mats[r]
+        slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        slot_map[:keep] = slots
+        at = keep
+        for src in range(G):
+            c = recv_splits[src]
+            if c:
+                _, _, send_rows, send_slots, send_splits, _, _ = mats[src]
+                off = sum(send_splits[:r])
+                y1[at:at + c] = send_rows[off:off + c]
+                slot_map[at:at + c] = send_slots[off:off + c]
+                at += c
+        assert at == n_loc
+        outs.append(y1)
+        maps.append(slot_map)
+    all_slots = torch.cat(maps).to(torch.int64)
+    assert torch.equal(torch.sort(all_slots).values, torch.arange(n_tot, device=dev))
+    assert torch.equal(torch.cat(outs), want[all_slots])
+    # grouping is stable: ascending slots inside every owner group of the send buffer
+    for r in range(G):
+        pairs = bucketed[r][0].to(torch.int64)
+        start = 0
+        for o in range(G):
+            grp = pairs[start:start + int(counts[r, o])]
+            start += int(counts[r, o])
+            assert bool((grp[1:, 0] > grp[:-1, 0]).all())
+
+
 @pytest.mark.parametrize("partitionable", [False, True])
 def test_sharded_pull_x64_indices(dev, partitionable):
     """jax_enable_x64 semantics of the index draw (int64 randint, 64-bit draws) for the pull path: slices vs the
