@@ -383,6 +383,77 @@ def extra_workloads(dev, peak_gbs):
     return out
 
 
+def sharded_parity(dev, rank, world):
+    """N > 1: every sharded form of the global resample (and the global Box + PRK partition) against the
+    single-device step on the concatenated state, on real NCCL / NVLink, at a small size (every rank holds the
+    whole reference result).  Returns {variant: bool} after a MIN over ranks; the caller fails the run on a False."""
+    import torch
+    import torch.distributed as dist
+
+    import mccube_b200 as mccube
+    from mccube_b200 import _lib
+    from mccube_b200 import diffrax_compat as dfx
+    from mccube_b200._distributed import PeerShards, ShardedBoxStep, ShardedMonteCarloStep
+
+    d, n_loc = 16, 4096
+    n_tot = n_loc * world
+    terms = mccube.MCCTerm(
+        dfx.ODETerm(mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev)),
+        dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                      mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4242)                                   # the SAME full state on every rank
+    y_full = torch.randn((n_tot, d), generator=gen, device=dev) * 1.5 + 1.0
+    mine = y_full[rank * n_loc:(rank + 1) * n_loc].contiguous()
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    lo, hi = rank * n_loc, (rank + 1) * n_loc
+    ok = {}
+
+    def mc_solver(replace, x64=False):
+        return mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n_tot, replace, key=42, x64=x64))
+
+    want_r, *_ = mc_solver(True).step(terms, t0, t1, y_full, None, None, False)      # with replacement
+    want_n, *_ = mc_solver(False).step(terms, t0, t1, y_full, None, None, False)     # the reference's default
+    shards = PeerShards(n_loc, d, rank, world, dev)
+    try:
+        sh_r = ShardedMonteCarloStep(mc_solver(True), terms, world)
+        sh_n = ShardedMonteCarloStep(mc_solver(False), terms, world)
+        shards.load(mine)
+        ok["pull"] = bool(torch.equal(sh_r.step_pull(t0, t1, rank, shards), want_r[lo:hi]))
+        ok["p2p"] = bool(torch.equal(sh_n.step_p2p(t0, t1, mine, rank, shards), want_n[lo:hi]))
+        ok["a2a"] = bool(torch.equal(sh_n.step(t0, t1, mine, rank), want_n[lo:hi]))
+        y1, smap = sh_n.step_owner(t0, t1, mine, rank)
+        ok["owner"] = bool(torch.equal(y1, want_n[smap.to(torch.int64)]))
+        y1, smap = sh_r.step_owner_ids(t0, t1, mine, rank)
+        ok["owner_ids"] = bool(torch.equal(y1, want_r[smap.to(torch.int64)]))
+        # the slot maps of all ranks together are a permutation of the output slots
+        allmaps = [torch.empty_like(smap) for _ in range(world)]
+        dist.all_gather(allmaps, smap)
+        ok["owner_ids_permutation"] = bool(torch.equal(torch.sort(torch.cat(allmaps).to(torch.int64)).values,
+                                                       torch.arange(n_tot, device=dev)))
+        # 64-bit child ids (jax_enable_x64 index semantics: config 5): pull vs id exchange, same multiset
+        sh_x = ShardedMonteCarloStep(mc_solver(True, x64=True), terms, world)
+        shards.load(mine)
+        pull_x = sh_x.step_pull(t0, t1, rank, shards).clone()
+        full_x = [torch.empty_like(pull_x) for _ in range(world)]
+        dist.all_gather(full_x, pull_x)
+        y1, smap = sh_x.step_owner_ids(t0, t1, mine, rank)
+        ok["owner_ids_x64"] = bool(torch.equal(y1, torch.cat(full_x)[smap.to(torch.int64)]))
+        # global Box + PRK partition over the shards
+        per = 16
+        box = mccube.MCCSolver(dfx.Euler(), mccube.PartitioningRecombinationKernel(
+            mccube.BoxPartitionKernel(n_tot // per, dims=(0, 1, 2, 3), bits=2), mccube.MonteCarloKernel(per, key=11)))
+        want_b, *_ = box.step(terms, t0, t1, y_full, None, None, False)
+        shards.load(mine)
+        ok["box"] = bool(torch.equal(ShardedBoxStep(box, terms, world).step(t0, t1, rank, shards), want_b[lo:hi]))
+    finally:
+        shards.close()
+    flags = torch.tensor([1.0 if ok.get(k_, False) else 0.0 for k_ in sorted(ok)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    _lib.release_workspace()
+    return {k_: bool(v > 0) for k_, v in zip(sorted(ok), flags.tolist())}
+
+
 def sharded_global_mc(dev, rank, world, steps=5):
     """N > 1 only: the global MonteCarloKernel(with_replacement=True) resample over all ranks' particles
     (SURVEY.md 8e): `step` = one variable-size NCCL all-to-all, shards bit-identical to the single-device
@@ -407,7 +478,7 @@ def sharded_global_mc(dev, rank, world, steps=5):
     gen = torch.Generator(device=dev)
     out = {"n_per_gpu": n_loc, "d": d, "n_gpus": world}
     shards = PeerShards(n_loc, d, rank, world, dev)
-    for name in ("step_pull", "step_p2p", "step", "step_owner"):
+    for name in ("step_pull", "step_p2p", "step", "step_owner", "step_owner_ids"):
         gen.manual_seed(11 + rank)
         ys = torch.randn((n_loc, d), generator=gen, device=dev)
         if name == "step_pull":
@@ -495,6 +566,58 @@ def sharded_global_mc(dev, rank, world, steps=5):
         shards5.close()
     except Exception as e:  # noqa: BLE001
         out["config5_n2^27_d64_step_pull"] = {"error": repr(e)}
+    # BASELINE config 5 through the id exchange: ranks exchange 8 bytes per output row and every rank materialises
+    # the children of its own parents (no parent or child row crosses the link but the binomial imbalance)
+    try:
+        n5 = 1 << 27
+        n_loc5 = n5 // world
+        sh5 = ShardedMonteCarloStep(mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n5, True, key=42, x64=True)),
+                                    terms, world)
+        gen.manual_seed(17 + rank)
+        y5 = torch.randn((n_loc5, d), generator=gen, device=dev)
+        for i in range(2):
+            y5, _ = sh5.step_owner_ids(times[i][0], times[i][1], y5, rank)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(2, 2 + steps):
+            y5, smap5 = sh5.step_owner_ids(times[i][0], times[i][1], y5, rank)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        fin = torch.tensor([float(torch.isfinite(y5).all())], device=dev)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        # every output slot of the last step is held by exactly one rank: sum and sum of squares of the slot maps
+        chk = torch.stack([smap5.to(torch.float64).sum(), (smap5.to(torch.float64) ** 2).sum()])
+        dist.all_reduce(chk)
+        want_chk = [n5 * (n5 - 1) / 2.0, (n5 - 1) * n5 * (2 * n5 - 1) / 6.0]
+        out["config5_n2^27_d64_step_owner_ids"] = {
+            "n_per_gpu": n_loc5, "ms_per_step": float(ms) / steps, "particle_steps_per_sec": n5 * steps / (float(ms) * 1e-3),
+            "algorithmic_gbs_per_gpu": 2.0 * n_loc5 * d * 4 / (float(ms) / steps * 1e-3) / 1e9, "finite": bool(fin.item()),
+            "slot_map_is_a_permutation": bool(abs(chk[0].item() - want_chk[0]) <= 1e-9 * want_chk[0]
+                                              and abs(chk[1].item() - want_chk[1]) <= 1e-9 * want_chk[1]),
+            "id_exchange_bytes_per_rank_per_step": int(n_loc5 * 8 * (world - 1) / world),
+            "note": "2^34 implicit children, int64 index draw; (slot, child id) pairs exchanged, rows stay with their parents"}
+        del y5, smap5
+        torch.cuda.empty_cache()
+        # the same step on ONE GPU's worth of particles (n = 2^24, 32-bit ids), every rank on its own: the 1-GPU figure
+        # the efficiency below is quoted against
+        n1 = 1 << 24
+        if n_loc5 <= n1:
+            solver1 = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n1, True, key=42))
+            gen.manual_seed(19 + rank)
+            ms1, _ = time_steps(solver1, terms, torch.randn((n1, d), generator=gen, device=dev), times, steps)
+            t1g = torch.tensor([ms1], device=dev)
+            dist.all_reduce(t1g, op=dist.ReduceOp.MAX)
+            one_gpu = n1 / (float(t1g) * 1e-3)
+            best = max(v["particle_steps_per_sec"] for k_, v in out.items()
+                       if k_.startswith("config5_") and isinstance(v, dict) and "particle_steps_per_sec" in v)
+            out["config5"] = {"one_gpu_n2^24_particle_steps_per_sec": one_gpu, "one_gpu_ms_per_step": float(t1g),
+                              "best_particle_steps_per_sec": best, "speedup_vs_1gpu": best / one_gpu,
+                              "efficiency_vs_1gpu": best / one_gpu / world}
+    except Exception as e:  # noqa: BLE001
+        out["config5_n2^27_d64_step_owner_ids"] = {"error": repr(e)}
     out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
     out["note"] = ("step_pull: every rank draws only its own slice of the (counter-based) index vector and the gather "
                    "kernel reads the selected parents from the owners' shards over NVLink peer memory: O(n_loc) work per "
@@ -502,7 +625,9 @@ def sharded_global_mc(dev, rank, world, steps=5):
                    "step_p2p: fused expand + scatter into the destination rank's shard over NVLink peer memory (no "
                    "collective in the data path, no host sync), shards bit-identical to the single-device step; "
                    "step: the same through a send buffer + NCCL all-to-all; "
-                   "step_owner: owner-computes, only the imbalance is exchanged (row order differs by the exported slot map)")
+                   "step_owner: owner-computes, only the imbalance is exchanged (row order differs by the exported slot map); "
+                   "step_owner_ids: the same placement from an exchange of (slot, child id) pairs: every rank draws only "
+                   "its own index slice, O(n_loc) memory, 64-bit ids")
     return out
 
 
@@ -688,6 +813,12 @@ def main():
                "one_call_at_a_time": {"ms_per_step": ms_serial, "value": world * n / (ms_serial * 1e-3), "steps": Ks}}
         del host_in, host_out, host_out2, yd2, y1
 
+    parity = None
+    if world > 1:
+        try:
+            parity = sharded_parity(dev, rank, world)
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": repr(e)}
     sharded = None
     if world > 1 and not a.no_extras:
         del y
@@ -769,9 +900,16 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "extras": extras,
     }
+    if parity is not None:
+        line["sharded_parity"] = parity
+    if isinstance(sharded, dict) and isinstance(sharded.get("config5"), dict):
+        line["config5"] = sharded["config5"]           # tracked round over round: config 5 vs one GPU
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (all(v is True for v in parity.values()) and "error" not in parity):
+        sys.stderr.write(f"sharded parity FAILED: {parity}\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

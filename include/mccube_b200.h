@@ -349,13 +349,13 @@ MCCB200_API int mccb200_expand_scatter_slots(const float* y0, uint64_t n_loc, in
 /* Id exchange of the sharded global resample with replacement (SURVEY.md 8e "owner-computes"; the semantics are
  * jr.choice(..., replace=True) of /root/reference/mccube/_kernels/random.py:49-68 on the concatenated state): `idx` is
  * THIS rank's slice of the global index vector (child ids, uint32, or uint64 when idx_is_64), entry q belonging to
- * output slot first_slot + q.  pairs_out[n][2] = (slot, child id relative to the owner's first parent), grouped by
- * owner rank = child / (n_loc * k) and ascending in slot inside a group -- the send buffer of the exchange;
- * counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32 and slots < 2^32. */
+ * output slot first_slot + q.  slots_out[n] / ids_out[n] = (slot, child id relative to the owner's first parent),
+ * grouped by owner rank = child / (n_loc * k) and ascending in slot inside a group -- the send buffers of the
+ * exchange; counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32 and slots < 2^32. */
 MCCB200_API size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks);
 MCCB200_API int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
-                                         int k, int n_ranks, uint32_t* pairs_out, uint32_t* counts_out, void* workspace,
-                                         size_t workspace_bytes, void* stream);
+                                         int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
+                                         void* workspace, size_t workspace_bytes, void* stream);
 MCCB200_API int mccb200_compact_slots(const uint32_t* idx_slots, uint64_t n_slots, uint32_t* list, uint64_t capacity,
                                       uint32_t* cursor, void* stream);
 

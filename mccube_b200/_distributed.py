@@ -345,30 +345,30 @@ class ShardedMonteCarloStep:
 
 
     # ---- id exchange + owner-computes: O(n_loc) memory per rank, 64-bit child ids, no row leaves its owner
-    def owner_ids_bucket(self, t0, y_shard: torch.Tensor, rank: int):
+    def owner_ids_bucket(self, t0, n_loc: int, rank: int, device):
         """Phase 1 (local): this rank draws ONLY the index slice of the output slots [rank * n_loc, (rank+1) * n_loc)
-        (`with_replacement=True`: the draws are counter based) and groups the (slot, LOCAL child id) pairs by the
-        rank that owns the selected parent, stably (ascending slot inside a group).
-        Returns (pairs [n_loc, 2] int32 grouped by owner, per-owner counts as a device tensor [G])."""
-        import math
-
+        (`with_replacement=True`: the draws are counter based) and groups (slot, LOCAL child id) by the rank that owns
+        the selected parent, stably (ascending slot inside a group).  Depends on (key, t0) only, not on the state.
+        Returns (slots [n_loc] int32, ids [n_loc] int32, per-owner counts as a device tensor [G])."""
         from . import _lib
 
         kernel = self.solver.recombination_kernel
         if not kernel.with_replacement:
             raise ValueError("step_owner_ids needs with_replacement=True (the shuffle is not sliceable)")
-        n_loc, _ = y_shard.shape
         G = self.n_ranks
         n_tot = n_loc * G
+        if kernel.recombination_count != n_tot:
+            raise ValueError(f"MonteCarloKernel.recombination_count must be the GLOBAL particle count {n_tot}")
         k = self.terms.cde.control.gaussian_cubature.point_count
         if n_loc * k > 2 ** 32:
             raise ValueError("step_owner_ids: a shard's children need 32-bit local ids (n_loc * k <= 2^32)")
-        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, y_shard.device)
+        idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, device)
         return _lib.shard_bucket_ids(idx, rank * n_loc, n_loc, k, G)
 
-    def owner_ids_materialise(self, t0, t1, y_shard: torch.Tensor, rank: int, recv_pairs: torch.Tensor, counts):
-        """Phase 2 (local, after the id exchange): `recv_pairs` = the (slot, local child id) pairs of every output
-        slot whose selected parent lives on this rank, in sender order; `counts[src][owner]` = the replicated
+    def owner_ids_materialise(self, t0, t1, y_shard: torch.Tensor, rank: int, recv_slots: torch.Tensor,
+                              recv_ids: torch.Tensor, counts):
+        """Phase 2 (local, after the id exchange): `recv_slots` / `recv_ids` = output slot and local child id of every
+        output row whose selected parent lives on this rank, in sender order; `counts[src][owner]` = the replicated
         matrix of pair counts.  Materialises the first n_loc of them into this rank's next shard and the surplus
         into a send buffer for the ranks with a deficit (`plan_rebalance`, O(sqrt(n_loc)) rows).
         Returns (y1 [n_loc, d] with rows [:keep] filled, slots [keep], send_rows, send_slots, send_splits,
@@ -384,46 +384,73 @@ class ShardedMonteCarloStep:
         per_owner = counts.sum(axis=0)                       # rows every rank materialises
         transfers = plan_rebalance(per_owner, n_loc)
         total = int(per_owner[rank])
-        assert recv_pairs.shape[0] == total
+        assert recv_ids.shape[0] == total and recv_slots.shape[0] == total
         keep = min(total, n_loc)
-        slots = recv_pairs[:, 0].contiguous()
-        ids = recv_pairs[:, 1].contiguous()
         y1 = torch.empty((n_loc, d), dtype=torch.float32, device=y_shard.device)
         if keep:
-            _lib.expand_select(y_shard, d, False, drift, dt, cub, ids[:keep], n_out=keep, out=y1[:keep])
+            _lib.expand_select(y_shard, d, False, drift, dt, cub, recv_ids[:keep], n_out=keep, out=y1[:keep])
         n_give = total - keep
-        send_rows = (_lib.expand_select(y_shard, d, False, drift, dt, cub, ids[keep:].contiguous(), n_out=n_give)
+        send_rows = (_lib.expand_select(y_shard, d, False, drift, dt, cub, recv_ids[keep:], n_out=n_give)
                      if n_give else y1.new_empty((0, d)))
-        return (y1, slots[:keep], send_rows, slots[keep:].contiguous(), [int(c) for c in transfers[rank]],
+        return (y1, recv_slots[:keep], send_rows, recv_slots[keep:], [int(c) for c in transfers[rank]],
                 [int(c) for c in transfers[:, rank]], keep)
 
-    def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None):
+    def _ids_exchange(self, t, n_loc: int, rank: int, device, group):
+        """Draw + bucket + exchange of the (slot, child id) pairs of the step whose outer time is `t`, on the current
+        stream.  One host synchronisation (the replicated counts matrix sizes the variable all-to-all)."""
+        G = self.n_ranks
+        slots, ids, counts_dev = self.owner_ids_bucket(t, n_loc, rank, device)
+        if G == 1:
+            return slots, ids, counts_dev.cpu().numpy().reshape(1, 1)
+        allc = [torch.empty_like(counts_dev) for _ in range(G)]
+        dist.all_gather(allc, counts_dev, group=group)
+        counts = torch.stack(allc).cpu().numpy()              # counts[src][owner]
+        send, recv = [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]]
+        return exchange_rows(slots, send, recv, group), exchange_rows(ids, send, recv, group), counts
+
+    def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None, prefetch: bool = True):
         """One step with a GLOBAL `MonteCarloKernel(with_replacement=True)` resample in which no parent row and
         (up to the binomial imbalance) no child row crosses the link: ranks exchange 8 bytes per output row --
         (slot, child id) -- and every rank materialises the selected children of its OWN parents with the local
         fused gather.  Works with 64-bit global child ids (`kernel.x64`, BASELINE config 5: 2^34 children) in
-        O(n_loc) memory per rank.  Returns (y1_shard, slot_map): y1_shard[q] is row slot_map[q] of the
-        single-device step on the concatenated state (same multiset, known permutation)."""
+        O(n_loc) memory per rank.  The index vector depends on (key, t) only, so with `prefetch` the draw, the
+        bucketing and the id exchange of the NEXT step (outer time t1) run on a side stream and a second
+        communicator while this step's gather keeps HBM busy.  Returns (y1_shard, slot_map): y1_shard[q] is row
+        slot_map[q] of the single-device step on the concatenated state (same multiset, known permutation)."""
+        from ._solvers import _side_stream
+
         G = self.n_ranks
-        pairs, counts_dev = self.owner_ids_bucket(t0, y_shard.contiguous(), rank)
-        if G == 1:
-            counts = counts_dev.cpu().numpy().reshape(1, 1)
-            recv_pairs = pairs
+        y_shard = y_shard.contiguous()
+        n_loc, dev = y_shard.shape[0], y_shard.device
+        main = torch.cuda.current_stream(dev)
+        ready = getattr(self, "_ids_ready", None)
+        self._ids_ready = None
+        if ready is not None and ready[0] == (float(t0), n_loc, rank):
+            _, event, recv_slots, recv_ids, counts = ready
+            main.wait_event(event)
+            recv_slots.record_stream(main)
+            recv_ids.record_stream(main)
         else:
-            allc = [torch.empty_like(counts_dev) for _ in range(G)]
-            dist.all_gather(allc, counts_dev, group=group)
-            counts = torch.stack(allc).cpu().numpy()          # counts[src][owner]: the step's one host synchronisation
-            recv_pairs = exchange_rows(pairs, [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]], group)
+            recv_slots, recv_ids, counts = self._ids_exchange(t0, n_loc, rank, dev, group)
         y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
-            t0, t1, y_shard, rank, recv_pairs, counts)
-        slot_map = torch.empty(y_shard.shape[0], dtype=torch.int32, device=y_shard.device)
+            t0, t1, y_shard, rank, recv_slots, recv_ids, counts)
+        slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
         slot_map[:keep] = slots
         if G > 1 and (sum(send_splits) or sum(recv_splits)):
             rows = exchange_rows(send_rows, send_splits, recv_splits, group)
-            got = exchange_rows(send_slots.reshape(-1, 1), send_splits, recv_splits, group).reshape(-1)
+            got = exchange_rows(send_slots.contiguous(), send_splits, recv_splits, group)
             if rows.shape[0]:
                 y1[keep:keep + rows.shape[0]] = rows
                 slot_map[keep:keep + rows.shape[0]] = got
+        if prefetch and G > 1:
+            if getattr(self, "_ids_group", None) is None:     # its own communicator: independent of the data path's
+                self._ids_group = dist.new_group(list(range(G))) if group is None else group
+            side = _side_stream(dev)
+            with torch.cuda.stream(side):
+                nxt = self._ids_exchange(t1, n_loc, rank, dev, self._ids_group)
+                event = torch.cuda.Event()
+                event.record(side)
+            self._ids_ready = ((float(t1), n_loc, rank), event) + nxt
         return y1, slot_map
 
 

@@ -78,7 +78,7 @@ _SIGNATURES = {
                                                C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_shard_bucket_ids_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mccb200_shard_bucket_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_compact_slots": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
     "mccb200_mc_indices_slice": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
@@ -779,23 +779,25 @@ def shard_owner_keys(idx, n_loc, k, n_ranks):
 
 
 def shard_bucket_ids(idx, first_slot, n_loc, k, n_ranks):
-    """Send buffer of the id exchange: (pairs [n, 2] int32 = (slot, owner-local child id) grouped by owner rank,
-    counts [n_ranks] int32) from this rank's slice `idx` (int32 bit patterns or int64) of the global index vector."""
+    """Send buffers of the id exchange: (slots [n] int32, ids [n] int32 = owner-local child ids, both grouped by
+    owner rank and ascending in slot inside a group, counts [n_ranks] int32) from this rank's slice `idx` (int32 bit
+    patterns or int64) of the global index vector."""
     lib = load()
     _require_cuda(idx)
     if idx.dtype not in (torch.int32, torch.uint32, torch.int64) or not idx.is_contiguous():
         raise MccubeB200Error(f"shard_bucket_ids: expected a contiguous int32 / int64 index slice, got {idx.dtype}")
     n = idx.numel()
-    pairs = torch.empty((n, 2), dtype=torch.int32, device=idx.device)
+    slots = torch.empty(n, dtype=torch.int32, device=idx.device)
+    ids = torch.empty(n, dtype=torch.int32, device=idx.device)
     counts = torch.empty(n_ranks, dtype=torch.int32, device=idx.device)
     nbytes = lib.mccb200_shard_bucket_ids_workspace_bytes(int(n_ranks))
     if nbytes == 0:
         raise MccubeB200Error(f"shard_bucket_ids: unsupported rank count {n_ranks}")
     ws = workspace(nbytes, idx.device)
     _check(lib.mccb200_shard_bucket_ids(idx.data_ptr(), int(idx.dtype == torch.int64), n, int(first_slot), int(n_loc),
-                                        int(k), int(n_ranks), pairs.data_ptr(), counts.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), _stream()), "shard_bucket_ids")
-    return pairs, counts
+                                        int(k), int(n_ranks), slots.data_ptr(), ids.data_ptr(), counts.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream()), "shard_bucket_ids")
+    return slots, ids, counts
 
 
 def shard_send_ids(idx, order, start, count, child_offset):

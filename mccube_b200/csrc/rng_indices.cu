@@ -76,12 +76,20 @@ randint_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint32_t span
   mult = (mult * mult) % span;
   const bool part = partitionable != 0;
   const uint32_t stride = gridDim.x * blockDim.x;
+  // mult == 0 (e.g. every power-of-two span >= 2^16: 65536^2 wraps to 0) makes the high draw drop out of
+  // ((hi % span) * mult + lo % span) % span: its threefry block and two of the three divisions are skipped, and
+  // for a power-of-two span the remaining one is a mask.  Same values, a third of the arithmetic.
+  const bool pow2 = (span & (span - 1u)) == 0u;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < slice; q += stride) {
     const uint32_t i = first + q;
-    uint32_t hi = random_bits32_at(k1, i, count, part);
-    uint32_t lo = random_bits32_at(k2, i, count, part);
-    uint32_t off = (hi % span) * mult + (lo % span);
-    out[q] = off % span;
+    const uint32_t lo = random_bits32_at(k2, i, count, part);
+    if (mult == 0u) {
+      out[q] = pow2 ? (lo & (span - 1u)) : (lo % span);
+    } else {
+      const uint32_t hi = random_bits32_at(k1, i, count, part);
+      const uint32_t off = (hi % span) * mult + (lo % span);
+      out[q] = off % span;
+    }
   }
 }
 
@@ -106,12 +114,17 @@ randint64_kernel(const DerivedKeys* __restrict__ dk, uint32_t count, uint64_t sp
   mult = (mult * mult) % span;                            // the product wraps in 64 bits, as lax.mul on uint64 does
   const bool part = partitionable != 0;
   const uint32_t stride = gridDim.x * blockDim.x;
+  const bool pow2 = (span & (span - 1ull)) == 0ull;       // (see randint_kernel: mult == 0 drops the high draw)
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < slice; q += stride) {
     const uint32_t i = first + q;
-    const uint64_t hi = random_bits64_at(k1, i, count, part);
     const uint64_t lo = random_bits64_at(k2, i, count, part);
-    const uint64_t off = (hi % span) * mult + (lo % span);
-    out[q] = off % span;
+    if (mult == 0ull) {
+      out[q] = pow2 ? (lo & (span - 1ull)) : (lo % span);
+    } else {
+      const uint64_t hi = random_bits64_at(k1, i, count, part);
+      const uint64_t off = (hi % span) * mult + (lo % span);
+      out[q] = off % span;
+    }
   }
 }
 

@@ -76,100 +76,115 @@ compact_slots_kernel(const uint32_t* __restrict__ idx_slots, uint64_t n_slots, u
 
 
 // ---------------------------------------------------------------- id exchange: stable partition of a slice by owner
-// A rank's slice of the global index vector (child ids, 32 or 64 bit) -> pairs (global slot, LOCAL child id of the
-// owner) grouped by owner rank, ascending slot inside a group: the send buffer of the id exchange.  Three small
-// kernels: per-CTA histograms over contiguous chunks, one scan, a stable scatter (tile by tile inside the chunk,
-// __match_any_sync ranks inside a warp).  8 bytes out per slot; G <= 64.
+// A rank's slice of the global index vector (child ids, 32 or 64 bit) -> (global slot, LOCAL child id of the
+// owner), grouped by owner rank and ascending in slot inside a group: the send buffers of the id exchange.
+// Every WARP owns a contiguous chunk of the slice: a histogram pass (per-warp counts), one scan over
+// [bucket][warp], and a scatter pass in which a warp walks its chunk 32 entries at a time (__match_any_sync gives
+// the rank among the same owner inside the warp, the warp's running offsets live in its own shared-memory row), so
+// there is no block-wide synchronisation in either pass.  8 bytes out per slot; G <= 64.
 constexpr int SB_THREADS = 256;
+constexpr int SB_WARPS = SB_THREADS / 32;
 constexpr int SB_MAX_RANKS = 64;
 
+struct OwnerOf {                 // owner = child / children_per_rank (a shift when that is a power of two)
+  uint64_t cpr;
+  int shift;                     // log2(cpr) or -1
+  __device__ __forceinline__ void decode(uint64_t c, uint32_t& owner, uint32_t& c_loc) const {
+    if (shift >= 0) { owner = (uint32_t)(c >> shift); c_loc = (uint32_t)(c & (cpr - 1ull)); }
+    else { owner = (uint32_t)(c / cpr); c_loc = (uint32_t)(c - (uint64_t)owner * cpr); }
+  }
+};
+
 template <typename IdxT>
-__device__ __forceinline__ void sb_decode(const IdxT* idx, uint64_t q, uint64_t children_per_rank, uint32_t& owner,
-                                          uint32_t& c_loc) {
-  const uint64_t c = (uint64_t)idx[q];
-  owner = (uint32_t)(c / children_per_rank);
-  c_loc = (uint32_t)(c - (uint64_t)owner * children_per_rank);
+__global__ void __launch_bounds__(SB_THREADS)
+shard_bucket_count_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chunk, OwnerOf own, int G,
+                          uint32_t n_warps, uint32_t* __restrict__ hist /*[G][n_warps]*/) {
+  __shared__ uint32_t s_cnt[SB_WARPS][SB_MAX_RANKS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gw = blockIdx.x * SB_WARPS + warp;
+  for (int g = lane; g < G; g += 32) s_cnt[warp][g] = 0u;
+  __syncwarp();
+  const uint64_t q0 = (uint64_t)gw * chunk, q1 = min(n, q0 + chunk);
+  for (uint64_t t0 = q0; t0 < q1; t0 += 32) {
+    const uint64_t q = t0 + lane;
+    uint32_t owner = 0xFFFFFFFFu, c_loc;
+    if (q < q1) own.decode((uint64_t)__ldcs(idx + q), owner, c_loc);
+    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+    if (q < q1 && (peers & ((1u << lane) - 1u)) == 0u) s_cnt[warp][owner] += (uint32_t)__popc(peers);
+    __syncwarp();
+  }
+  if (gw < n_warps)
+    for (int g = lane; g < G; g += 32) hist[(uint64_t)g * n_warps + gw] = s_cnt[warp][g];
+}
+
+// hist[g][w] (bucket-major) -> exclusive prefix in (bucket, warp) order = where warp w's entries of bucket g start;
+// counts[g] = bucket totals.  One CTA, 1024 threads, coalesced passes.
+__global__ void __launch_bounds__(1024)
+shard_bucket_scan_kernel(uint32_t* __restrict__ hist, uint32_t n_warps, int G, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t wtot[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0u;
+  __syncthreads();
+  for (int g = 0; g < G; ++g) {
+    const uint32_t bucket_start = carry_s;
+    for (uint32_t base = 0; base < n_warps; base += 1024) {
+      const uint32_t i = base + threadIdx.x;
+      const uint32_t v = i < n_warps ? hist[(uint64_t)g * n_warps + i] : 0u;
+      uint32_t x = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+      }
+      if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = x;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const uint32_t t = wtot[threadIdx.x];
+        uint32_t sc = t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, sc, o);
+          if (threadIdx.x >= o) sc += y;
+        }
+        wtot[threadIdx.x] = sc - t;
+      }
+      __syncthreads();
+      const uint32_t carry = carry_s;
+      const uint32_t incl = x + wtot[threadIdx.x >> 5];
+      if (i < n_warps) hist[(uint64_t)g * n_warps + i] = carry + incl - v;
+      __syncthreads();
+      if (threadIdx.x == 1023) carry_s = carry + incl;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[g] = carry_s - bucket_start;
+  }
 }
 
 template <typename IdxT>
 __global__ void __launch_bounds__(SB_THREADS)
-shard_bucket_count_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chunk, uint64_t children_per_rank, int G,
-                          uint32_t* __restrict__ hist /*[gridDim.x][G]*/) {
-  __shared__ uint32_t s_cnt[SB_MAX_RANKS];
-  for (int i = threadIdx.x; i < G; i += blockDim.x) s_cnt[i] = 0u;
-  __syncthreads();
-  const uint64_t q0 = (uint64_t)blockIdx.x * chunk, q1 = min(n, q0 + chunk);
-  for (uint64_t t0 = q0; t0 < q1; t0 += blockDim.x) {          // (whole warps iterate together)
-    const uint64_t q = t0 + threadIdx.x;
+shard_bucket_scatter_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chunk, uint64_t first_slot, OwnerOf own,
+                            int G, uint32_t n_warps, const uint32_t* __restrict__ start /*[G][n_warps]*/,
+                            uint32_t* __restrict__ slots_out, uint32_t* __restrict__ ids_out) {
+  __shared__ uint32_t s_run[SB_WARPS][SB_MAX_RANKS];            // next output position of every bucket, per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gw = blockIdx.x * SB_WARPS + warp;
+  if (gw >= n_warps) return;
+  for (int g = lane; g < G; g += 32) s_run[warp][g] = start[(uint64_t)g * n_warps + gw];
+  __syncwarp();
+  const uint64_t q0 = (uint64_t)gw * chunk, q1 = min(n, q0 + chunk);
+  for (uint64_t t0 = q0; t0 < q1; t0 += 32) {
+    const uint64_t q = t0 + lane;
     const bool have = q < q1;
     uint32_t owner = 0xFFFFFFFFu, c_loc = 0;
-    if (have) sb_decode(idx, q, children_per_rank, owner, c_loc);
+    if (have) own.decode((uint64_t)__ldcs(idx + q), owner, c_loc);
     const uint32_t peers = __match_any_sync(0xffffffffu, owner);
-    if (have && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&s_cnt[owner], (uint32_t)__popc(peers));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < G; i += blockDim.x) hist[(uint64_t)blockIdx.x * G + i] = s_cnt[i];
-}
-
-// hist[b][g] -> start of CTA b's entries of bucket g in the grouped output; counts[g] = bucket totals
-__global__ void __launch_bounds__(SB_MAX_RANKS)
-shard_bucket_scan_kernel(uint32_t* __restrict__ hist, int n_ctas, int G, uint32_t* __restrict__ counts) {
-  __shared__ uint32_t s_tot[SB_MAX_RANKS];
-  const int g = threadIdx.x;
-  uint32_t run = 0;
-  if (g < G) {
-    for (int b = 0; b < n_ctas; ++b) {
-      const uint32_t v = hist[(uint64_t)b * G + g];
-      hist[(uint64_t)b * G + g] = run;
-      run += v;
-    }
-    s_tot[g] = run;
-    counts[g] = run;
-  }
-  __syncthreads();
-  if (g < G) {
-    uint32_t base = 0;
-    for (int i = 0; i < g; ++i) base += s_tot[i];
-    if (base)
-      for (int b = 0; b < n_ctas; ++b) hist[(uint64_t)b * G + g] += base;
-  }
-}
-
-template <typename IdxT>
-__global__ void __launch_bounds__(SB_THREADS)
-shard_bucket_scatter_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chunk, uint64_t first_slot,
-                            uint64_t children_per_rank, int G, const uint32_t* __restrict__ start /*[gridDim.x][G]*/,
-                            uint2* __restrict__ pairs) {
-  __shared__ uint32_t s_run[SB_MAX_RANKS];                      // next output position of every bucket (this CTA)
-  __shared__ uint32_t s_warp[SB_THREADS / 32][SB_MAX_RANKS];    // per-warp bucket counts of the current tile
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < G; i += blockDim.x) s_run[i] = start[(uint64_t)blockIdx.x * G + i];
-  const uint64_t q0 = (uint64_t)blockIdx.x * chunk, q1 = min(n, q0 + chunk);
-  for (uint64_t t0 = q0; t0 < q1; t0 += blockDim.x) {          // tiles in order: stability across tiles
-    for (int i = threadIdx.x; i < (SB_THREADS / 32) * SB_MAX_RANKS; i += blockDim.x) (&s_warp[0][0])[i] = 0u;
-    __syncthreads();
-    const uint64_t q = t0 + threadIdx.x;
-    const bool have = q < q1;
-    uint32_t owner = 0xFFFFFFFFu, c_loc = 0, rank_in_warp = 0;
-    if (have) sb_decode(idx, q, children_per_rank, owner, c_loc);
-    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+    uint32_t pos = 0;
+    if (have) pos = s_run[warp][owner] + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
     if (have) {
-      rank_in_warp = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      if (rank_in_warp == 0u) s_warp[warp][owner] = (uint32_t)__popc(peers);
+      slots_out[pos] = (uint32_t)(first_slot + q);
+      ids_out[pos] = c_loc;
+      if ((peers >> lane) == 1u) s_run[warp][owner] = pos + 1u;   // the highest peer lane advances the bucket
     }
-    __syncthreads();
-    if (have) {
-      uint32_t before = 0;
-      for (int w = 0; w < warp; ++w) before += s_warp[w][owner];
-      pairs[s_run[owner] + before + rank_in_warp] = make_uint2((uint32_t)(first_slot + q), c_loc);
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      uint32_t tot = 0;
-      for (int w = 0; w < SB_THREADS / 32; ++w) tot += s_warp[w][g];
-      s_run[g] += tot;
-    }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -274,27 +289,27 @@ extern "C" int mccb200_scatter_rows(const float* in, int ld, const uint32_t* slo
   return check_launch("scatter_rows");
 }
 
-static int sb_grid(uint64_t n, uint64_t& chunk) {
-  uint64_t ctas = (uint64_t)sm_count() * 4;
-  chunk = (n + ctas - 1) / ctas;
-  chunk = (chunk + SB_THREADS - 1) / SB_THREADS * SB_THREADS;
-  if (chunk == 0) chunk = SB_THREADS;
-  return (int)((n + chunk - 1) / chunk);
+static uint32_t sb_warps(uint64_t n, uint64_t& chunk) {
+  uint64_t warps = (uint64_t)sm_count() * 4 * SB_WARPS;
+  chunk = (n + warps - 1) / warps;
+  chunk = (chunk + 31) / 32 * 32;
+  if (chunk == 0) chunk = 32;
+  return (uint32_t)((n + chunk - 1) / chunk);
 }
 
 extern "C" size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks) {
   if (n_ranks < 1 || n_ranks > SB_MAX_RANKS) return 0;
-  return ((size_t)sm_count() * 4 + 1) * (size_t)n_ranks * sizeof(uint32_t);
+  return ((size_t)sm_count() * 4 * SB_WARPS + 1) * (size_t)n_ranks * sizeof(uint32_t);
 }
 
-/* The send buffer of the id exchange (`ShardedMonteCarloStep.step_owner_ids`): `idx` = this rank's slice of the
- * global index vector (child ids, uint32 or uint64), output slot of entry q = first_slot + q.  pairs_out[n][2] =
- * (slot, child id relative to the owner's first parent) grouped by owner rank = child / (n_loc * k), ascending slot
- * inside a group; counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32, slots < 2^32. */
+/* The send buffers of the id exchange (`ShardedMonteCarloStep.step_owner_ids`): `idx` = this rank's slice of the
+ * global index vector (child ids, uint32 or uint64), output slot of entry q = first_slot + q.  slots_out[n] /
+ * ids_out[n] = (slot, child id relative to the owner's first parent) grouped by owner rank = child / (n_loc * k),
+ * ascending slot inside a group; counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32, slots < 2^32. */
 extern "C" int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
-                                        int k, int n_ranks, uint32_t* pairs_out, uint32_t* counts_out, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
-  MCCB_REQUIRE(idx && pairs_out && counts_out && workspace, "shard_bucket_ids: NULL argument");
+                                        int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  MCCB_REQUIRE(idx && slots_out && ids_out && counts_out && workspace, "shard_bucket_ids: NULL argument");
   MCCB_REQUIRE(n_ranks >= 1 && n_ranks <= SB_MAX_RANKS && n_loc >= 1 && k >= 1, "shard_bucket_ids: bad shape");
   MCCB_REQUIRE(n_loc * (uint64_t)k <= 0x100000000ull, "shard_bucket_ids: n_loc * k exceeds 2^32 local child ids");
   MCCB_REQUIRE(first_slot + n <= 0x100000000ull, "shard_bucket_ids: slots exceed 32 bits");
@@ -306,19 +321,23 @@ extern "C" int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t
     return MCCB200_OK;
   }
   uint64_t chunk;
-  const int grid = sb_grid(n, chunk);
-  const uint64_t cpr = n_loc * (uint64_t)k;
+  const uint32_t n_warps = sb_warps(n, chunk);
+  const int grid = (int)((n_warps + SB_WARPS - 1) / SB_WARPS);
+  OwnerOf own;
+  own.cpr = n_loc * (uint64_t)k;
+  own.shift = -1;
+  if ((own.cpr & (own.cpr - 1)) == 0) { own.shift = 0; while ((1ull << own.shift) < own.cpr) ++own.shift; }
   uint32_t* hist = (uint32_t*)workspace;
   if (idx_is_64) {
-    shard_bucket_count_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, cpr, n_ranks, hist);
-    shard_bucket_scan_kernel<<<1, SB_MAX_RANKS, 0, st>>>(hist, grid, n_ranks, counts_out);
-    shard_bucket_scatter_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, first_slot, cpr,
-                                                                        n_ranks, hist, (uint2*)pairs_out);
+    shard_bucket_count_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, own, n_ranks, n_warps, hist);
+    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, counts_out);
+    shard_bucket_scatter_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, first_slot, own,
+                                                                        n_ranks, n_warps, hist, slots_out, ids_out);
   } else {
-    shard_bucket_count_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, cpr, n_ranks, hist);
-    shard_bucket_scan_kernel<<<1, SB_MAX_RANKS, 0, st>>>(hist, grid, n_ranks, counts_out);
-    shard_bucket_scatter_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, first_slot, cpr,
-                                                                        n_ranks, hist, (uint2*)pairs_out);
+    shard_bucket_count_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, own, n_ranks, n_warps, hist);
+    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, counts_out);
+    shard_bucket_scatter_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, first_slot, own,
+                                                                        n_ranks, n_warps, hist, slots_out, ids_out);
   }
   count_launches(3);
   return check_launch("shard_bucket_ids");

@@ -765,16 +765,17 @@ def test_sharded_owner_ids_emulated_ranks(dev, G, n_loc, d, x64):
         want = _lib.expand_gather_peers(ptrs, 1, n_tot, d, drift, dt, cub, idx, torch.empty_like(yt))
     sh = ShardedMonteCarloStep(make(), terms, G)
     shards = [yt[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
-    bucketed = [sh.owner_ids_bucket(t0, shards[r], r) for r in range(G)]
-    counts = torch.stack([c for _, c in bucketed]).cpu().numpy()           # counts[src][owner]
+    bucketed = [sh.owner_ids_bucket(t0, n_loc, r, dev) for r in range(G)]
+    counts = torch.stack([c for _, _, c in bucketed]).cpu().numpy()        # counts[src][owner]
     assert counts.sum() == n_tot and (counts.sum(1) == n_loc).all()
     mats = []
     for r in range(G):
-        parts = []
+        ps, pi = [], []
         for src in range(G):
             off = int(counts[src, :r].sum())
-            parts.append(bucketed[src][0][off:off + int(counts[src, r])])
-        mats.append(sh.owner_ids_materialise(t0, t1, shards[r], r, torch.cat(parts), counts))
+            ps.append(bucketed[src][0][off:off + int(counts[src, r])])
+            pi.append(bucketed[src][1][off:off + int(counts[src, r])])
+        mats.append(sh.owner_ids_materialise(t0, t1, shards[r], r, torch.cat(ps), torch.cat(pi), counts))
     outs, maps = [], []
     for r in range(G):
         y1, slots, _, _, _, recv_splits, keep = mats[r]
@@ -795,14 +796,16 @@ def test_sharded_owner_ids_emulated_ranks(dev, G, n_loc, d, x64):
     all_slots = torch.cat(maps).to(torch.int64)
     assert torch.equal(torch.sort(all_slots).values, torch.arange(n_tot, device=dev))
     assert torch.equal(torch.cat(outs), want[all_slots])
-    # grouping is stable: ascending slots inside every owner group of the send buffer
+    # grouping is stable: ascending slots inside every owner group of the send buffer, ids local to the owner
+    k = terms.cde.control.gaussian_cubature.point_count
     for r in range(G):
-        pairs = bucketed[r][0].to(torch.int64)
+        slots_r, ids_r = bucketed[r][0].to(torch.int64), bucketed[r][1].to(torch.int64) & 0xFFFFFFFF
         start = 0
         for o in range(G):
-            grp = pairs[start:start + int(counts[r, o])]
-            start += int(counts[r, o])
-            assert bool((grp[1:, 0] > grp[:-1, 0]).all())
+            c = int(counts[r, o])
+            assert bool((slots_r[start + 1:start + c] > slots_r[start:start + c - 1]).all())
+            assert c == 0 or int(ids_r[start:start + c].max()) < n_loc * k
+            start += c
 
 
 @pytest.mark.parametrize("partitionable", [False, True])
