@@ -601,23 +601,29 @@ def sharded_global_mc(dev, rank, world, steps=5):
             "note": "2^34 implicit children, int64 index draw; (slot, child id) pairs exchanged, rows stay with their parents"}
         del y5, smap5
         torch.cuda.empty_cache()
-        # the same step on ONE GPU's worth of particles (n = 2^24, 32-bit ids), every rank on its own: the 1-GPU figure
-        # the efficiency below is quoted against
-        n1 = 1 << 24
-        if n_loc5 <= n1:
-            solver1 = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n1, True, key=42))
-            gen.manual_seed(19 + rank)
-            ms1, _ = time_steps(solver1, terms, torch.randn((n1, d), generator=gen, device=dev), times, steps)
-            t1g = torch.tensor([ms1], device=dev)
-            dist.all_reduce(t1g, op=dist.ReduceOp.MAX)
-            one_gpu = n1 / (float(t1g) * 1e-3)
-            best = max(v["particle_steps_per_sec"] for k_, v in out.items()
-                       if k_.startswith("config5_") and isinstance(v, dict) and "particle_steps_per_sec" in v)
-            out["config5"] = {"one_gpu_n2^24_particle_steps_per_sec": one_gpu, "one_gpu_ms_per_step": float(t1g),
-                              "best_particle_steps_per_sec": best, "speedup_vs_1gpu": best / one_gpu,
-                              "efficiency_vs_1gpu": best / one_gpu / world}
     except Exception as e:  # noqa: BLE001
         out["config5_n2^27_d64_step_owner_ids"] = {"error": repr(e)}
+    # the same step on ONE GPU's worth of particles (n = 2^24, 32-bit ids), every rank on its own: the 1-GPU figure the
+    # config-5 efficiency is quoted against (the north star asks for >= 6x one GPU at 8 GPUs)
+    try:
+        n1 = 1 << 24
+        solver1 = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n1, True, key=42))
+        gen.manual_seed(19 + rank)
+        ms1, _ = time_steps(solver1, terms, torch.randn((n1, d), generator=gen, device=dev), times, steps)
+        t1g = torch.tensor([ms1], device=dev)
+        dist.all_reduce(t1g, op=dist.ReduceOp.MAX)
+        one_gpu = n1 / (float(t1g) * 1e-3)
+        done5 = {k_: v["particle_steps_per_sec"] for k_, v in out.items()
+                 if k_.startswith("config5_") and isinstance(v, dict) and "particle_steps_per_sec" in v}
+        if done5:
+            best_name = max(done5, key=done5.get)
+            out["config5"] = {"one_gpu_n2^24_particle_steps_per_sec": one_gpu, "one_gpu_ms_per_step": float(t1g),
+                              "best": best_name, "best_particle_steps_per_sec": done5[best_name],
+                              "speedup_vs_1gpu": done5[best_name] / one_gpu,
+                              "efficiency_vs_1gpu": done5[best_name] / one_gpu / world}
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["config5"] = {"error": repr(e)}
     out["step"]["exchange_bytes_per_rank_per_step"] = int(n_loc * d * 4 * (world - 1) / world)
     out["note"] = ("step_pull: every rank draws only its own slice of the (counter-based) index vector and the gather "
                    "kernel reads the selected parents from the owners' shards over NVLink peer memory: O(n_loc) work per "

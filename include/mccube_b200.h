@@ -147,6 +147,11 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
  * child c = ((i*k + j_1)*k + j_2)..., y <- y + (dts[s] * f(y) + scales[s] * M[j_s, :]) for s = 0..n_substeps-1,
  * the drift re-evaluated at every intermediate state.  Hadamard cubature, drift kinds 0 / 2 (an array drift
  * is only known at the parents), unweighted, n * k^n_substeps <= 2^32.  dts / scales are HOST arrays. */
+/* The same with child ids `idx_stride` 32-bit words apart (idx_stride = 2: the id column of packed (slot, id) pairs
+ * received from the id exchange, mccb200_shard_bucket_ids); unweighted, no permutation. */
+MCCB200_API int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                              const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
+                                              uint64_t n_out, float* y1, void* stream);
 MCCB200_API int mccb200_expand_select_substeps(const float* y0, uint64_t n, int d, const mccb200_drift* drift,
                                                int n_substeps, const float* dts_host, const float* scales_host,
                                                int k, const uint32_t* idx, uint64_t n_out, float* y1, void* stream);
@@ -351,11 +356,13 @@ MCCB200_API int mccb200_expand_scatter_slots(const float* y0, uint64_t n_loc, in
  * THIS rank's slice of the global index vector (child ids, uint32, or uint64 when idx_is_64), entry q belonging to
  * output slot first_slot + q.  slots_out[n] / ids_out[n] = (slot, child id relative to the owner's first parent),
  * grouped by owner rank = child / (n_loc * k) and ascending in slot inside a group -- the send buffers of the
- * exchange; counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32 and slots < 2^32. */
+ * exchange; counts_out[n_ranks] = group sizes.  n_loc * k <= 2^32 and slots < 2^32.  ids_out == NULL packs the two
+ * into slots_out[n][2] = (slot, id) instead (one all-to-all; mccb200_unzip_pairs splits them on the receiving side). */
 MCCB200_API size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks);
 MCCB200_API int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
                                          int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
                                          void* workspace, size_t workspace_bytes, void* stream);
+MCCB200_API int mccb200_unzip_pairs(const uint32_t* pairs /*[n][2]*/, uint64_t n, uint32_t* slots, uint32_t* ids, void* stream);
 MCCB200_API int mccb200_compact_slots(const uint32_t* idx_slots, uint64_t n_slots, uint32_t* list, uint64_t capacity,
                                       uint32_t* cursor, void* stream);
 

@@ -345,7 +345,7 @@ class ShardedMonteCarloStep:
 
 
     # ---- id exchange + owner-computes: O(n_loc) memory per rank, 64-bit child ids, no row leaves its owner
-    def owner_ids_bucket(self, t0, n_loc: int, rank: int, device):
+    def owner_ids_bucket(self, t0, n_loc: int, rank: int, device, packed: bool = False):
         """Phase 1 (local): this rank draws ONLY the index slice of the output slots [rank * n_loc, (rank+1) * n_loc)
         (`with_replacement=True`: the draws are counter based) and groups (slot, LOCAL child id) by the rank that owns
         the selected parent, stably (ascending slot inside a group).  Depends on (key, t0) only, not on the state.
@@ -363,14 +363,14 @@ class ShardedMonteCarloStep:
         if n_loc * k > 2 ** 32:
             raise ValueError("step_owner_ids: a shard's children need 32-bit local ids (n_loc * k <= 2^32)")
         idx = kernel.indices_slice(t0, n_tot * k, n_tot, rank * n_loc, n_loc, device)
-        return _lib.shard_bucket_ids(idx, rank * n_loc, n_loc, k, G)
+        return _lib.shard_bucket_ids(idx, rank * n_loc, n_loc, k, G, packed=packed)
 
-    def owner_ids_materialise(self, t0, t1, y_shard: torch.Tensor, rank: int, recv_slots: torch.Tensor,
-                              recv_ids: torch.Tensor, counts):
-        """Phase 2 (local, after the id exchange): `recv_slots` / `recv_ids` = output slot and local child id of every
+    def owner_ids_materialise(self, t0, t1, y_shard: torch.Tensor, rank: int, recv_pairs: torch.Tensor, counts):
+        """Phase 2 (local, after the id exchange): `recv_pairs` [T, 2] int32 = (output slot, local child id) of every
         output row whose selected parent lives on this rank, in sender order; `counts[src][owner]` = the replicated
         matrix of pair counts.  Materialises the first n_loc of them into this rank's next shard and the surplus
-        into a send buffer for the ranks with a deficit (`plan_rebalance`, O(sqrt(n_loc)) rows).
+        into a send buffer for the ranks with a deficit (`plan_rebalance`, O(sqrt(n_loc)) rows); the gather reads the
+        id column of the pairs in place.
         Returns (y1 [n_loc, d] with rows [:keep] filled, slots [keep], send_rows, send_slots, send_splits,
         recv_splits, keep)."""
         import numpy as np
@@ -384,29 +384,36 @@ class ShardedMonteCarloStep:
         per_owner = counts.sum(axis=0)                       # rows every rank materialises
         transfers = plan_rebalance(per_owner, n_loc)
         total = int(per_owner[rank])
-        assert recv_ids.shape[0] == total and recv_slots.shape[0] == total
+        assert recv_pairs.shape[0] == total
         keep = min(total, n_loc)
         y1 = torch.empty((n_loc, d), dtype=torch.float32, device=y_shard.device)
         if keep:
-            _lib.expand_select(y_shard, d, False, drift, dt, cub, recv_ids[:keep], n_out=keep, out=y1[:keep])
+            _lib.expand_select_pairs(y_shard, d, drift, dt, cub, recv_pairs, n_out=keep, out=y1[:keep])
         n_give = total - keep
-        send_rows = (_lib.expand_select(y_shard, d, False, drift, dt, cub, recv_ids[keep:], n_out=n_give)
+        send_rows = (_lib.expand_select_pairs(y_shard, d, drift, dt, cub, recv_pairs, n_out=n_give, first=keep)
                      if n_give else y1.new_empty((0, d)))
-        return (y1, recv_slots[:keep], send_rows, recv_slots[keep:], [int(c) for c in transfers[rank]],
+        return (y1, recv_pairs[:keep, 0], send_rows, recv_pairs[keep:, 0], [int(c) for c in transfers[rank]],
                 [int(c) for c in transfers[:, rank]], keep)
 
-    def _ids_exchange(self, t, n_loc: int, rank: int, device, group):
-        """Draw + bucket + exchange of the (slot, child id) pairs of the step whose outer time is `t`, on the current
-        stream.  One host synchronisation (the replicated counts matrix sizes the variable all-to-all)."""
+    def _ids_launch(self, t, n_loc: int, rank: int, device, group):
+        """First half of the id exchange of the step whose outer time is `t` (current stream, nothing waits on the
+        host): draw + bucket + all-gather of the per-owner counts."""
         G = self.n_ranks
-        slots, ids, counts_dev = self.owner_ids_bucket(t, n_loc, rank, device)
+        pairs, counts_dev = self.owner_ids_bucket(t, n_loc, rank, device, packed=True)
         if G == 1:
-            return slots, ids, counts_dev.cpu().numpy().reshape(1, 1)
+            return pairs, counts_dev, None
         allc = [torch.empty_like(counts_dev) for _ in range(G)]
         dist.all_gather(allc, counts_dev, group=group)
-        counts = torch.stack(allc).cpu().numpy()              # counts[src][owner]
-        send, recv = [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]]
-        return exchange_rows(slots, send, recv, group), exchange_rows(ids, send, recv, group), counts
+        return pairs, counts_dev, allc
+
+    def _ids_finish(self, launched, rank: int, group):
+        """Second half: the step's one host synchronisation (the replicated counts matrix sizes the variable
+        all-to-all) and one packed all-to-all.  Returns (pairs received [T, 2], counts[src][owner])."""
+        pairs, counts_dev, allc = launched
+        if allc is None:
+            return pairs, counts_dev.cpu().numpy().reshape(1, 1)
+        counts = torch.stack(allc).cpu().numpy()
+        return exchange_rows(pairs, [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]], group), counts
 
     def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None, prefetch: bool = True):
         """One step with a GLOBAL `MonteCarloKernel(with_replacement=True)` resample in which no parent row and
@@ -414,40 +421,47 @@ class ShardedMonteCarloStep:
         (slot, child id) -- and every rank materialises the selected children of its OWN parents with the local
         fused gather.  Works with 64-bit global child ids (`kernel.x64`, BASELINE config 5: 2^34 children) in
         O(n_loc) memory per rank.  The index vector depends on (key, t) only, so with `prefetch` the draw, the
-        bucketing and the id exchange of the NEXT step (outer time t1) run on a side stream and a second
-        communicator while this step's gather keeps HBM busy.  Returns (y1_shard, slot_map): y1_shard[q] is row
-        slot_map[q] of the single-device step on the concatenated state (same multiset, known permutation)."""
-        from ._solvers import _side_stream
-
+        bucketing and the id exchange of the NEXT step (outer time t1) are issued on a high-priority side stream
+        and a second communicator before this step's HBM-bound gather is enqueued, and run under it.  Returns
+        (y1_shard, slot_map): y1_shard[q] is row slot_map[q] of the single-device step on the concatenated state
+        (same multiset, known permutation)."""
         G = self.n_ranks
         y_shard = y_shard.contiguous()
-        n_loc, dev = y_shard.shape[0], y_shard.device
+        n_loc, d = y_shard.shape
+        dev = y_shard.device
         main = torch.cuda.current_stream(dev)
         ready = getattr(self, "_ids_ready", None)
         self._ids_ready = None
         if ready is not None and ready[0] == (float(t0), n_loc, rank):
-            _, event, recv_slots, recv_ids, counts = ready
+            _, event, recv_pairs, counts = ready
             main.wait_event(event)
-            recv_slots.record_stream(main)
-            recv_ids.record_stream(main)
+            recv_pairs.record_stream(main)
         else:
-            recv_slots, recv_ids, counts = self._ids_exchange(t0, n_loc, rank, dev, group)
-        y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
-            t0, t1, y_shard, rank, recv_slots, recv_ids, counts)
-        slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
-        slot_map[:keep] = slots
-        if G > 1 and (sum(send_splits) or sum(recv_splits)):
-            rows = exchange_rows(send_rows, send_splits, recv_splits, group)
-            got = exchange_rows(send_slots.contiguous(), send_splits, recv_splits, group)
-            if rows.shape[0]:
-                y1[keep:keep + rows.shape[0]] = rows
-                slot_map[keep:keep + rows.shape[0]] = got
+            recv_pairs, counts = self._ids_finish(self._ids_launch(t0, n_loc, rank, dev, group), rank, group)
+        launched = side = None
         if prefetch and G > 1:
             if getattr(self, "_ids_group", None) is None:     # its own communicator: independent of the data path's
                 self._ids_group = dist.new_group(list(range(G))) if group is None else group
-            side = _side_stream(dev)
+                self._ids_stream = torch.cuda.Stream(device=dev, priority=-1)   # its CTAs go ahead of the gather's
+            side = self._ids_stream
             with torch.cuda.stream(side):
-                nxt = self._ids_exchange(t1, n_loc, rank, dev, self._ids_group)
+                launched = self._ids_launch(t1, n_loc, rank, dev, self._ids_group)
+        y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
+            t0, t1, y_shard, rank, recv_pairs, counts)
+        slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        slot_map[:keep] = slots
+        if G > 1 and (sum(send_splits) or sum(recv_splits)):
+            # the surplus rows travel with their slot as one more column (its int32 bit pattern): one all-to-all
+            packed = torch.empty((send_rows.shape[0], d + 1), dtype=torch.float32, device=dev)
+            packed[:, :d] = send_rows
+            packed[:, d] = send_slots.contiguous().view(torch.float32)
+            got = exchange_rows(packed, send_splits, recv_splits, group)
+            if got.shape[0]:
+                y1[keep:keep + got.shape[0]] = got[:, :d]
+                slot_map[keep:keep + got.shape[0]] = got[:, d].contiguous().view(torch.int32)
+        if launched is not None:                              # the gather is enqueued: now the host may wait
+            with torch.cuda.stream(side):
+                nxt = self._ids_finish(launched, rank, self._ids_group)
                 event = torch.cuda.Event()
                 event.record(side)
             self._ids_ready = ((float(t1), n_loc, rank), event) + nxt

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "mccb200_shard_bucket_ids_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mccb200_shard_bucket_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_expand_select_strided": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                               C.POINTER(Cubature), C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_unzip_pairs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mccb200_compact_slots": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
     "mccb200_mc_indices_slice": (C.c_int, [C.POINTER(Rng), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
@@ -361,6 +364,22 @@ def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=No
     _check(lib.mccb200_expand_select(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
                                      C.byref(cub), idx.data_ptr(), _ptr(perm), out_per_part, in_per_part, n_out,
                                      out.data_ptr(), _stream()), "expand_select")
+    return out
+
+
+def expand_select_pairs(y0, d, drift: Drift, dt, cub: Cubature, pairs, n_out=None, out=None, first=0):
+    """expand_select reading the child ids from column 1 of packed (slot, id) pairs [n, 2] int32, rows
+    [first, first + n_out)."""
+    lib = load()
+    _require_cuda(y0, pairs)
+    _f32c(y0)
+    _i32c(pairs, "expand_select_pairs")
+    n, ld = y0.shape
+    n_out = pairs.shape[0] - first if n_out is None else n_out
+    out = torch.empty((n_out, ld), dtype=torch.float32, device=y0.device) if out is None else out
+    _check(lib.mccb200_expand_select_strided(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                             pairs.data_ptr() + 8 * first + 4, 2, n_out, out.data_ptr(), _stream()),
+           "expand_select_strided")
     return out
 
 
@@ -778,26 +797,38 @@ def shard_owner_keys(idx, n_loc, k, n_ranks):
     return keys, counts
 
 
-def shard_bucket_ids(idx, first_slot, n_loc, k, n_ranks):
-    """Send buffers of the id exchange: (slots [n] int32, ids [n] int32 = owner-local child ids, both grouped by
-    owner rank and ascending in slot inside a group, counts [n_ranks] int32) from this rank's slice `idx` (int32 bit
-    patterns or int64) of the global index vector."""
+def shard_bucket_ids(idx, first_slot, n_loc, k, n_ranks, packed: bool = False):
+    """Send buffers of the id exchange from this rank's slice `idx` (int32 bit patterns or int64) of the global index
+    vector: (slots [n] int32, ids [n] int32 = owner-local child ids, counts [n_ranks] int32), both grouped by owner
+    rank and ascending in slot inside a group; `packed` returns (pairs [n, 2] int32, counts) for one all-to-all."""
     lib = load()
     _require_cuda(idx)
     if idx.dtype not in (torch.int32, torch.uint32, torch.int64) or not idx.is_contiguous():
         raise MccubeB200Error(f"shard_bucket_ids: expected a contiguous int32 / int64 index slice, got {idx.dtype}")
     n = idx.numel()
-    slots = torch.empty(n, dtype=torch.int32, device=idx.device)
-    ids = torch.empty(n, dtype=torch.int32, device=idx.device)
+    slots = torch.empty((n, 2) if packed else (n,), dtype=torch.int32, device=idx.device)
+    ids = None if packed else torch.empty(n, dtype=torch.int32, device=idx.device)
     counts = torch.empty(n_ranks, dtype=torch.int32, device=idx.device)
     nbytes = lib.mccb200_shard_bucket_ids_workspace_bytes(int(n_ranks))
     if nbytes == 0:
         raise MccubeB200Error(f"shard_bucket_ids: unsupported rank count {n_ranks}")
     ws = workspace(nbytes, idx.device)
     _check(lib.mccb200_shard_bucket_ids(idx.data_ptr(), int(idx.dtype == torch.int64), n, int(first_slot), int(n_loc),
-                                        int(k), int(n_ranks), slots.data_ptr(), ids.data_ptr(), counts.data_ptr(),
+                                        int(k), int(n_ranks), slots.data_ptr(), _ptr(ids), counts.data_ptr(),
                                         ws.data_ptr(), ws.numel(), _stream()), "shard_bucket_ids")
-    return slots, ids, counts
+    return (slots, counts) if packed else (slots, ids, counts)
+
+
+def unzip_pairs(pairs):
+    """(slots [n], ids [n]) from packed pairs [n, 2] int32."""
+    lib = load()
+    _require_cuda(pairs)
+    _i32c(pairs, "unzip_pairs")
+    n = pairs.shape[0]
+    slots = torch.empty(n, dtype=torch.int32, device=pairs.device)
+    ids = torch.empty(n, dtype=torch.int32, device=pairs.device)
+    _check(lib.mccb200_unzip_pairs(pairs.data_ptr(), n, slots.data_ptr(), ids.data_ptr(), _stream()), "unzip_pairs")
+    return slots, ids
 
 
 def shard_send_ids(idx, order, start, count, child_offset):

@@ -19,6 +19,7 @@ struct ExpandArgs {
   float scale;
   const float* lam;
   const uint32_t* idx;
+  uint32_t idx_stride;   // idx entries are idx_stride words apart (2: the id column of packed (slot, id) pairs); 0 = 1
   const uint32_t* perm;
   uint32_t out_per_part, in_per_part;
   uint64_t n_out;

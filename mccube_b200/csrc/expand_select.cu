@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r
     uint32_t l = (uint32_t)(r - (uint64_t)b * a.out_per_part);
     return a.perm[(uint64_t)b * a.in_per_part + a.idx[l]];
   }
-  return a.idx ? a.idx[r] : (uint32_t)r;
+  return a.idx ? a.idx[a.idx_stride > 1u ? r * a.idx_stride : r] : (uint32_t)r;
 }
 
 // MODE 0: plain (the hot path: nothing below costs it an instruction); 1: scatter to peer shards;
@@ -350,6 +350,20 @@ extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int wei
     MCCB_REQUIRE(out_per_part < 0x100000000ull && in_per_part < 0x100000000ull, "expand_select: partition too large");
   }
   a.idx = idx; a.perm = perm; a.out_per_part = (uint32_t)out_per_part; a.in_per_part = (uint32_t)in_per_part;
+  a.n_out = n_out; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+/* expand_select whose child ids are `idx_stride` 32-bit words apart: idx_stride = 2 reads the id column of packed
+ * (slot, id) pairs, as they arrive from the id exchange of the sharded resample (mccb200_shard_bucket_ids). */
+extern "C" int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                             const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
+                                             uint64_t n_out, float* y1, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, 0, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(idx && y1 && idx_stride >= 1, "expand_select_strided: bad argument");
+  a.idx = idx; a.idx_stride = (uint32_t)idx_stride; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
   a.n_out = n_out; a.y1 = y1;
   return run_expand(a, (cudaStream_t)stream);
 }

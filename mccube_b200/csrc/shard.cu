@@ -162,7 +162,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(SB_THREADS)
 shard_bucket_scatter_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chunk, uint64_t first_slot, OwnerOf own,
                             int G, uint32_t n_warps, const uint32_t* __restrict__ start /*[G][n_warps]*/,
-                            uint32_t* __restrict__ slots_out, uint32_t* __restrict__ ids_out) {
+                            uint32_t* __restrict__ slots_out, uint32_t* __restrict__ ids_out /* NULL: packed pairs */) {
   __shared__ uint32_t s_run[SB_WARPS][SB_MAX_RANKS];            // next output position of every bucket, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gw = blockIdx.x * SB_WARPS + warp;
@@ -180,8 +180,12 @@ shard_bucket_scatter_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t c
     if (have) pos = s_run[warp][owner] + (uint32_t)__popc(peers & ((1u << lane) - 1u));
     __syncwarp();
     if (have) {
-      slots_out[pos] = (uint32_t)(first_slot + q);
-      ids_out[pos] = c_loc;
+      if (ids_out == nullptr) {
+        reinterpret_cast<uint2*>(slots_out)[pos] = make_uint2((uint32_t)(first_slot + q), c_loc);
+      } else {
+        slots_out[pos] = (uint32_t)(first_slot + q);
+        ids_out[pos] = c_loc;
+      }
       if ((peers >> lane) == 1u) s_run[warp][owner] = pos + 1u;   // the highest peer lane advances the bucket
     }
     __syncwarp();
@@ -289,6 +293,25 @@ extern "C" int mccb200_scatter_rows(const float* in, int ld, const uint32_t* slo
   return check_launch("scatter_rows");
 }
 
+// slots[q] = pairs[q].x, ids[q] = pairs[q].y  (the receive side of the id exchange: one packed all-to-all)
+__global__ void __launch_bounds__(256)
+unzip_pairs_kernel(const uint2* __restrict__ pairs, uint64_t n, uint32_t* __restrict__ slots, uint32_t* __restrict__ ids) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint2 v = __ldcs(pairs + q);
+    slots[q] = v.x;
+    ids[q] = v.y;
+  }
+}
+
+extern "C" int mccb200_unzip_pairs(const uint32_t* pairs, uint64_t n, uint32_t* slots, uint32_t* ids, void* stream) {
+  MCCB_REQUIRE((pairs && slots && ids) || n == 0, "unzip_pairs: NULL argument");
+  if (n == 0) return MCCB200_OK;
+  const int grid = (int)min((n + 255) / 256, (uint64_t)mccb::sm_count() * 8);
+  unzip_pairs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint2*)pairs, n, slots, ids);
+  mccb::count_launches(1);
+  return mccb::check_launch("unzip_pairs");
+}
+
 static uint32_t sb_warps(uint64_t n, uint64_t& chunk) {
   uint64_t warps = (uint64_t)sm_count() * 4 * SB_WARPS;
   chunk = (n + warps - 1) / warps;
@@ -309,7 +332,7 @@ extern "C" size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks) {
 extern "C" int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
                                         int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-  MCCB_REQUIRE(idx && slots_out && ids_out && counts_out && workspace, "shard_bucket_ids: NULL argument");
+  MCCB_REQUIRE(idx && slots_out && counts_out && workspace, "shard_bucket_ids: NULL argument");
   MCCB_REQUIRE(n_ranks >= 1 && n_ranks <= SB_MAX_RANKS && n_loc >= 1 && k >= 1, "shard_bucket_ids: bad shape");
   MCCB_REQUIRE(n_loc * (uint64_t)k <= 0x100000000ull, "shard_bucket_ids: n_loc * k exceeds 2^32 local child ids");
   MCCB_REQUIRE(first_slot + n <= 0x100000000ull, "shard_bucket_ids: slots exceed 32 bits");

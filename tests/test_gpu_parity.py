@@ -766,16 +766,20 @@ def test_sharded_owner_ids_emulated_ranks(dev, G, n_loc, d, x64):
     sh = ShardedMonteCarloStep(make(), terms, G)
     shards = [yt[r * n_loc:(r + 1) * n_loc].contiguous() for r in range(G)]
     bucketed = [sh.owner_ids_bucket(t0, n_loc, r, dev) for r in range(G)]
+    packed = [sh.owner_ids_bucket(t0, n_loc, r, dev, packed=True) for r in range(G)]
+    for (s_, i_, c_), (p_, c2_) in zip(bucketed, packed):     # the packed form holds the same pairs
+        assert torch.equal(p_[:, 0], s_) and torch.equal(p_[:, 1], i_) and torch.equal(c_, c2_)
+        s2_, i2_ = _lib.unzip_pairs(p_)
+        assert torch.equal(s2_, s_) and torch.equal(i2_, i_)
     counts = torch.stack([c for _, _, c in bucketed]).cpu().numpy()        # counts[src][owner]
     assert counts.sum() == n_tot and (counts.sum(1) == n_loc).all()
     mats = []
     for r in range(G):
-        ps, pi = [], []
+        pp = []
         for src in range(G):
             off = int(counts[src, :r].sum())
-            ps.append(bucketed[src][0][off:off + int(counts[src, r])])
-            pi.append(bucketed[src][1][off:off + int(counts[src, r])])
-        mats.append(sh.owner_ids_materialise(t0, t1, shards[r], r, torch.cat(ps), torch.cat(pi), counts))
+            pp.append(packed[src][0][off:off + int(counts[src, r])])
+        mats.append(sh.owner_ids_materialise(t0, t1, shards[r], r, torch.cat(pp), counts))
     outs, maps = [], []
     for r in range(G):
         y1, slots, _, _, _, recv_splits, keep = mats[r]
