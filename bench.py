@@ -424,8 +424,23 @@ def sharded_parity(dev, rank, world):
         ok["a2a"] = bool(torch.equal(sh_n.step(t0, t1, mine, rank), want_n[lo:hi]))
         y1, smap = sh_n.step_owner(t0, t1, mine, rank)
         ok["owner"] = bool(torch.equal(y1, want_n[smap.to(torch.int64)]))
-        y1, smap = sh_r.step_owner_ids(t0, t1, mine, rank)
+        y1, smap = sh_r.step_owner_ids(t0, t1, mine, rank, prefetch=False)
         ok["owner_ids"] = bool(torch.equal(y1, want_r[smap.to(torch.int64)]))
+        # three chained steps with the next step's ids prefetched through the copy engines (and through NCCL): every
+        # step must equal the single-device step on the concatenation of the shards it started from
+        for mode, dma in (("owner_ids_dma_chain", True), ("owner_ids_nccl_chain", False)):
+            sh_c = ShardedMonteCarloStep(mc_solver(True), terms, world)
+            cur, good = mine, True
+            ts = dfx.step_times(0.25, 0.25 + 3 * DT0, DT0, np.float32)
+            for (a_, b_) in ts[:3]:
+                parts = [torch.empty_like(cur) for _ in range(world)]
+                dist.all_gather(parts, cur)
+                ref, *_ = mc_solver(True).step(terms, a_, b_, torch.cat(parts), None, None, False)
+                cur, smap_c = sh_c.step_owner_ids(a_, b_, cur, rank, dma=dma)
+                good = good and bool(torch.equal(cur, ref[smap_c.to(torch.int64)]))
+            torch.cuda.synchronize()
+            sh_c.close()
+            ok[mode] = good
         # the slot maps of all ranks together are a permutation of the output slots
         allmaps = [torch.empty_like(smap) for _ in range(world)]
         dist.all_gather(allmaps, smap)
@@ -437,7 +452,7 @@ def sharded_parity(dev, rank, world):
         pull_x = sh_x.step_pull(t0, t1, rank, shards).clone()
         full_x = [torch.empty_like(pull_x) for _ in range(world)]
         dist.all_gather(full_x, pull_x)
-        y1, smap = sh_x.step_owner_ids(t0, t1, mine, rank)
+        y1, smap = sh_x.step_owner_ids(t0, t1, mine, rank, prefetch=False)
         ok["owner_ids_x64"] = bool(torch.equal(y1, torch.cat(full_x)[smap.to(torch.int64)]))
         # global Box + PRK partition over the shards
         per = 16
@@ -505,6 +520,9 @@ def sharded_global_mc(dev, rank, world, steps=5):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[name] = {"ms_per_step": float(ms) / steps, "particle_steps_per_sec": n_tot * steps / (float(ms) * 1e-3)}
         del ys
+        if name == "step_owner_ids":
+            torch.cuda.synchronize()
+            sh.close()
     # the headline kernel pair with ONE global partition over all ranks' particles (the reference's partition of
     # the concatenated state; the headline value uses a partition per rank): counts + ranks per rank, two tiny
     # collectives, fused expand + scatter into the owners' shards over NVLink
@@ -600,6 +618,8 @@ def sharded_global_mc(dev, rank, world, steps=5):
             "id_exchange_bytes_per_rank_per_step": int(n_loc5 * 8 * (world - 1) / world),
             "note": "2^34 implicit children, int64 index draw; (slot, child id) pairs exchanged, rows stay with their parents"}
         del y5, smap5
+        torch.cuda.synchronize()
+        sh5.close()
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["config5_n2^27_d64_step_owner_ids"] = {"error": repr(e)}

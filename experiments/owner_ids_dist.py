@@ -33,20 +33,34 @@ def main():
     times = dfx.step_times(0.0, 0.05 * 40, 0.05, np.float32)
     y = torch.randn((n_loc, d), device=dev)
     res = {}
-    for prefetch in (False, True):
+    for prefetch, dma in ((False, False), (True, False), (True, True)):
         yy = y
         for i in range(3):
-            yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=prefetch)
+            yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=prefetch, dma=dma)
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tic = time.perf_counter()
         e0.record()
         for i in range(3, 13):
-            yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=prefetch)
+            yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=prefetch, dma=dma)
         e1.record()
         torch.cuda.synchronize()
-        res[f"prefetch={prefetch}"] = {"gpu_ms_per_step": e0.elapsed_time(e1) / 10, "wall_ms_per_step": (time.perf_counter() - tic) * 100}
+        res[f"prefetch={prefetch},dma={dma}"] = {"gpu_ms_per_step": e0.elapsed_time(e1) / 10, "wall_ms_per_step": (time.perf_counter() - tic) * 100}
         sh._ids_ready = None
+        torch.cuda.synchronize()
+    # timeline of three steady-state steps in the copy-engine mode (ms since the first event)
+    yy = y
+    for i in range(3):
+        yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=True, dma=True)
+    sh._trace = []
+    for i in range(3, 6):
+        yy, _ = sh.step_owner_ids(times[i][0], times[i][1], yy, rank, prefetch=True, dma=True)
+    torch.cuda.synchronize()
+    base = sh._trace[0][1]
+    res["timeline_ms"] = [(lab, round(base.elapsed_time(ev), 3)) for lab, ev in sh._trace]
+    sh._trace = None
+    sh._ids_ready = None
+    sh.close()
     # phases, no prefetch
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -60,8 +74,7 @@ def main():
     allc = [torch.empty_like(counts_dev) for _ in range(world)]
     dist.all_gather(allc, counts_dev); counts = torch.stack(allc).cpu().numpy(); mark("all_gather+host sync")
     recv = exchange_rows(pairs, [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]]); mark("all_to_all ids")
-    slots, ids = _lib.unzip_pairs(recv); mark("unzip")
-    out = sh.owner_ids_materialise(t0, t1, y, rank, slots, ids, counts); mark("materialise (gather)")
+    out = sh.owner_ids_materialise(t0, t1, y, rank, recv, counts); mark("materialise (gather)")
     torch.cuda.synchronize()
     res["phases_gpu_ms"] = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
     res["phases_host_ms"] = {marks[i][0]: (marks[i][2] - marks[i - 1][2]) * 1e3 for i in range(1, len(marks))}

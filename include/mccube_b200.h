@@ -152,6 +152,13 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
 MCCB200_API int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                               const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
                                               uint64_t n_out, float* y1, void* stream);
+/* Residency of the gather kernels launched by THIS thread from now on: at most `ctas_per_sm` CTAs per SM (1..8; 0
+ * restores the default, which fills the SM).  A gather that leaves a quarter of every SM free lets the index draw and
+ * the bucketing of the next step run under it (mccube_b200/_distributed.py::step_owner_ids). */
+MCCB200_API void mccb200_set_expand_residency(int ctas_per_sm);
+/* The counterpart for the kernels meant to run UNDER such a gather (index draw with replacement, id bucketing): at
+ * most `ctas_per_sm` CTAs per SM (0 = default grids). */
+MCCB200_API void mccb200_set_side_residency(int ctas_per_sm);
 MCCB200_API int mccb200_expand_select_substeps(const float* y0, uint64_t n, int d, const mccb200_drift* drift,
                                                int n_substeps, const float* dts_host, const float* scales_host,
                                                int k, const uint32_t* idx, uint64_t n_out, float* y1, void* stream);
@@ -362,6 +369,15 @@ MCCB200_API size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks);
 MCCB200_API int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
                                          int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
                                          void* workspace, size_t workspace_bytes, void* stream);
+/* The same with every owner's group in its own fixed-capacity region (group g starts at entry g * region_cap; 0 = back to
+ * back): regions of a known size can be pushed to their owners with plain device-to-device copies before any count
+ * is known on the host.  The caller checks counts_out[g] <= region_cap afterwards. */
+MCCB200_API int mccb200_shard_bucket_ids_regions(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot,
+                                                 uint64_t n_loc, int k, int n_ranks, uint64_t region_cap,
+                                                 uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
+                                                 void* workspace, size_t workspace_bytes, void* stream);
+/* cudaMemcpyAsync(dst, src, bytes, DeviceToDevice) on `stream`; dst may be a peer mapping (mccb200_peer_open). */
+MCCB200_API int mccb200_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 MCCB200_API int mccb200_unzip_pairs(const uint32_t* pairs /*[n][2]*/, uint64_t n, uint32_t* slots, uint32_t* ids, void* stream);
 MCCB200_API int mccb200_compact_slots(const uint32_t* idx_slots, uint64_t n_slots, uint32_t* list, uint64_t capacity,
                                       uint32_t* cursor, void* stream);

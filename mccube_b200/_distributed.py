@@ -184,6 +184,63 @@ class PeerShards:
         self.local = []
 
 
+class PeerIdBuffers:
+    """Receive side of the copy-engine id exchange: per rank, two (ping-pong) buffers of G fixed-capacity regions of
+    (slot, id) pairs -- region `src` is written by rank `src` -- and a [G, G] counts matrix, all mapped into every
+    other rank's address space (CUDA IPC, as `PeerShards`).  Plus a local staging buffer of the same shape."""
+
+    def __init__(self, n_loc: int, rank: int, world: int, device, group=None):
+        import math
+
+        from . import _lib
+
+        self.rank, self.world, self.group = rank, world, group
+        mean = n_loc / world
+        self.cap = int(mean + 8.0 * math.sqrt(mean) + 1024)           # 8 sigma of the binomial group size
+        self.cap = (self.cap + 63) // 64 * 64
+        words = 2 * world * self.cap                                   # int32 words of one pairs buffer
+        self.stage = torch.empty((world * self.cap, 2), dtype=torch.int32, device=device)
+        self.stage_counts = torch.empty(world, dtype=torch.int32, device=device)
+        self.local = [_lib.peer_alloc((words + world * world,), device) for _ in range(2)]   # pairs | counts matrix
+        handles = [_lib.peer_export(t) for t in self.local]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.opened, self.base = [], []
+        for b in range(2):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(self.local[b].data_ptr())
+                else:
+                    ptr = _lib.peer_open(gathered[r][b], device)
+                    self.opened.append(ptr)
+                    row.append(ptr)
+            self.base.append(row)
+        self.words = words
+        self.flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.host_counts = [torch.empty((world, world), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        self.turn = 0
+
+    def pairs(self, b: int) -> torch.Tensor:
+        return self.local[b][:self.words].view(torch.int32).view(self.world * self.cap, 2)
+
+    def counts(self, b: int) -> torch.Tensor:
+        return self.local[b][self.words:].view(torch.int32).view(self.world, self.world)
+
+    def close(self):
+        from . import _lib
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for ptr in self.opened:
+            _lib.peer_close(ptr)
+        self.opened = []
+        dist.barrier(group=self.group)
+        for t in self.local:
+            _lib.peer_free(t)
+        self.local = []
+
+
 class ShardedMonteCarloStep:
     """One MCCSolver step with a GLOBAL MonteCarloKernel resample over row-sharded particles.
 
@@ -415,41 +472,160 @@ class ShardedMonteCarloStep:
         counts = torch.stack(allc).cpu().numpy()
         return exchange_rows(pairs, [int(c) for c in counts[rank]], [int(c) for c in counts[:, rank]], group), counts
 
-    def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None, prefetch: bool = True):
+    # ---- the same exchange through the copy engines: fixed-capacity regions pushed into peer memory
+    def _dma_launch(self, t, n_loc: int, rank: int, device, pib: PeerIdBuffers, b: int):
+        """Draw + bucket into fixed-capacity regions + one device-to-device copy per peer (region `owner` of the
+        staging buffer -> region `rank` of the owner's receive buffer `b`, and this rank's counts row into every
+        peer's counts matrix).  Copy engines over NVLink: nothing here needs an SM once the two kernels are done,
+        and nothing waits on the host."""
+        from . import _lib
+
+        kernel = self.solver.recombination_kernel
+        G = self.n_ranks
+        n_tot = n_loc * G
+        k = self.terms.cde.control.gaussian_cubature.point_count
+        import os
+
+        with _lib.side_residency(int(os.environ.get("MCCB200_IDS_SIDE_CTAS", "0"))):   # (co-residency knobs: measured no gain, see profiles/README.md)
+            idx = kernel.indices_slice(t, n_tot * k, n_tot, rank * n_loc, n_loc, device)
+            _lib.shard_bucket_regions(idx, rank * n_loc, n_loc, k, G, pib.cap, pib.stage, pib.stage_counts)
+        for o in range(G):
+            _lib.peer_copy(pib.base[b][o] + 8 * pib.cap * rank, pib.stage[o * pib.cap:], 8 * pib.cap)
+            _lib.peer_copy(pib.base[b][o] + 4 * pib.words + 4 * G * rank, pib.stage_counts, 4 * G)
+
+    def _dma_seal(self, pib: PeerIdBuffers, b: int, after: "torch.cuda.Event"):
+        """Cross-rank barrier (every rank's pushes into buffer `b` have landed; every rank is done reading the
+        buffer the NEXT pushes will overwrite: `after` = this rank's gather) + the counts matrix to pinned host
+        memory.  Returns the event the next step waits for."""
+        side = torch.cuda.current_stream()
+        side.wait_event(after)
+        dist.all_reduce(pib.flag, group=self._ids_group)
+        pib.host_counts[b].copy_(pib.counts(b), non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(side)
+        return event
+
+    def _materialise_regions(self, t0, t1, y_shard, rank: int, pib: PeerIdBuffers, b: int, counts):
+        """`owner_ids_materialise` reading the G receive regions of buffer `b` in place (sender order)."""
+        import numpy as np
+
+        from . import _lib
+
+        solver = self.solver
+        n_loc, d = y_shard.shape
+        G = self.n_ranks
+        drift, cub, dt, k, _ = solver._describe(self.terms, y_shard, *solver.substep_times(t0, t1)[0], None)
+        counts = np.asarray(counts, dtype=np.int64)
+        per_owner = counts.sum(axis=0)
+        transfers = plan_rebalance(per_owner, n_loc)
+        total = int(per_owner[rank])
+        keep = min(total, n_loc)
+        n_give = total - keep
+        pairs = pib.pairs(b)
+        y1 = torch.empty((n_loc, d), dtype=torch.float32, device=y_shard.device)
+        slot_map = torch.empty(n_loc, dtype=torch.int32, device=y_shard.device)
+        send_rows = y1.new_empty((n_give, d))
+        send_slots = torch.empty(n_give, dtype=torch.int32, device=y_shard.device)
+        pos = 0
+        for src in range(G):
+            c = int(counts[src, rank])
+            first = src * pib.cap
+            n1 = max(0, min(c, keep - pos))
+            if n1:
+                _lib.expand_select_pairs(y_shard, d, drift, dt, cub, pairs, n_out=n1, out=y1[pos:pos + n1], first=first)
+                _lib.unzip_slots_(pairs, first, n1, slot_map[pos:pos + n1])
+            if c - n1:
+                sp = pos + n1 - keep
+                _lib.expand_select_pairs(y_shard, d, drift, dt, cub, pairs, n_out=c - n1, out=send_rows[sp:sp + c - n1],
+                                         first=first + n1)
+                _lib.unzip_slots_(pairs, first + n1, c - n1, send_slots[sp:sp + c - n1])
+            pos += c
+        return (y1, slot_map, send_rows, send_slots, [int(c) for c in transfers[rank]],
+                [int(c) for c in transfers[:, rank]], keep)
+
+    def step_owner_ids(self, t0, t1, y_shard: torch.Tensor, rank: int, group=None, prefetch: bool = True, dma=None):
         """One step with a GLOBAL `MonteCarloKernel(with_replacement=True)` resample in which no parent row and
         (up to the binomial imbalance) no child row crosses the link: ranks exchange 8 bytes per output row --
         (slot, child id) -- and every rank materialises the selected children of its OWN parents with the local
         fused gather.  Works with 64-bit global child ids (`kernel.x64`, BASELINE config 5: 2^34 children) in
         O(n_loc) memory per rank.  The index vector depends on (key, t) only, so with `prefetch` the draw, the
         bucketing and the id exchange of the NEXT step (outer time t1) are issued on a high-priority side stream
-        and a second communicator before this step's HBM-bound gather is enqueued, and run under it.  Returns
+        before this step's HBM-bound gather and run under it: with `dma` (default when prefetching) the pairs go
+        into fixed-capacity regions that the copy engines push into the owners' memory (no collective, no host
+        synchronisation until the next step starts) and the gather leaves a quarter of every SM to the draw and
+        bucketing kernels; otherwise through an all-gather of counts and one variable NCCL all-to-all.  Returns
         (y1_shard, slot_map): y1_shard[q] is row slot_map[q] of the single-device step on the concatenated state
         (same multiset, known permutation)."""
+        import os
+
+        from . import _lib
+
         G = self.n_ranks
         y_shard = y_shard.contiguous()
         n_loc, d = y_shard.shape
         dev = y_shard.device
         main = torch.cuda.current_stream(dev)
+        if dma is None:
+            dma = os.environ.get("MCCB200_IDS_DMA", "1") != "0"
+        use_dma = bool(prefetch and dma and G > 1)
         ready = getattr(self, "_ids_ready", None)
         self._ids_ready = None
+        regions = None
         if ready is not None and ready[0] == (float(t0), n_loc, rank):
-            _, event, recv_pairs, counts = ready
-            main.wait_event(event)
-            recv_pairs.record_stream(main)
+            if ready[1] == "dma":
+                _, _, event, b = ready
+                event.synchronize()                           # the step's one host wait: the counts matrix
+                counts = self._pib.host_counts[b].numpy().copy()
+                if int(counts.max()) <= self._pib.cap:
+                    regions = b
+                else:                                         # a group outgrew its region (8 sigma): redo through NCCL
+                    recv_pairs, counts = self._ids_finish(self._ids_launch(t0, n_loc, rank, dev, group), rank, group)
+            else:
+                _, _, event, recv_pairs, counts = ready
+                main.wait_event(event)
+                recv_pairs.record_stream(main)
         else:
             recv_pairs, counts = self._ids_finish(self._ids_launch(t0, n_loc, rank, dev, group), rank, group)
+        trace = getattr(self, "_trace", None)                 # experiments: [(label, event)] with timing events
+
+        def mark(label, stream):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((label, ev))
+
+        mark("step_begin(main)", main)
         launched = side = None
         if prefetch and G > 1:
             if getattr(self, "_ids_group", None) is None:     # its own communicator: independent of the data path's
                 self._ids_group = dist.new_group(list(range(G))) if group is None else group
                 self._ids_stream = torch.cuda.Stream(device=dev, priority=-1)   # its CTAs go ahead of the gather's
             side = self._ids_stream
+            if use_dma and (getattr(self, "_pib", None) is None or self._pib_n_loc != n_loc):
+                if getattr(self, "_pib", None) is not None:
+                    self._pib.close()
+                self._pib, self._pib_n_loc = PeerIdBuffers(n_loc, rank, G, dev, self._ids_group), n_loc
             with torch.cuda.stream(side):
-                launched = self._ids_launch(t1, n_loc, rank, dev, self._ids_group)
-        y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
-            t0, t1, y_shard, rank, recv_pairs, counts)
-        slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
-        slot_map[:keep] = slots
+                mark("prefetch_begin(side)", side)
+                if use_dma:
+                    nb = self._pib.turn
+                    self._pib.turn ^= 1
+                    self._dma_launch(t1, n_loc, rank, dev, self._pib, nb)
+                else:
+                    launched = self._ids_launch(t1, n_loc, rank, dev, self._ids_group)
+                mark("prefetch_launched(side)", side)
+        if regions is not None:
+            with _lib.expand_residency(int(os.environ.get("MCCB200_IDS_GATHER_CTAS", "0"))):   # (0 = default residency)
+                y1, slot_map, send_rows, send_slots, send_splits, recv_splits, keep = self._materialise_regions(
+                    t0, t1, y_shard, rank, self._pib, regions, counts)
+        else:
+            y1, slots, send_rows, send_slots, send_splits, recv_splits, keep = self.owner_ids_materialise(
+                t0, t1, y_shard, rank, recv_pairs, counts)
+            slot_map = torch.empty(n_loc, dtype=torch.int32, device=dev)
+            slot_map[:keep] = slots
+        gather_done = torch.cuda.Event()
+        gather_done.record(main)
+        mark("gather_done(main)", main)
         if G > 1 and (sum(send_splits) or sum(recv_splits)):
             # the surplus rows travel with their slot as one more column (its int32 bit pattern): one all-to-all
             packed = torch.empty((send_rows.shape[0], d + 1), dtype=torch.float32, device=dev)
@@ -459,13 +635,25 @@ class ShardedMonteCarloStep:
             if got.shape[0]:
                 y1[keep:keep + got.shape[0]] = got[:, :d]
                 slot_map[keep:keep + got.shape[0]] = got[:, d].contiguous().view(torch.int32)
-        if launched is not None:                              # the gather is enqueued: now the host may wait
+        if prefetch and G > 1:                                # the gather is enqueued: now the side stream may wait
             with torch.cuda.stream(side):
-                nxt = self._ids_finish(launched, rank, self._ids_group)
-                event = torch.cuda.Event()
-                event.record(side)
-            self._ids_ready = ((float(t1), n_loc, rank), event) + nxt
+                if use_dma:
+                    self._ids_ready = ((float(t1), n_loc, rank), "dma", self._dma_seal(self._pib, nb, gather_done), nb)
+                else:
+                    nxt = self._ids_finish(launched, rank, self._ids_group)
+                    event = torch.cuda.Event()
+                    event.record(side)
+                    self._ids_ready = ((float(t1), n_loc, rank), "nccl", event) + nxt
+                mark("prefetch_sealed(side)", side)
+        mark("step_end(main)", main)
         return y1, slot_map
+
+    def close(self):
+        """Frees the peer-mapped id buffers (collective: every rank calls it)."""
+        if getattr(self, "_pib", None) is not None:
+            self._pib.close()
+            self._pib = None
+        self._ids_ready = None
 
 
 class ShardedBoxStep:

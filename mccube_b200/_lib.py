@@ -81,6 +81,12 @@ _SIGNATURES = {
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_expand_select_strided": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
                                                C.POINTER(Cubature), C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "mccb200_shard_bucket_ids_regions": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                                  C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p]),
+    "mccb200_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_set_expand_residency": (None, [C.c_int]),
+    "mccb200_set_side_residency": (None, [C.c_int]),
     "mccb200_unzip_pairs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mccb200_compact_slots": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_enable_peer_access": (C.c_int, [C.c_int]),
@@ -817,6 +823,67 @@ def shard_bucket_ids(idx, first_slot, n_loc, k, n_ranks, packed: bool = False):
                                         int(k), int(n_ranks), slots.data_ptr(), _ptr(ids), counts.data_ptr(),
                                         ws.data_ptr(), ws.numel(), _stream()), "shard_bucket_ids")
     return (slots, counts) if packed else (slots, ids, counts)
+
+
+def shard_bucket_regions(idx, first_slot, n_loc, k, n_ranks, region_cap, out_pairs, out_counts):
+    """`shard_bucket_ids(packed=True)` with owner g's group written at out_pairs[g * region_cap :] (caller-provided
+    buffers: [n_ranks * region_cap, 2] int32 and [n_ranks] int32)."""
+    lib = load()
+    _require_cuda(idx, out_pairs, out_counts)
+    if idx.dtype not in (torch.int32, torch.uint32, torch.int64) or not idx.is_contiguous():
+        raise MccubeB200Error(f"shard_bucket_regions: expected a contiguous int32 / int64 index slice, got {idx.dtype}")
+    _i32c(out_pairs, "shard_bucket_regions pairs"); _i32c(out_counts, "shard_bucket_regions counts")
+    if out_pairs.numel() < 2 * n_ranks * region_cap or out_counts.numel() < n_ranks:
+        raise MccubeB200Error("shard_bucket_regions: output buffers too small")
+    nbytes = lib.mccb200_shard_bucket_ids_workspace_bytes(int(n_ranks))
+    ws = workspace(nbytes, idx.device)
+    _check(lib.mccb200_shard_bucket_ids_regions(idx.data_ptr(), int(idx.dtype == torch.int64), idx.numel(), int(first_slot),
+                                                int(n_loc), int(k), int(n_ranks), int(region_cap), out_pairs.data_ptr(),
+                                                None, out_counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+           "shard_bucket_ids_regions")
+
+
+def peer_copy(dst_ptr: int, src: torch.Tensor, nbytes: int):
+    """cudaMemcpyAsync D2D of the first `nbytes` bytes of `src` to the (possibly peer-mapped) address `dst_ptr`."""
+    _require_cuda(src)
+    _check(load().mccb200_peer_copy(int(dst_ptr), src.data_ptr(), int(nbytes), _stream()), "peer_copy")
+
+
+class expand_residency:
+    """`with expand_residency(3): ...` -- the gather kernels launched inside leave a quarter of every SM free."""
+
+    def __init__(self, ctas_per_sm: int):
+        self.ctas = int(ctas_per_sm)
+
+    def __enter__(self):
+        load().mccb200_set_expand_residency(self.ctas)
+
+    def __exit__(self, *exc):
+        load().mccb200_set_expand_residency(0)
+
+
+class side_residency:
+    """`with side_residency(1): ...` -- the index-draw and id-bucketing kernels launched inside use one CTA per SM, so
+    that they fit beside a gather running under `expand_residency(3)`."""
+
+    def __init__(self, ctas_per_sm: int):
+        self.ctas = int(ctas_per_sm)
+
+    def __enter__(self):
+        load().mccb200_set_side_residency(self.ctas)
+
+    def __exit__(self, *exc):
+        load().mccb200_set_side_residency(0)
+
+
+def unzip_slots_(pairs, first: int, count: int, out):
+    """out[:count] = pairs[first : first + count, 0]  (the slot column of packed (slot, id) pairs)."""
+    lib = load()
+    _require_cuda(pairs, out)
+    _i32c(pairs, "unzip_slots"); _i32c(out, "unzip_slots out")
+    _check(lib.mccb200_unzip_pairs(pairs.data_ptr() + 8 * int(first), int(count), out.data_ptr(), None, _stream()),
+           "unzip_pairs")
+    return out
 
 
 def unzip_pairs(pairs):

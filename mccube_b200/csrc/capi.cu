@@ -57,6 +57,9 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+static thread_local int g_side_ctas = 0;
+int side_ctas() { return g_side_ctas; }
+
 int sm_count() {
   static thread_local int cached_dev = -1;
   static thread_local int cached = 0;
@@ -73,6 +76,9 @@ int sm_count() {
 
 }  // namespace mccb
 
+extern "C" void mccb200_set_side_residency(int ctas_per_sm) {
+  mccb::g_side_ctas = ctas_per_sm < 0 ? 0 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+}
 extern "C" int mccb200_version(void) { return MCCB200_VERSION; }
 extern "C" const char* mccb200_last_error(void) { return mccb::g_err; }
 extern "C" int mccb200_sm_count(void) { return mccb::sm_count(); }

@@ -14,7 +14,8 @@ void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
-int env_int(const char* name, int dflt);   // experiment knobs (read once per call site)
+int env_int(const char* name, int dflt);
+int side_ctas();   // > 0: CTAs per SM for the index-draw / bucketing kernels launched by this thread (see mccb200_set_side_residency)   // experiment knobs (read once per call site)
 void count_launches(int n);
 void phase_mark(const char* name, cudaStream_t st);  // no-op unless mccb200_profile_enable(1)  // kernels / device copies enqueued by this library (bench.py gpu_launches)
 

@@ -312,6 +312,11 @@ namespace mccb { int run_expand_select(ExpandArgs& a, cudaStream_t st); }
 
 static int run_expand(ExpandArgs& a, cudaStream_t st) { return mccb::run_expand_select(a, st); }
 
+static thread_local int g_expand_residency = 0;
+extern "C" void mccb200_set_expand_residency(int ctas_per_sm) {
+  g_expand_residency = ctas_per_sm < 0 ? 0 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+}
+
 int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
   if (a.n_out == 0) return MCCB200_OK;
   int vec = a.weighted ? 1 : pick_vec(a.d, a.ld, a.y0, a.y1);
@@ -323,8 +328,14 @@ int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
   a.rows_per_iter = EX_THREADS / a.vpr;
   uint64_t rows_per_cta = (uint64_t)a.rows_per_iter * EX_UNROLL;
   uint64_t want = (a.n_out + rows_per_cta - 1) / rows_per_cta;
-  const int ctas_per_sm = env_int("MCCB200_EXPAND_CTAS", 8);
-  const int pad_smem = env_int("MCCB200_EXPAND_SMEM_PAD", 0);
+  int ctas_per_sm = env_int("MCCB200_EXPAND_CTAS", 8);
+  int pad_smem = env_int("MCCB200_EXPAND_SMEM_PAD", 0);
+  if (g_expand_residency > 0) {      // one persistent wave of `residency` CTAs per SM, enforced by a shared-memory pad
+    ctas_per_sm = g_expand_residency;
+    pad_smem = (int)((220u * 1024u / (unsigned)g_expand_residency) & ~1023u);
+    if (pad_smem > 99 * 1024 && g_expand_residency > 1) pad_smem = 99 * 1024;
+    if (g_expand_residency >= 4) pad_smem = 0;
+  }
   int grid = (int)min(want, (uint64_t)sm_count() * ctas_per_sm);
   phase_mark(a.idx ? "expand_select" : "expand_all", st);
   if (vec == 4) launch_expand<4>(a, grid, st, pad_smem);

@@ -423,7 +423,7 @@ extern "C" int mccb200_mc_indices_slice(const mccb200_rng* rng, uint64_t n_input
   DerivedKeys* dk = (DerivedKeys*)((char*)workspace + p.off_dk);
   phase_mark("mc_indices", st);
   derive_keys_kernel<<<1, 32, 0, st>>>(*rng, 0, dk);
-  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * 8);
+  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * (side_ctas() > 0 ? side_ctas() : 8));
   randint_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, (uint32_t)n_inputs, rng->partitionable, idx_out,
                                        (uint32_t)first, (uint32_t)slice);
   phase_mark("end", st);
@@ -447,7 +447,7 @@ extern "C" int mccb200_mc_indices_slice64(const mccb200_rng* rng, uint64_t n_inp
   DerivedKeys* dk = (DerivedKeys*)workspace;
   phase_mark("mc_indices", st);
   derive_keys_kernel<<<1, 32, 0, st>>>(*rng, 0, dk);
-  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * 8);
+  int grid = (int)min((uint64_t)(slice + 255) / 256, (uint64_t)sm_count() * (side_ctas() > 0 ? side_ctas() : 8));
   randint64_kernel<<<grid, 256, 0, st>>>(dk, (uint32_t)count, n_inputs, rng->partitionable, idx_out, (uint32_t)first,
                                          (uint32_t)slice);
   phase_mark("end", st);

@@ -120,12 +120,18 @@ shard_bucket_count_kernel(const IdxT* __restrict__ idx, uint64_t n, uint64_t chu
 // hist[g][w] (bucket-major) -> exclusive prefix in (bucket, warp) order = where warp w's entries of bucket g start;
 // counts[g] = bucket totals.  One CTA, 1024 threads, coalesced passes.
 __global__ void __launch_bounds__(1024)
-shard_bucket_scan_kernel(uint32_t* __restrict__ hist, uint32_t n_warps, int G, uint32_t* __restrict__ counts) {
+shard_bucket_scan_kernel(uint32_t* __restrict__ hist, uint32_t n_warps, int G, uint32_t region_cap,
+                         uint32_t* __restrict__ counts) {
   __shared__ uint32_t wtot[32];
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0u;
   __syncthreads();
   for (int g = 0; g < G; ++g) {
+    if (region_cap != 0u) {                                   // fixed-capacity regions: bucket g starts at g * cap
+      __syncthreads();
+      if (threadIdx.x == 0) carry_s = (uint32_t)g * region_cap;
+      __syncthreads();
+    }
     const uint32_t bucket_start = carry_s;
     for (uint32_t base = 0; base < n_warps; base += 1024) {
       const uint32_t i = base + threadIdx.x;
@@ -299,12 +305,12 @@ unzip_pairs_kernel(const uint2* __restrict__ pairs, uint64_t n, uint32_t* __rest
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
     const uint2 v = __ldcs(pairs + q);
     slots[q] = v.x;
-    ids[q] = v.y;
+    if (ids) ids[q] = v.y;
   }
 }
 
 extern "C" int mccb200_unzip_pairs(const uint32_t* pairs, uint64_t n, uint32_t* slots, uint32_t* ids, void* stream) {
-  MCCB_REQUIRE((pairs && slots && ids) || n == 0, "unzip_pairs: NULL argument");
+  MCCB_REQUIRE((pairs && slots) || n == 0, "unzip_pairs: NULL argument");   // ids may be NULL (slots only)
   if (n == 0) return MCCB200_OK;
   const int grid = (int)min((n + 255) / 256, (uint64_t)mccb::sm_count() * 8);
   unzip_pairs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint2*)pairs, n, slots, ids);
@@ -313,7 +319,7 @@ extern "C" int mccb200_unzip_pairs(const uint32_t* pairs, uint64_t n, uint32_t* 
 }
 
 static uint32_t sb_warps(uint64_t n, uint64_t& chunk) {
-  uint64_t warps = (uint64_t)sm_count() * 4 * SB_WARPS;
+  uint64_t warps = (uint64_t)sm_count() * (side_ctas() > 0 ? side_ctas() : 4) * SB_WARPS;
   chunk = (n + warps - 1) / warps;
   chunk = (chunk + 31) / 32 * 32;
   if (chunk == 0) chunk = 32;
@@ -325,6 +331,11 @@ extern "C" size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks) {
   return ((size_t)sm_count() * 4 * SB_WARPS + 1) * (size_t)n_ranks * sizeof(uint32_t);
 }
 
+extern "C" int mccb200_shard_bucket_ids_regions(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot,
+                                                uint64_t n_loc, int k, int n_ranks, uint64_t region_cap,
+                                                uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
+                                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* The send buffers of the id exchange (`ShardedMonteCarloStep.step_owner_ids`): `idx` = this rank's slice of the
  * global index vector (child ids, uint32 or uint64), output slot of entry q = first_slot + q.  slots_out[n] /
  * ids_out[n] = (slot, child id relative to the owner's first parent) grouped by owner rank = child / (n_loc * k),
@@ -332,7 +343,19 @@ extern "C" size_t mccb200_shard_bucket_ids_workspace_bytes(int n_ranks) {
 extern "C" int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot, uint64_t n_loc,
                                         int k, int n_ranks, uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
                                         void* workspace, size_t workspace_bytes, void* stream) {
+  return mccb200_shard_bucket_ids_regions(idx, idx_is_64, n, first_slot, n_loc, k, n_ranks, 0, slots_out, ids_out,
+                                          counts_out, workspace, workspace_bytes, stream);
+}
+
+/* The same with every owner's group written to its own fixed-capacity region: group g starts at entry g * region_cap
+ * (region_cap = 0: groups back to back).  A group larger than region_cap spills into the next region: the caller must
+ * check counts_out[g] <= region_cap before using the regions (and fall back to the back-to-back form otherwise). */
+extern "C" int mccb200_shard_bucket_ids_regions(const void* idx, int idx_is_64, uint64_t n, uint64_t first_slot,
+                                                uint64_t n_loc, int k, int n_ranks, uint64_t region_cap,
+                                                uint32_t* slots_out, uint32_t* ids_out, uint32_t* counts_out,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
   MCCB_REQUIRE(idx && slots_out && counts_out && workspace, "shard_bucket_ids: NULL argument");
+  MCCB_REQUIRE(region_cap * (uint64_t)n_ranks < 0x100000000ull, "shard_bucket_ids: regions exceed 32-bit positions");
   MCCB_REQUIRE(n_ranks >= 1 && n_ranks <= SB_MAX_RANKS && n_loc >= 1 && k >= 1, "shard_bucket_ids: bad shape");
   MCCB_REQUIRE(n_loc * (uint64_t)k <= 0x100000000ull, "shard_bucket_ids: n_loc * k exceeds 2^32 local child ids");
   MCCB_REQUIRE(first_slot + n <= 0x100000000ull, "shard_bucket_ids: slots exceed 32 bits");
@@ -353,15 +376,28 @@ extern "C" int mccb200_shard_bucket_ids(const void* idx, int idx_is_64, uint64_t
   uint32_t* hist = (uint32_t*)workspace;
   if (idx_is_64) {
     shard_bucket_count_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, own, n_ranks, n_warps, hist);
-    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, counts_out);
+    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, (uint32_t)region_cap, counts_out);
     shard_bucket_scatter_kernel<uint64_t><<<grid, SB_THREADS, 0, st>>>((const uint64_t*)idx, n, chunk, first_slot, own,
                                                                         n_ranks, n_warps, hist, slots_out, ids_out);
   } else {
     shard_bucket_count_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, own, n_ranks, n_warps, hist);
-    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, counts_out);
+    shard_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_warps, n_ranks, (uint32_t)region_cap, counts_out);
     shard_bucket_scatter_kernel<uint32_t><<<grid, SB_THREADS, 0, st>>>((const uint32_t*)idx, n, chunk, first_slot, own,
                                                                         n_ranks, n_warps, hist, slots_out, ids_out);
   }
   count_launches(3);
   return check_launch("shard_bucket_ids");
+}
+
+/* Device-to-device copy on `stream`, `dst` possibly a peer mapping (mccb200_peer_open): one cudaMemcpyAsync, served by
+ * the copy engines over NVLink, so it runs under kernels that occupy every SM. */
+extern "C" int mccb200_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  MCCB_REQUIRE((dst && src) || bytes == 0, "peer_copy: NULL argument");
+  if (bytes == 0) return MCCB200_OK;
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(MCCB200_ERR_CUDA, "peer_copy: cudaMemcpyAsync failed");
+  }
+  count_launches(1);
+  return MCCB200_OK;
 }
