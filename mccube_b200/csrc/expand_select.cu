@@ -214,12 +214,23 @@ gather_kernel(const float* __restrict__ in, int ld, int vpr, int rows_per_iter, 
   }
 }
 
+// Sum of the weight column (one 4-byte word every `ld` floats: a sector per row) with eight independent loads in
+// flight per thread, then y[:, -1] /= sum.  The divide pass re-reads the sectors the sum pass left in L2 when the
+// column fits there.  (Round 1: one load in flight per thread, 188 GB/s-equivalent; now bound by sectors per second.)
 __global__ void __launch_bounds__(256)
 weight_sum_kernel(const float* __restrict__ y, uint64_t n, int ld, double* __restrict__ out) {
   __shared__ double red[8];
   double acc = 0.0;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
-    acc += (double)y[r * ld + (ld - 1)];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; r + 7 * stride < n; r += 8 * stride) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ld_strided(y + (r + u * stride) * ld + (ld - 1));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+  }
+  for (; r < n; r += stride) acc += (double)ld_strided(y + r * ld + (ld - 1));
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -233,8 +244,16 @@ weight_sum_kernel(const float* __restrict__ y, uint64_t n, int ld, double* __res
 __global__ void __launch_bounds__(256)
 weight_div_kernel(float* __restrict__ y, uint64_t n, int ld, const double* __restrict__ total) {
   const float s = (float)*total;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
-    y[r * ld + (ld - 1)] = __fdiv_rn(y[r * ld + (ld - 1)], s);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; r + 7 * stride < n; r += 8 * stride) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = y[(r + u * stride) * ld + (ld - 1)];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) y[(r + u * stride) * ld + (ld - 1)] = __fdiv_rn(v[u], s);
+  }
+  for (; r < n; r += stride) y[r * ld + (ld - 1)] = __fdiv_rn(y[r * ld + (ld - 1)], s);
 }
 
 static int pick_vec(int d, int ld, const void* p0, const void* p1) {
@@ -497,7 +516,7 @@ extern "C" int mccb200_normalise_weights(float* y, uint64_t n, int ld, double* w
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(workspace, 0, sizeof(double), st) != cudaSuccess)
     return fail(MCCB200_ERR_CUDA, "normalise_weights: memset failed");
-  int grid = (int)min((n + 255) / 256, (uint64_t)sm_count() * 8);
+  int grid = (int)min((n + 2047) / 2048, (uint64_t)sm_count() * 8);
   if (grid < 1) grid = 1;
   weight_sum_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);
   weight_div_kernel<<<grid, 256, 0, st>>>(y, n, ld, workspace);

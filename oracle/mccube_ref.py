@@ -301,7 +301,15 @@ class PartitioningRecombinationKernel:
 
     def __call__(self, t, particles, args=None, weighted=False):
         parts = self.partitioning_kernel(t, particles, args, weighted)        # [m, P/m, d]
-        rec = np.stack([self.recombination_kernel(t, q, args, weighted) for q in parts])
+        rk = self.recombination_kernel
+        uniform = not (weighted and getattr(rk, "weighting_function", None) is not None)
+        if isinstance(rk, MonteCarloKernel) and uniform:
+            # quirk Q4: the vmapped kernel closes over ONE key, so the index vector is the same for every
+            # partition -- draw it once (what XLA's vmap does), not m times
+            idx = rk.indices(t, parts.shape[1])
+            rec = parts[:, idx]
+        else:
+            rec = np.stack([rk(t, q, args, weighted) for q in parts])
         return rec.reshape(-1, particles.shape[-1])
 
 

@@ -104,3 +104,49 @@ def test_monte_carlo_config3_size_with_replacement(dev):
     centre = yp + (float(dt) * ((2.0 - yp) * (1.0 / 3.0)))
     resid = (y1[sample] - centre).abs()
     assert float((resid - float(cub.scale)).abs().max()) < 1e-5
+
+
+def test_config4_full_covariance_step_full_size(dev):
+    """BASELINE config 4 at its FULL size (n = 2^20, d = 512, k = 1024: 2^30 implicit children): the tcgen05
+    drift and the fused step, checked on sampled rows against float64.  Tolerances: drift rows within 1e-5 RELATIVE
+    to each row's own norm-scale (max |F_row|), states within 1e-5 relative (the north-star bar)."""
+    n, d = 1 << 20, 512
+    rs = np.random.default_rng(1)
+    am = rs.normal(size=(d, d))
+    cov = am @ am.T / d + np.eye(d)
+    mu = rs.normal(size=d) * 2.0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    y0 = torch.randn((n, d), generator=gen, device=dev) * 1.5 + torch.tensor(mu, dtype=torch.float32, device=dev)
+    drift = mccube.GaussianFullDrift(mu, cov, device=dev)
+    f = drift(0.0, y0)
+    assert drift.last_path == "tcgen05:3xtf32"
+    rows = torch.arange(0, n, 1237, device=dev)                      # 848 sampled rows
+    ys = y0[rows].cpu().numpy().astype(np.float64)
+    prec = drift.prec.cpu().numpy().astype(np.float64)
+    want = -(ys - drift.mean.cpu().numpy().astype(np.float64)) @ prec
+    got = f[rows].cpu().numpy().astype(np.float64)
+    row_scale = np.abs(want).max(axis=1, keepdims=True)
+    assert (np.abs(got - want) <= 1e-5 * row_scale).all(), float((np.abs(got - want) / row_scale).max())
+    # one whole step: global MonteCarloKernel with replacement, drift handed over as an array
+    terms = mccube.MCCTerm(
+        dfx.ODETerm(drift),
+        dfx.WeaklyDiagonalControlTerm(lambda t, y, args: math.sqrt(2.0),
+                                      mccube.LocalLinearCubaturePath(mccube.Hadamard(mccube.GaussianRegion(d)))))
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, True, key=42))
+    t0, t1 = np.float32(0.05), np.float32(0.1)
+    y1, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    k = 1024
+    idx = (_lib.mc_indices(_lib.make_rng((0, 42), t0), n * k, n, True, dev).to(torch.int64) & 0xFFFFFFFF)[rows]
+    parent, point = (idx // k).cpu().numpy(), (idx % k).cpu().numpy()
+    yp = y0[torch.as_tensor(parent, device=dev)].cpu().numpy().astype(np.float64)
+    fp = -(yp - drift.mean.cpu().numpy().astype(np.float64)) @ prec
+    dt = float(np.float32(t1) - np.float32(t0))     # quirk Q1 shifts the interval, not its length
+    scale = float(np.float32(np.float32(math.sqrt(2.0)) * np.float32(math.sqrt(np.float32(dt)))))
+    cols = np.arange(d)
+    half = k // 2 - 1
+    par = np.array([[bin(int(j) & half & int(c)).count("1") & 1 for c in cols] for j in point])
+    sign = 1.0 - 2.0 * (par ^ (point[:, None] > half))
+    want1 = yp + dt * fp + scale * sign
+    got1 = y1[rows].cpu().numpy().astype(np.float64)
+    assert np.abs(got1 - want1).max() <= 1e-5 * np.abs(want1).max()
