@@ -70,7 +70,9 @@ rs_histogram(const uint32_t* __restrict__ keys, uint64_t count, int shift, uint3
 
 // --- exclusive scan of `len` uint32 entries: chunk sums -> scan of sums -> apply.
 __global__ void __launch_bounds__(256)
-rs_scan_reduce(const uint32_t* __restrict__ table, uint64_t len, uint32_t* __restrict__ sums) {
+rs_scan_reduce(const uint32_t* __restrict__ table, uint64_t len, uint32_t* __restrict__ sums,
+               const uint32_t* __restrict__ guard = nullptr) {
+  if (guard && *guard == 0u) return;               // guarded launch: see rng_select.cu
   __shared__ uint32_t red[8];
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK;
   uint32_t acc = 0;
@@ -89,7 +91,8 @@ rs_scan_reduce(const uint32_t* __restrict__ table, uint64_t len, uint32_t* __res
 }
 
 __global__ void __launch_bounds__(1024)
-rs_scan_sums(uint32_t* __restrict__ sums, uint32_t n_sums) {
+rs_scan_sums(uint32_t* __restrict__ sums, uint32_t n_sums, const uint32_t* __restrict__ guard = nullptr) {
+  if (guard && *guard == 0u) return;
   // single CTA, sequential over 1024-wide slabs
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry_s;
@@ -125,7 +128,9 @@ rs_scan_sums(uint32_t* __restrict__ sums, uint32_t n_sums) {
 }
 
 __global__ void __launch_bounds__(256)
-rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __restrict__ sums) {
+rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __restrict__ sums,
+              const uint32_t* __restrict__ guard = nullptr) {
+  if (guard && *guard == 0u) return;
   // exclusive scan inside a chunk of SCAN_CHUNK = 256 threads x 16 consecutive entries
   __shared__ uint32_t warp_tot[8];
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * 16;
@@ -499,6 +504,20 @@ int sort_pairs_impl(const uint32_t* keys_in, const uint32_t* vals_in, uint64_t c
 }
 
 size_t sort_pairs_ws(uint64_t count) { return make_plan(count).total; }
+
+// In-place exclusive scan of `len` uint32 entries (the three scan kernels above); `sums` = ceil(len / SCAN_CHUNK) words.
+size_t scan_u32_ws(uint64_t len) { return align_up(((len + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * sizeof(uint32_t), 256); }
+// `guard`: nullptr, or a device flag that must be non-zero for the scan to happen.
+int scan_u32_exclusive(uint32_t* data, uint64_t len, void* ws, cudaStream_t st, const uint32_t* guard) {
+  if (len == 0) return MCCB200_OK;
+  const uint32_t n_chunks = (uint32_t)((len + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  uint32_t* sums = (uint32_t*)ws;
+  rs_scan_reduce<<<n_chunks, 256, 0, st>>>(data, len, sums, guard);
+  rs_scan_sums<<<1, 1024, 0, st>>>(sums, n_chunks, guard);
+  rs_scan_apply<<<n_chunks, 256, 0, st>>>(data, len, sums, guard);
+  count_launches(3);
+  return check_launch("scan_u32");
+}
 
 // ---- first `top` entries of the stable sort, top << count (the last round of jax.random._shuffle
 // feeds permutation(...)[:n]): one stable pass on the MOST significant byte over everything, then

@@ -16,6 +16,10 @@ int sort_pairs_impl(const uint32_t*, const uint32_t*, uint64_t, int, uint32_t*, 
 size_t sort_pairs_ws(uint64_t);
 bool sort_pairs_top_worthwhile(uint64_t count, uint64_t top);
 size_t sort_pairs_top_ws(uint64_t count, uint64_t top);
+size_t mc_select_ws(uint64_t n_inputs, uint64_t count);
+bool mc_select_worthwhile(uint64_t n_inputs, uint64_t count);
+int mc_select_impl(const DerivedKeys* dk, int rounds, int partitionable, uint64_t n_inputs, uint64_t count,
+                   uint32_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sort_pairs_top_impl(const uint32_t*, const uint32_t*, uint64_t, uint64_t, uint32_t*, void*, size_t, cudaStream_t);
 
 __global__ void derive_keys_kernel(mccb200_rng rng, int rounds, DerivedKeys* out) {
@@ -314,6 +318,8 @@ static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
     size_t sw = sort_pairs_ws(n_inputs);
     if (count >= 1 && sort_pairs_top_worthwhile(n_inputs, count)) sw = max(sw, sort_pairs_top_ws(n_inputs, count));
     cur += sw;
+    if (mc_select_worthwhile(n_inputs, count))      // the selection path lays its own scratch over everything after dk
+      cur = max(cur, align_up(sizeof(DerivedKeys), 256) + mc_select_ws(n_inputs, count));
   }
   p.total = cur;
   return p;
@@ -378,6 +384,14 @@ extern "C" int mccb200_mc_indices(const mccb200_rng* rng, uint64_t n_inputs, uin
     iota_kernel<<<1, 256, 0, st>>>((uint32_t)count, idx_out);
     count_launches(2);
     return check_launch("mc_indices(identity)");
+  }
+  const bool use_select = env_int("MCCB200_SHUFFLE_SELECT", 1) != 0;   // (0: the radix-sort shuffle, kept for tests)
+  if (use_select && mc_select_worthwhile(n_inputs, count)) {
+    const size_t off = align_up(sizeof(DerivedKeys), 256);
+    int rc = mc_select_impl(dk, p.rounds, rng->partitionable, n_inputs, count, idx_out, w + off, p.total - off, st);
+    phase_mark("end", st);
+    count_launches(1);
+    return rc;
   }
   uint32_t* keys = (uint32_t*)(w + p.off_keys);
   uint32_t* va = (uint32_t*)(w + p.off_va);

@@ -737,6 +737,37 @@ def test_sharded_pull_gather_emulated_ranks(dev):
         mccube.MonteCarloKernel(n_tot, False, key=42).indices_slice(t0, n_tot * k, n_tot, 0, n_loc, dev)
 
 
+@pytest.mark.parametrize("n_inputs,count", [(1 << 16, 1 << 11), (100003, 25000), (1 << 20, 1 << 15), (3_000_017, 9), (1 << 22, 1 << 20)])
+@pytest.mark.parametrize("partitionable", [False, True])
+def test_shuffle_by_selection_equals_sort_shuffle(dev, monkeypatch, n_inputs, count, partitionable):
+    """`permutation[:count]` by rank selection (rng_select.cu) against the full multi-round radix-sort shuffle, and
+    against the oracle's restatement of jax.random._shuffle where that is quick."""
+    rng = _lib.make_rng((0, 42), np.float32(0.35), partitionable=partitionable)
+    monkeypatch.setenv("MCCB200_SHUFFLE_SELECT", "1")
+    got = _lib.mc_indices(rng, n_inputs, count, False, dev)
+    monkeypatch.setenv("MCCB200_SHUFFLE_SELECT", "0")
+    want = _lib.mc_indices(rng, n_inputs, count, False, dev)
+    assert torch.equal(got, want)
+    assert torch.unique(got).numel() == count
+    if n_inputs <= (1 << 20):
+        key = jr.mc_step_key(jr.prng_key(42), np.float32(0.35), partitionable=partitionable)
+        ref = jr.choice_indices(key, n_inputs, count, False, partitionable=partitionable)
+        assert np.array_equal(got.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, ref)
+
+
+@pytest.mark.parametrize("n_inputs,count", [(1 << 18, 1 << 12), (1 << 22, 1 << 19)])
+def test_shuffle_by_selection_rerun_when_bucket_limit_too_small(dev, monkeypatch, n_inputs, count):
+    """The round processed first looks only at the leading buckets (they hold the `count` smallest keys); when that
+    limit is too small a device flag re-runs the round over all buckets.  Forced here with a limit of half the need."""
+    rng = _lib.make_rng((0, 7), np.float32(0.6))
+    monkeypatch.setenv("MCCB200_SHUFFLE_SELECT", "0")
+    want = _lib.mc_indices(rng, n_inputs, count, False, dev)
+    monkeypatch.setenv("MCCB200_SHUFFLE_SELECT", "1")
+    monkeypatch.setenv("MCCB200_SELECT_SHORT_LIMIT", "1")
+    got = _lib.mc_indices(rng, n_inputs, count, False, dev)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("G,n_loc,d,x64", [(4, 250, 12, False), (3, 333, 8, True), (8, 64, 64, True), (1, 100, 4, False)])
 def test_sharded_owner_ids_emulated_ranks(dev, G, n_loc, d, x64):
     """Id exchange + owner-computes (`step_owner_ids`): every rank draws only its own index slice, the ranks
