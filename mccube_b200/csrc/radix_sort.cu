@@ -136,12 +136,22 @@ rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __rest
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * 16;
   uint32_t v[16];
   uint32_t tsum = 0;
+  const bool vec = base + 16 <= len && (((uintptr_t)table) & 15) == 0;   // base is a multiple of 16 entries
+  if (vec) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    uint64_t g = base + i;
-    v[i] = g < len ? table[g] : 0u;
-    tsum += v[i];
+    for (int i = 0; i < 4; ++i) {
+      const uint4 t = reinterpret_cast<const uint4*>(table + base)[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint64_t g = base + i;
+      v[i] = g < len ? table[g] : 0u;
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tsum += v[i];
   uint32_t x = tsum;
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -152,6 +162,18 @@ rs_scan_apply(uint32_t* __restrict__ table, uint64_t len, const uint32_t* __rest
   uint32_t woff = 0;
   for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_tot[w];
   uint32_t run = sums[blockIdx.x] + woff + x - tsum;
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 t;
+      t.x = run; run += v[4 * i];
+      t.y = run; run += v[4 * i + 1];
+      t.z = run; run += v[4 * i + 2];
+      t.w = run; run += v[4 * i + 3];
+      reinterpret_cast<uint4*>(table + base)[i] = t;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     uint64_t g = base + i;

@@ -45,16 +45,18 @@ static SelShape sel_shape(uint64_t n_inputs, uint64_t count) {
   return s;
 }
 
-struct SelLayout { size_t off_hist, off_cursor, off_bitmap, off_scan, off_members, off_qs, off_qc, off_qr, off_q0, off_q1, off_flag, total; };
+struct SelLayout { size_t off_hist[2], off_scan[2], off_cursor, off_bitmap, off_members, off_qs, off_qc, off_qr, off_q0, off_q1, off_flag, total; };
 
 static SelLayout sel_layout(const SelShape& s) {
   SelLayout L{};
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t o = cur; cur += align_up(bytes, 256); return o; };
-  L.off_hist = take(((size_t)s.nb + 1) * 4);
+  for (int i = 0; i < 2; ++i) {                   // rounds alternate: the next round's counts are built on a side stream
+    L.off_hist[i] = take(((size_t)s.nb + 1) * 4);
+    L.off_scan[i] = take(scan_u32_ws((uint64_t)s.nb + 1));
+  }
   L.off_cursor = take((size_t)s.nb * 4);
   L.off_bitmap = take((size_t)(s.nb + 31) / 32 * 4);
-  L.off_scan = take(scan_u32_ws((uint64_t)s.nb + 1));
   L.off_members = take((size_t)s.n * 8);          // (key, position) of the members of queried buckets
   L.off_qs = take((size_t)s.count * 4);
   L.off_qc = take((size_t)s.count * 4);
@@ -252,18 +254,41 @@ sel_answer_kernel(SelShape s, const uint32_t* __restrict__ qs, const uint32_t* _
   }
 }
 
+// Side stream and events of the calling thread's current device (created once, kept for the life of the process).
+struct SelSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+
+static SelSide* sel_side() {
+  static thread_local SelSide sides[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SelSide& sd = sides[dev];
+  if (!sd.stream) {
+    if (cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) {
+      sd.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &sd;
+}
+
 // idx_out[q] = shuffle(key, arange(n))[q] for q < count.  `dk` holds the round keys (derive_keys_kernel).
 //
 // The round processed first asks for the ranks 0 .. count-1, i.e. for the `count` smallest keys: only the leading
 // buckets can hold them, so that round looks at `nbl` buckets chosen to hold count + 8 sigma keys, and is re-run over
 // all buckets, on the device (guarded launches, no host round trip), in the 1e-15 case the limit was too small.
+//
+// The bucket counts of a round do not depend on the queries: while the stream resolves round r (locate, scatter,
+// rank: latency-bound), a side stream builds the scanned counts of round r-1 (L2-atomic-bound) in the other buffer.
 int mc_select_impl(const DerivedKeys* dk, int rounds, int partitionable, uint64_t n_inputs, uint64_t count,
                    uint32_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const SelShape s = sel_shape(n_inputs, count);
   const SelLayout L = sel_layout(s);
   if (workspace_bytes < L.total) return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "mc_select: workspace %zu < %zu", workspace_bytes, L.total);
   char* w = (char*)workspace;
-  uint32_t* hist = (uint32_t*)(w + L.off_hist);
+  uint32_t* hists[2] = {(uint32_t*)(w + L.off_hist[0]), (uint32_t*)(w + L.off_hist[1])};
+  void* scans[2] = {w + L.off_scan[0], w + L.off_scan[1]};
   uint32_t* cursor = (uint32_t*)(w + L.off_cursor);
   uint32_t* bitmap = (uint32_t*)(w + L.off_bitmap);
   uint2* members = (uint2*)(w + L.off_members);
@@ -284,33 +309,58 @@ int mc_select_impl(const DerivedKeys* dk, int rounds, int partitionable, uint64_
   uint32_t nbl_first = nbl_first64 < s.nb ? (uint32_t)nbl_first64 : s.nb;
   // test hook: a limit that is certainly too small, to exercise the guarded re-run
   if (env_int("MCCB200_SELECT_SHORT_LIMIT", 0) != 0) nbl_first = (uint32_t)((double)s.count / per_bucket / 2.0) + 1u;
+  SelSide* side = env_int("MCCB200_SELECT_OVERLAP", 1) != 0 ? sel_side() : nullptr;
 
-  auto round_pass = [&](int r, const uint32_t* queries, uint32_t nbl, uint32_t* out, uint32_t* overflow,
-                        const uint32_t* guard) -> int {
-    const int grid_z = (int)min(((uint64_t)nbl + 256) / 256, (uint64_t)sms * 8);
-    sel_zero_kernel<<<grid_z, 256, 0, st>>>(hist, (size_t)nbl + 1, cursor, nbl, bitmap, ((size_t)nbl + 31) / 32, guard);
-    sel_hist_kernel<<<grid_n, 256, 0, st>>>(dk, r, s, nbl, partitionable, hist, guard);
-    int rc = scan_u32_exclusive(hist, (uint64_t)nbl + 1, w + L.off_scan, st, guard);
-    if (rc) return rc;
+  // scanned bucket counts of round r over the first nbl buckets, into hists[r & 1]
+  auto counts_pass = [&](int r, uint32_t nbl, const uint32_t* guard, cudaStream_t cs) -> int {
+    uint32_t* hist = hists[r & 1];
+    const int grid_z = (int)min(((uint64_t)nbl + 256) / 256, (uint64_t)sms * 4);
+    sel_zero_kernel<<<grid_z, 256, 0, cs>>>(hist, (size_t)nbl + 1, nullptr, 0, nullptr, 0, guard);
+    sel_hist_kernel<<<grid_n, 256, 0, cs>>>(dk, r, s, nbl, partitionable, hist, guard);
+    count_launches(2);
+    return scan_u32_exclusive(hist, (uint64_t)nbl + 1, scans[r & 1], cs, guard);
+  };
+  // queries -> answers of round r, given its scanned counts
+  auto resolve_pass = [&](int r, const uint32_t* queries, uint32_t nbl, uint32_t* out, uint32_t* overflow,
+                          const uint32_t* guard) {
+    uint32_t* hist = hists[r & 1];
+    const int grid_z = (int)min(((uint64_t)nbl + 256) / 256, (uint64_t)sms * 4);
+    sel_zero_kernel<<<grid_z, 256, 0, st>>>(cursor, nbl, bitmap, ((size_t)nbl + 31) / 32, nullptr, 0, guard);
     sel_locate_kernel<<<grid_q, 256, 0, st>>>(queries, s, nbl, hist, qs, qc, qr, bitmap, overflow, guard);
     sel_scatter_kernel<<<grid_n, 256, 0, st>>>(dk, r, s, nbl, partitionable, bitmap, hist, cursor, members, guard);
     sel_answer_kernel<<<grid_w, 256, 0, st>>>(s, qs, qc, qr, members, out, guard);
-    count_launches(8);
-    return 0;
+    count_launches(4);
   };
 
   const uint32_t* queries = nullptr;               // round processed first: ranks 0 .. count-1
-  for (int r = rounds - 1; r >= 0; --r) {
+  const int first = rounds - 1;
+  const bool limited = nbl_first < s.nb;
+  int rc = counts_pass(first, limited ? nbl_first : s.nb, nullptr, st);
+  if (rc) return rc;
+  for (int r = first; r >= 0; --r) {
     uint32_t* out = r == 0 ? idx_out : qbuf[r & 1];
-    const bool first = r == rounds - 1;
-    if (first && nbl_first < s.nb) {
+    bool forked = false;
+    if (r > 0 && side) {                             // hists[(r - 1) & 1] is free: round r + 1 has been enqueued before
+      if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess)
+        return fail(MCCB200_ERR_CUDA, "mc_select: fork failed");
+      rc = counts_pass(r - 1, s.nb, nullptr, side->stream);
+      if (rc) return rc;
+      if (cudaEventRecord(side->join, side->stream) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "mc_select: join failed");
+      forked = true;
+    }
+    if (r == first && limited) {
       if (cudaMemsetAsync(flag, 0, 4, st) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "mc_select: memset failed");
-      int rc = round_pass(r, queries, nbl_first, out, flag, nullptr);
+      resolve_pass(r, queries, nbl_first, out, flag, nullptr);
+      rc = counts_pass(r, s.nb, flag, st);           // does nothing unless the limit was too small
       if (rc) return rc;
-      rc = round_pass(r, queries, s.nb, out, nullptr, flag);      // does nothing unless the limit was too small
-      if (rc) return rc;
+      resolve_pass(r, queries, s.nb, out, nullptr, flag);
     } else {
-      int rc = round_pass(r, queries, s.nb, out, nullptr, nullptr);
+      resolve_pass(r, queries, s.nb, out, nullptr, nullptr);
+    }
+    if (forked) {
+      if (cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return fail(MCCB200_ERR_CUDA, "mc_select: join failed");
+    } else if (r > 0) {
+      rc = counts_pass(r - 1, s.nb, nullptr, st);
       if (rc) return rc;
     }
     queries = out;
