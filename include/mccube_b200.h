@@ -152,6 +152,17 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
 MCCB200_API int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                               const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
                                               uint64_t n_out, float* y1, void* stream);
+/* MonteCarloKernel(with_replacement=True) and the expand step in ONE kernel (replaces mccube/_kernels/random.py:45-66
+ * followed by the gather of mccube/_solvers.py:117-142): output row r is child
+ * jr.choice(key_at(t), n * k, (n_out,), replace=True)[r], the 32-bit randint drawn inside the kernel, so the index
+ * vector never exists in HBM (idx_out, optional, receives it).  Unweighted states with d / 4 a power of two in
+ * 4 .. 32 (ask mccb200_expand_select_draw_supported); n * k < 2^32 - 1. */
+MCCB200_API size_t mccb200_expand_select_draw_workspace_bytes(void);
+MCCB200_API int mccb200_expand_select_draw_supported(int d, int ld, int weighted);
+MCCB200_API int mccb200_expand_select_draw(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                           const mccb200_cubature* cub, const mccb200_rng* rng, uint64_t n_out,
+                                           float* y1, uint32_t* idx_out, void* workspace, size_t workspace_bytes,
+                                           void* stream);
 /* Residency of the gather kernels launched by THIS thread from now on: at most `ctas_per_sm` CTAs per SM (1..8; 0
  * restores the default, which fills the SM).  A gather that leaves a quarter of every SM free lets the index draw and
  * the bucketing of the next step run under it (mccube_b200/_distributed.py::step_owner_ids). */

@@ -79,6 +79,11 @@ _SIGNATURES = {
     "mccb200_shard_bucket_ids_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mccb200_shard_bucket_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_expand_select_draw_workspace_bytes": (C.c_size_t, []),
+    "mccb200_expand_select_draw_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "mccb200_expand_select_draw": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                             C.POINTER(Cubature), C.POINTER(Rng), C.c_uint64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]),
     "mccb200_expand_select_strided": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
                                                C.POINTER(Cubature), C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mccb200_shard_bucket_ids_regions": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
@@ -370,6 +375,29 @@ def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=No
     _check(lib.mccb200_expand_select(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
                                      C.byref(cub), idx.data_ptr(), _ptr(perm), out_per_part, in_per_part, n_out,
                                      out.data_ptr(), _stream()), "expand_select")
+    return out
+
+
+def expand_select_draw_supported(d: int, ld: int, weighted: bool) -> bool:
+    return bool(load().mccb200_expand_select_draw_supported(int(d), int(ld), int(weighted)))
+
+
+def expand_select_draw(y0, d, drift: Drift, dt, cub: Cubature, rng: Rng, n_out: int, out=None, idx_out=None):
+    """`MonteCarloKernel(with_replacement=True)` + expand in one kernel: the child ids are drawn inside the gather
+    (no index vector in HBM).  `idx_out` (int32 [n_out], optional) receives the drawn ids."""
+    lib = load()
+    _require_cuda(y0)
+    _f32c(y0)
+    n, ld = y0.shape
+    out = torch.empty((n_out, ld), dtype=torch.float32, device=y0.device) if out is None else out
+    if idx_out is not None:
+        _require_cuda(idx_out)
+        _i32c(idx_out, "expand_select_draw idx_out")
+    ws = workspace(lib.mccb200_expand_select_draw_workspace_bytes(), y0.device)
+    _check(lib.mccb200_expand_select_draw(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                          C.byref(rng), n_out, out.data_ptr(),
+                                          idx_out.data_ptr() if idx_out is not None else None, ws.data_ptr(), ws.numel(),
+                                          _stream()), "expand_select_draw")
     return out
 
 

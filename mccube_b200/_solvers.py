@@ -69,6 +69,7 @@ class MCCSolver(AbstractWrappedSolver):
         self.weighted = weighted
         self.time_dtype = np.dtype(time_dtype)
         self.fused = fused
+        self.fuse_draw = True   # with_replacement=True: draw the child ids inside the gather kernel when the shape allows
         self.last_path = None  # which implementation the last step took (for tests / bench)
         self._point_tables: dict = {}
         self.__check_init__()
@@ -172,9 +173,18 @@ class MCCSolver(AbstractWrappedSolver):
             yv = y0c[:, :-1] if self.weighted else y0c
             drift, cub, dt, k, d = self._describe(terms, yv, *times[0], args)
             n = y0c.shape[0]
-            idx = kernel.indices(t0, n * k, kernel.recombination_count, y0c.device)
-            y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
-            self.last_path = "fused:mc_indices+expand_select" + ("(weighted)" if self.weighted else "")
+            draw_in_kernel = (self.fuse_draw and kernel.with_replacement and not getattr(kernel, "x64", False)
+                              and n * k < 2 ** 32 - 1
+                              and _lib.expand_select_draw_supported(d, y0c.shape[1], self.weighted))
+            if draw_in_kernel:
+                # with_replacement=True draws are counter based: the gather kernel draws its own child ids
+                rng = _lib.make_rng(kernel.key, t0, partitionable=kernel.threefry_partitionable)
+                y1_hat = _lib.expand_select_draw(y0c, d, drift, dt, cub, rng, kernel.recombination_count)
+                self.last_path = "fused:expand_select_draw"
+            else:
+                idx = kernel.indices(t0, n * k, kernel.recombination_count, y0c.device)
+                y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
+                self.last_path = "fused:mc_indices+expand_select" + ("(weighted)" if self.weighted else "")
         elif self._substeps_fusable(terms, kernel, y0c):
             y1_hat = self._substeps_step(terms, t0, times, y0c, args, kernel)
         elif (fusable and type(kernel) is PartitioningRecombinationKernel

@@ -42,6 +42,13 @@ struct ExpandArgs {
   const float* keycols;   // optional [n, 4]: y0[:, c0 .. c0+3] of the 4 vectorised box key columns, packed
   float* keycols_out;     // optional [n_out, 4]: the same columns of y1, written by the expand kernel
   int keycol0;            // c0 of keycols_out
+  // Fused index draw (MonteCarloKernel(with_replacement=True), 32-bit randint): the child of output row r is
+  // jr.randint(k, (draw_count,), 0, draw_span)[draw_first + r], computed in the kernel -- no index vector in HBM.
+  const uint32_t* draw_keys;   // device: randint_hi.xy, randint_lo.xy of the step's DerivedKeys (nullptr = not fused)
+  uint32_t draw_count, draw_span, draw_first;
+  int draw_partitionable;
+  uint32_t* draw_idx_out;      // optional: the drawn ids, [n_out]
+  int vpr_shift;               // log2(vpr) when the draw is fused (vpr a power of two, 4 .. 32)
   int vpr;            // vectors per row = d / VEC
   int rows_per_iter;  // rows covered by one CTA pass = blockDim / vpr
 };

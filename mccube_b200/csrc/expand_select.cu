@@ -11,6 +11,7 @@
 // cannot contract into FMA:   y1 = y0 + (dt * f + noise).
 #include "common.cuh"
 #include "expand.cuh"
+#include "rng.cuh"
 
 namespace mccb {
 
@@ -66,14 +67,25 @@ __device__ __forceinline__ uint32_t child_of_row(const ExpandArgs& a, uint64_t r
   return a.idx ? a.idx[a.idx_stride > 1u ? r * a.idx_stride : r] : (uint32_t)r;
 }
 
+// jr.randint(key, (count,), 0, span)[i] for int32 (the arithmetic of randint_kernel, rng_indices.cu)
+__device__ __forceinline__ uint32_t draw_child(u32x2 k_hi, u32x2 k_lo, uint32_t i, uint32_t count, uint32_t span,
+                                               uint32_t mult, bool part) {
+  const uint32_t lo = random_bits32_at(k_lo, i, count, part);
+  if (mult == 0u) return (span & (span - 1u)) == 0u ? (lo & (span - 1u)) : (lo % span);
+  const uint32_t hi = random_bits32_at(k_hi, i, count, part);
+  return ((hi % span) * mult + (lo % span)) % span;
+}
+
 // MODE 0: plain (the hot path: nothing below costs it an instruction); 1: scatter to peer shards;
-// 2: fused sub-steps; 3: pull -- parents are read from the peer shard that owns them.
+// 2: fused sub-steps; 3: pull -- parents are read from the peer shard that owns them; 4: plain with the child ids
+// drawn in the kernel (one lane per output row runs the threefry block, the row's lanes fetch the id by shuffle).
 template <int VEC, int DRIFT, bool TABLE, int MODE = 0>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const ExpandArgs a) {
   constexpr bool SCATTER = MODE == 1;
   constexpr bool SUBSTEPS = MODE == 2;
   constexpr bool PULL = MODE == 3;
+  constexpr bool DRAW = MODE == 4;
   const int row_in_iter = threadIdx.x / a.vpr;
   const int col = (threadIdx.x - row_in_iter * a.vpr) * VEC;
   const bool active = row_in_iter < a.rows_per_iter;
@@ -95,6 +107,14 @@ expand_kernel(const ExpandArgs a) {
     load_vec<VEC>(a.inv_var + col, ivar);
   }
   const bool do_w = a.weighted && col == 0;
+  u32x2 dk_hi{}, dk_lo{};
+  uint32_t draw_mult = 0;
+  if (DRAW) {
+    dk_hi = {__ldg(a.draw_keys), __ldg(a.draw_keys + 1)};
+    dk_lo = {__ldg(a.draw_keys + 2), __ldg(a.draw_keys + 3)};
+    draw_mult = 65536u % a.draw_span;
+    draw_mult = (draw_mult * draw_mult) % a.draw_span;
+  }
 
   const uint64_t rows_per_cta_iter = (uint64_t)a.rows_per_iter * EX_UNROLL;
   for (uint64_t base = (uint64_t)blockIdx.x * rows_per_cta_iter; base < n_out;
@@ -103,11 +123,29 @@ expand_kernel(const ExpandArgs a) {
     uint64_t r[EX_UNROLL];
     bool ok[EX_UNROLL];
     uint32_t slot[EX_UNROLL];
+    uint32_t drawn = 0;
+    if (DRAW) {   // a warp holds 32 / vpr rows of every unroll slot: lane l draws for slot l / rpw, row l % rpw
+      const int lane = threadIdx.x & 31;
+      const int rpw_shift = 5 - a.vpr_shift;
+      const int u_l = lane >> rpw_shift, sub_l = lane & ((1 << rpw_shift) - 1);
+      if (u_l < EX_UNROLL) {
+        const uint64_t row = base + (uint64_t)u_l * a.rows_per_iter + ((threadIdx.x >> 5) << rpw_shift) + sub_l;
+        if (row < n_out) {
+          drawn = draw_child(dk_hi, dk_lo, a.draw_first + (uint32_t)row, a.draw_count, a.draw_span, draw_mult,
+                             a.draw_partitionable != 0);
+          if (a.draw_idx_out) a.draw_idx_out[row] = drawn;
+        }
+      }
+    }
 #pragma unroll
     for (int u = 0; u < EX_UNROLL; ++u) {
       r[u] = base + (uint64_t)u * a.rows_per_iter + row_in_iter;
       ok[u] = r[u] < n_out;
-      if (PULL && a.idx64 != nullptr) {                    // 64-bit global child id -> (global parent, point)
+      if (DRAW) {
+        const int lane = threadIdx.x & 31;
+        slot[u] = 0u;
+        c[u] = __shfl_sync(0xffffffffu, drawn, (u << (5 - a.vpr_shift)) + (lane >> a.vpr_shift));
+      } else if (PULL && a.idx64 != nullptr) {                    // 64-bit global child id -> (global parent, point)
         const uint64_t cg = ok[u] ? __ldg(a.idx64 + r[u]) : 0ull;
         slot[u] = (uint32_t)(cg >> a.k_shift);             // parent (n_tot < 2^32), decoded below
         c[u] = (uint32_t)(cg & (uint64_t)(a.k - 1u));
@@ -282,6 +320,16 @@ static void launch_expand(const ExpandArgs& a, int grid, cudaStream_t st, int pa
     else expand_kernel<VEC, 0, false, 2><<<grid, EX_THREADS, 0, st>>>(a);
     return;
   }
+  if (a.draw_keys) {  // fused index draw (VEC == 4 checked by the caller)
+    if constexpr (VEC == 4) {
+#define MCCB_LAUNCH_DRAW(D, T) expand_kernel<4, D, T, 4><<<grid, EX_THREADS, 0, st>>>(a)
+      if (a.drift_kind == 2) { if (table) MCCB_LAUNCH_DRAW(2, true); else MCCB_LAUNCH_DRAW(2, false); }
+      else if (a.drift_kind == 1) { if (table) MCCB_LAUNCH_DRAW(1, true); else MCCB_LAUNCH_DRAW(1, false); }
+      else { if (table) MCCB_LAUNCH_DRAW(0, true); else MCCB_LAUNCH_DRAW(0, false); }
+#undef MCCB_LAUNCH_DRAW
+    }
+    return;
+  }
 #define MCCB_LAUNCH(D, T) expand_kernel<VEC, D, T><<<grid, EX_THREADS, 0, st>>>(a)
   if (a.drift_kind == 2 && !table && pad_smem > 0) {   // residency cap (co-scheduling experiments)
     cudaFuncSetAttribute(expand_kernel<VEC, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem);
@@ -345,6 +393,13 @@ int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
   a.vpr = a.d / vec;
   MCCB_REQUIRE(a.vpr <= EX_THREADS, "expand: d=%d too wide for the row mapping", a.d);
   a.rows_per_iter = EX_THREADS / a.vpr;
+  if (a.draw_keys) {
+    int sh = 0;
+    while ((1 << sh) < a.vpr) ++sh;
+    if (vec != 4 || (1 << sh) != a.vpr || a.vpr < 4 || a.vpr > 32)
+      return fail(MCCB200_ERR_UNSUPPORTED, "expand_select_draw: d=%d (vectors per row %d) is outside the fused draw's shapes", a.d, a.vpr);
+    a.vpr_shift = sh;
+  }
   uint64_t rows_per_cta = (uint64_t)a.rows_per_iter * EX_UNROLL;
   uint64_t want = (a.n_out + rows_per_cta - 1) / rows_per_cta;
   int ctas_per_sm = env_int("MCCB200_EXPAND_CTAS", 8);
@@ -356,7 +411,7 @@ int mccb::run_expand_select(ExpandArgs& a, cudaStream_t st) {
     if (g_expand_residency >= 4) pad_smem = 0;
   }
   int grid = (int)min(want, (uint64_t)sm_count() * ctas_per_sm);
-  phase_mark(a.idx ? "expand_select" : "expand_all", st);
+  phase_mark(a.draw_keys ? "expand_select_draw" : a.idx ? "expand_select" : "expand_all", st);
   if (vec == 4) launch_expand<4>(a, grid, st, pad_smem);
   else if (vec == 2) launch_expand<2>(a, grid, st);
   else launch_expand<1>(a, grid, st);
@@ -380,6 +435,44 @@ extern "C" int mccb200_expand_select(const float* y0, uint64_t n, int d, int wei
     MCCB_REQUIRE(out_per_part < 0x100000000ull && in_per_part < 0x100000000ull, "expand_select: partition too large");
   }
   a.idx = idx; a.perm = perm; a.out_per_part = (uint32_t)out_per_part; a.in_per_part = (uint32_t)in_per_part;
+  a.n_out = n_out; a.y1 = y1;
+  return run_expand(a, (cudaStream_t)stream);
+}
+
+/* MonteCarloKernel(with_replacement=True) + expand in ONE kernel: output row r is child
+ * jr.choice(key_at(t), n * k, (n_out,), replace=True)[r] (32-bit randint) of the expanded set, the id drawn inside the
+ * kernel instead of being written to and re-read from HBM.  Shapes: unweighted, d a multiple of 4 with d / 4 a power of
+ * two in 4 .. 32 (mccb200_expand_select_draw_supported); idx_out (optional) receives the drawn ids.  workspace:
+ * mccb200_expand_select_draw_workspace_bytes().  Reference: mccube/_kernels/random.py:45-66 + _solvers.py:117-142. */
+extern "C" size_t mccb200_expand_select_draw_workspace_bytes(void) { return 256; }
+
+extern "C" int mccb200_expand_select_draw_supported(int d, int ld, int weighted) {
+  if (weighted || d <= 0 || d % 4 != 0 || ld % 4 != 0) return 0;
+  const int vpr = d / 4;
+  return (vpr & (vpr - 1)) == 0 && vpr >= 4 && vpr <= 32;
+}
+
+extern "C" int mccb200_expand_select_draw(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                          const mccb200_cubature* cub, const mccb200_rng* rng, uint64_t n_out, float* y1,
+                                          uint32_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, 0, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(rng && y1, "expand_select_draw: NULL rng / y1");
+  MCCB_REQUIRE(rng->n_leaves >= 1 && rng->leaf < rng->n_leaves, "expand_select_draw: bad leaf");
+  const uint64_t span = n * (uint64_t)cub->k;
+  MCCB_REQUIRE(span >= 1 && span < 0xFFFFFFFFull && n_out < 0xFFFFFFFFull, "expand_select_draw: sizes out of the 32-bit id range");
+  if (!workspace || workspace_bytes < 256)
+    return fail(MCCB200_ERR_WORKSPACE_TOO_SMALL, "expand_select_draw: workspace %zu < 256", workspace_bytes);
+  if (n_out == 0) return MCCB200_OK;
+  DerivedKeys* dk = (DerivedKeys*)workspace;
+  launch_derive_keys(*rng, 0, dk, (cudaStream_t)stream);
+  count_launches(1);
+  a.idx = nullptr; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
+  a.draw_keys = &dk->randint_hi.x;
+  a.draw_count = (uint32_t)n_out; a.draw_span = (uint32_t)span; a.draw_first = 0u;
+  a.draw_partitionable = rng->partitionable;
+  a.draw_idx_out = idx_out;
   a.n_out = n_out; a.y1 = y1;
   return run_expand(a, (cudaStream_t)stream);
 }

@@ -755,6 +755,40 @@ def test_shuffle_by_selection_equals_sort_shuffle(dev, monkeypatch, n_inputs, co
         assert np.array_equal(got.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, ref)
 
 
+@pytest.mark.parametrize("n,d,n_out,partitionable", [(1000, 16, 1000, False), (777, 64, 2001, False), (4096, 128, 4096, True),
+                                                    (513, 32, 100, True), (65536, 64, 65536, False), (1031, 64, 1031, False)])
+def test_expand_select_draw_equals_indices_then_expand(dev, n, d, n_out, partitionable):
+    """with_replacement=True: the gather kernel that draws its own child ids (no index vector in HBM) against the
+    two-kernel path (mc_indices, expand_select) and the oracle's randint restatement: same ids, same rows, bit for bit.
+    (65536 x 64 x k=128 gives the power-of-two span whose high draw drops out; 1031 a span that needs both draws.)"""
+    y, mean, inv_var = _setup(n, d, seed=5)
+    terms = _terms(d, mean, inv_var, dev)
+    yt = cuda(y, dev)
+    t0, t1 = np.float32(0.25), np.float32(0.3)
+    kern = mccube.MonteCarloKernel(n_out, True, key=42)
+    kern.threefry_partitionable = partitionable
+    solver = mccube.MCCSolver(dfx.Euler(), kern)
+    drift, cub, dt, k, _ = solver._describe(terms, yt, *solver.substep_times(t0, t1)[0], None)
+    idx = kern.indices(t0, n * k, n_out, dev)
+    want = _lib.expand_select(yt, d, False, drift, dt, cub, idx)
+    rng = _lib.make_rng(kern.key, t0, partitionable=partitionable)
+    idx_out = torch.empty(n_out, dtype=torch.int32, device=dev)
+    got = _lib.expand_select_draw(yt, d, drift, dt, cub, rng, n_out, idx_out=idx_out)
+    assert torch.equal(idx_out, idx)
+    assert torch.equal(got, want)
+    key = jr.mc_step_key(jr.prng_key(42), t0, partitionable=partitionable)
+    ref = jr.choice_indices(key, n * k, n_out, True, partitionable=partitionable)
+    assert np.array_equal(idx_out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, ref)
+    # the solver takes the fused path on its own, and says so
+    y1, *_ = solver.step(terms, t0, t1, yt, None, None, False)
+    assert solver.last_path == "fused:expand_select_draw"
+    assert torch.equal(y1, want)
+    solver.fuse_draw = False
+    y1b, *_ = solver.step(terms, t0, t1, yt, None, None, False)
+    assert solver.last_path.startswith("fused:mc_indices+expand_select") and torch.equal(y1b, want)
+    assert not _lib.expand_select_draw_supported(12, 12, False) and not _lib.expand_select_draw_supported(64, 65, True)
+
+
 @pytest.mark.parametrize("n_inputs,count", [(1 << 18, 1 << 12), (1 << 22, 1 << 19)])
 def test_shuffle_by_selection_rerun_when_bucket_limit_too_small(dev, monkeypatch, n_inputs, count):
     """The round processed first looks only at the leading buckets (they hold the `count` smallest keys); when that
