@@ -28,7 +28,7 @@ except ImportError:  # keeps the file importable for the text checks of tests/te
     jax = jnp = None
 
 _TARGETS = (
-    "mccb200_mc_indices_ffi", "mccb200_expand_select_ffi", "mccb200_expand_all_ffi", "mccb200_box_child_bounds_ffi",
+    "mccb200_mc_indices_ffi", "mccb200_expand_select_ffi", "mccb200_expand_select_draw_ffi", "mccb200_expand_all_ffi", "mccb200_box_child_bounds_ffi",
     "mccb200_box_prk_tables_ffi", "mccb200_box_prk_selection_ffi", "mccb200_box_prk_count_ffi",
     "mccb200_box_prk_rank_gather_ffi", "mccb200_box_prk_step_ffi", "mccb200_gaussian_full_drift_tc_prepare_ffi",
     "mccb200_gaussian_full_drift_tc_ffi", "mccb200_gaussian_full_drift_ffi", "mccb200_moments_sum_ffi",
@@ -92,6 +92,18 @@ def expand_select(y0, idx, k, dt, scale, drift_kind=0, weighted=False, f=None, m
     return jax.ffi.ffi_call("mccb200_expand_select_ffi", _f32(idx.shape[0], y0.shape[1]))(
         y0, *_drift_args(drift_kind, f, mean, inv_var), idx, drift_kind=np.int64(drift_kind),
         weighted=np.int64(weighted), k=np.int64(k), dt=np.float32(dt), scale=np.float32(scale))
+
+
+def expand_select_draw(y0, key, t, n_out, k, dt, scale, drift_kind=0, f=None, mean=None, inv_var=None):
+    """MonteCarloKernel(with_replacement=True) fused with the expansion: the child ids
+    jr.choice(step_key(key, t), n * k, (n_out,), replace=True) are drawn inside the gather kernel (random.py:45-66)."""
+    core = _load()
+    ws = core.mccb200_expand_select_draw_workspace_bytes()
+    y1, _ = jax.ffi.ffi_call("mccb200_expand_select_draw_ffi", (_f32(n_out, y0.shape[1]), _u8(ws)))(
+        y0, *_drift_args(drift_kind, f, mean, inv_var), jax.random.key_data(key).astype(jnp.uint32),
+        jnp.asarray(t, jnp.float32).reshape(1), drift_kind=np.int64(drift_kind), k=np.int64(k), dt=np.float32(dt),
+        scale=np.float32(scale), partitionable=np.int64(bool(jax.config.jax_threefry_partitionable)))
+    return y1
 
 
 def expand_all(y0, k, dt, scale, drift_kind=0, weighted=False, f=None, mean=None, inv_var=None):

@@ -89,6 +89,18 @@ ffi::Error ExpandSelectImpl(cudaStream_t s, F32 y0, F32 f, F32 mean, F32 inv_var
                                     idx.typed_data(), nullptr, 1, 1, (uint64_t)idx.element_count(), y1->typed_data(), s));
 }
 
+// ---- A1-A5 + A8 in one kernel: with_replacement=True child ids drawn inside the gather   (random.py:45-66)
+ffi::Error ExpandSelectDrawImpl(cudaStream_t s, F32 y0, F32 f, F32 mean, F32 inv_var, U32 key, F32 t, int64_t drift_kind,
+                                int64_t k, float dt, float scale, int64_t partitionable, Out<F32> y1, Out<U8> workspace) {
+  const auto dims = y0.dimensions();
+  const mccb200_drift drift = MakeDrift(drift_kind, f, mean, inv_var);
+  const mccb200_cubature cub = Hadamard(k, scale);
+  const mccb200_rng rng = MakeRng(key, t, 0, 1, partitionable);
+  return Fail(mccb200_expand_select_draw(y0.typed_data(), (uint64_t)dims[0], (int)dims[1], &drift, dt, &cub, &rng,
+                                         (uint64_t)y1->dimensions()[0], y1->typed_data(), nullptr,
+                                         workspace->typed_data(), workspace->size_bytes(), s));
+}
+
 // ---- generic path: the whole [n*k, ld] expansion (arbitrary kernels, weights)   (_solvers.py:132-141)
 ffi::Error ExpandAllImpl(cudaStream_t s, F32 y0, F32 f, F32 mean, F32 inv_var, int64_t drift_kind, int64_t weighted,
                          int64_t k, float dt, float scale, Out<F32> y1) {
@@ -239,6 +251,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_mc_indices_ffi, McIndicesImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_select_ffi, ExpandSelectImpl,
     MCCB_STREAM.Arg<F32>() MCCB_DRIFT_ARGS.Arg<U32>().Attr<int64_t>("drift_kind").Attr<int64_t>("weighted")
         .Attr<int64_t>("k").Attr<float>("dt").Attr<float>("scale").Ret<F32>(),
+    {ffi::Traits::kCmdBufferCompatible});
+XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_select_draw_ffi, ExpandSelectDrawImpl,
+    MCCB_STREAM.Arg<F32>() MCCB_DRIFT_ARGS.Arg<U32>().Arg<F32>().Attr<int64_t>("drift_kind").Attr<int64_t>("k")
+        .Attr<float>("dt").Attr<float>("scale").Attr<int64_t>("partitionable").Ret<F32>().Ret<U8>(),
     {ffi::Traits::kCmdBufferCompatible});
 XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_all_ffi, ExpandAllImpl,
     MCCB_STREAM.Arg<F32>() MCCB_DRIFT_ARGS.Attr<int64_t>("drift_kind").Attr<int64_t>("weighted").Attr<int64_t>("k")
