@@ -657,6 +657,39 @@ def sharded_global_mc(dev, rank, world, steps=5):
     return out
 
 
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pins this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers the e2e leg
+    allocates afterwards are first-touched on that GPU's NUMA node (one rank per GPU: every rank gets its own node-local
+    staging buffers).  Returns what was done, for the bench line."""
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:  # noqa: BLE001
+            info["numa_node"] = None
+        try:
+            gen, width = pynvml.nvmlDeviceGetCurrPcieLinkGeneration(h), pynvml.nvmlDeviceGetCurrPcieLinkWidth(h)
+            per_lane = {3: 0.985, 4: 1.969, 5: 3.938, 6: 7.563}.get(gen)
+            info["pcie"] = {"gen": gen, "width": width,
+                            "peak_GBps_each_way": round(per_lane * width, 1) if per_lane else None}
+        except Exception:  # noqa: BLE001
+            info["pcie"] = None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus), cpu_range=[min(cpus), max(cpus)])
+    except Exception as e:  # noqa: BLE001
+        info["error"] = repr(e)
+    return info
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -776,6 +809,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         Ke = max(1, min(a.e2e_steps, K))
+        host_numa = bind_to_gpu_numa(local)     # before the pinned allocations: first touch lands on the GPU's node
         host_in = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
         host_out = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
         host_in.copy_(y)
@@ -836,6 +870,10 @@ def main():
         e2e = {"value": world * n * Ke / (ms_e * 1e-3), "unit": "particle-steps/s", "steps": Ke,
                "ms_per_step": ms_e / Ke, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4,
                "mode": "host-resident batches pipelined over 3 streams (H2D i+1 | step i | D2H i-1)",
+               # the copies bound this leg: all ranks' H2D + D2H bytes over the timed region (each direction is half)
+               "copy_GBps_aggregate": world * 2 * n * d * 4 * Ke / (ms_e * 1e-3) / 1e9,
+               "copy_GBps_per_gpu_each_way": n * d * 4 * Ke / (ms_e * 1e-3) / 1e9,
+               "host_buffers": dict(host_numa, kind="pinned, allocated after binding the rank to its GPU's CPUs"),
                "one_call_at_a_time": {"ms_per_step": ms_serial, "value": world * n / (ms_serial * 1e-3), "steps": Ks}}
         del host_in, host_out, host_out2, yd2, y1
 

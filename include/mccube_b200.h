@@ -152,6 +152,17 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
 MCCB200_API int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                               const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
                                               uint64_t n_out, float* y1, void* stream);
+/* Median-split (KD) partitioner on the device: replaces the host callback of mccube/_kernels/tree.py:44-58 (sklearn
+ * KDTree / BallTree through jax.pure_callback).  idx_out[n] lists the rows of y [n, ld] (first d columns = coordinates)
+ * leaf by leaf: every level splits every node at its median ((end - start) / 2, as sklearn's _recursive_build) along
+ * the dimension of largest max - min.  The point SETS of the nodes equal sklearn's at the same depth; the order inside
+ * a leaf is sorted along the last split dimension (sklearn's is std::nth_element's, platform dependent).
+ * mccb200_kd_partition_levels(n, leaf_size) = floor(log2(n / leaf_size)): leaves of leaf_size .. 2 * leaf_size - 1
+ * points, one level deeper than sklearn's tree when n / leaf_size is a power of two. */
+MCCB200_API int mccb200_kd_partition_levels(uint64_t n, uint64_t leaf_size);
+MCCB200_API size_t mccb200_kd_partition_workspace_bytes(uint64_t n, int d, int levels);
+MCCB200_API int mccb200_kd_partition(const float* y, uint64_t n, int d, int ld, int levels, uint32_t* idx_out,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 /* MonteCarloKernel(with_replacement=True) and the expand step in ONE kernel (replaces mccube/_kernels/random.py:45-66
  * followed by the gather of mccube/_solvers.py:117-142): output row r is child
  * jr.choice(key_at(t), n * k, (n_out,), replace=True)[r], the 32-bit randint drawn inside the kernel, so the index

@@ -79,6 +79,10 @@ _SIGNATURES = {
     "mccb200_shard_bucket_ids_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mccb200_shard_bucket_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_kd_partition_levels": (C.c_int, [C.c_uint64, C.c_uint64]),
+    "mccb200_kd_partition_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
+    "mccb200_kd_partition": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]),
     "mccb200_expand_select_draw_workspace_bytes": (C.c_size_t, []),
     "mccb200_expand_select_draw_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mccb200_expand_select_draw": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
@@ -375,6 +379,23 @@ def expand_select(y0, d, weighted, drift: Drift, dt, cub: Cubature, idx, perm=No
     _check(lib.mccb200_expand_select(y0.data_ptr(), n, d, int(weighted), C.byref(drift), float(np.float32(dt)),
                                      C.byref(cub), idx.data_ptr(), _ptr(perm), out_per_part, in_per_part, n_out,
                                      out.data_ptr(), _stream()), "expand_select")
+    return out
+
+
+def kd_partition_levels(n: int, leaf_size: int) -> int:
+    return int(load().mccb200_kd_partition_levels(int(n), int(leaf_size)))
+
+
+def kd_partition(y, d: int, levels: int) -> torch.Tensor:
+    """Row indices of `y` [n, ld] ordered leaf by leaf of a `levels`-deep median-split tree on the first d columns."""
+    lib = load()
+    _require_cuda(y)
+    _f32c(y)
+    n, ld = y.shape
+    out = torch.empty(n, dtype=torch.int32, device=y.device)
+    ws = workspace(lib.mccb200_kd_partition_workspace_bytes(n, d, levels), y.device)
+    _check(lib.mccb200_kd_partition(y.data_ptr(), n, d, ld, levels, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+           "kd_partition")
     return out
 
 

@@ -1098,3 +1098,43 @@ def test_captured_solve_generic_path_and_refusal(dev):
     plain = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=1))
     assert torch.equal(dfx.capture_solve(terms, plain, 0.0, 0.2, 0.05, y0)(y0).ys,
                        dfx.diffeqsolve(terms, plain, 0.0, 0.2, 0.05, y0).ys)
+
+
+@pytest.mark.parametrize("n,d,leaf,weighted,mode", [(4096, 8, 64, False, "KDTree"), (1000, 5, 10, False, "BallTree"),
+                                                   (3000, 64, 100, True, "KDTree"), (1 << 16, 16, 64, False, "KDTree"),
+                                                   (777, 3, 7, False, "KDTree"), (512, 40, 512, False, "BallTree")])
+def test_device_median_split_partitioner_matches_sklearn_sets(dev, n, d, leaf, weighted, mode):
+    """`BinaryTreePartitioningKernel(device=True)`: the median-split tree built on the GPU holds, in every sklearn leaf's
+    range of idx_array, exactly the point set sklearn put there (reference: mccube/_kernels/tree.py:44-58 -> sklearn
+    _binary_tree.pxi _recursive_build); it is a permutation; and each of its own (one level deeper) leaves is split
+    from its sibling at the median of the widest dimension of their parent."""
+    from sklearn.neighbors import BallTree, KDTree
+
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal((n, d + (1 if weighted else 0))).astype(np.float32) * rng.uniform(0.5, 3.0, d + (1 if weighted else 0)).astype(np.float32)
+    yt = cuda(y, dev)
+    count = n // leaf
+    kern = mccube.BinaryTreePartitioningKernel(count, mode=mode, device=True)
+    idx = kern.indices(yt, count, weighted).cpu().numpy().reshape(-1)
+    assert np.array_equal(np.sort(idx), np.arange(n))
+    tree = {"KDTree": KDTree, "BallTree": BallTree}[mode](y[:, :d].astype(np.float64), leaf)
+    _, sk_idx, node_data, _ = tree.get_arrays()
+    leaves = [(int(nd["idx_start"]), int(nd["idx_end"])) for nd in node_data if nd["is_leaf"]]
+    assert sum(e - s for s, e in leaves) == n
+    for s, e in leaves:
+        assert set(idx[s:e].tolist()) == set(np.asarray(sk_idx[s:e]).tolist()), (s, e)
+    # the extra level: inside every sklearn leaf with >= 2 * leaf points, the halves are separated along the widest
+    # dimension of that leaf
+    levels = _lib.kd_partition_levels(n, leaf)
+    sk_levels = int(np.log2(max(1, (n - 1) // leaf)))
+    assert levels in (sk_levels, sk_levels + 1)
+    if levels == sk_levels + 1:
+        for s, e in leaves:
+            pts = y[idx[s:e], :d].astype(np.float64)
+            j = int(np.argmax(pts.max(0) - pts.min(0)))
+            mid = (e - s) // 2
+            assert pts[:mid, j].max() <= pts[mid:, j].min()
+    # the kernel call gathers the rows partition by partition
+    out = kern(np.float32(0.0), yt, None, weighted)
+    assert out.shape == (count, leaf, y.shape[1])
+    assert torch.equal(out.reshape(n, -1), yt[torch.from_numpy(idx.astype(np.int64)).to(dev)])
