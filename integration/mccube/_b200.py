@@ -28,7 +28,7 @@ except ImportError:  # keeps the file importable for the text checks of tests/te
     jax = jnp = None
 
 _TARGETS = (
-    "mccb200_mc_indices_ffi", "mccb200_expand_select_ffi", "mccb200_expand_select_draw_ffi", "mccb200_expand_all_ffi", "mccb200_box_child_bounds_ffi",
+    "mccb200_mc_indices_ffi", "mccb200_expand_select_ffi", "mccb200_expand_select_draw_ffi", "mccb200_kd_partition_ffi", "mccb200_expand_all_ffi", "mccb200_box_child_bounds_ffi",
     "mccb200_box_prk_tables_ffi", "mccb200_box_prk_selection_ffi", "mccb200_box_prk_count_ffi",
     "mccb200_box_prk_rank_gather_ffi", "mccb200_box_prk_step_ffi", "mccb200_gaussian_full_drift_tc_prepare_ffi",
     "mccb200_gaussian_full_drift_tc_ffi", "mccb200_gaussian_full_drift_ffi", "mccb200_moments_sum_ffi",
@@ -49,7 +49,8 @@ def _load():
     _core = ctypes.CDLL("libmccube_b200.so")
     for fn in ("mccb200_mc_indices_workspace_bytes", "mccb200_box_prk_step_workspace_bytes",
                "mccb200_box_prk_tables_bytes", "mccb200_box_prk_selection_bytes", "mccb200_box_bounds_workspace_bytes",
-               "mccb200_sort_pairs_workspace_bytes", "mccb200_gaussian_full_drift_tc_prepare_bytes"):
+               "mccb200_sort_pairs_workspace_bytes", "mccb200_gaussian_full_drift_tc_prepare_bytes",
+               "mccb200_expand_select_draw_workspace_bytes", "mccb200_kd_partition_workspace_bytes"):
         getattr(_core, fn).restype = ctypes.c_size_t
     return _core
 
@@ -104,6 +105,19 @@ def expand_select_draw(y0, key, t, n_out, k, dt, scale, drift_kind=0, f=None, me
         jnp.asarray(t, jnp.float32).reshape(1), drift_kind=np.int64(drift_kind), k=np.int64(k), dt=np.float32(dt),
         scale=np.float32(scale), partitionable=np.int64(bool(jax.config.jax_threefry_partitionable)))
     return y1
+
+
+def kd_partition(y, leaf_size, weighted=False):
+    """Drop-in for the `jax.pure_callback` into sklearn of BinaryTreePartitioningKernel (mccube/_kernels/tree.py:44-58):
+    idx[n // leaf_size, leaf_size] of a median-split tree built on the device (same node point sets as sklearn's)."""
+    core = _load()
+    n, ld = y.shape
+    d = ld - (1 if weighted else 0)
+    levels = core.mccb200_kd_partition_levels(ctypes.c_uint64(n), ctypes.c_uint64(leaf_size))
+    ws = core.mccb200_kd_partition_workspace_bytes(ctypes.c_uint64(n), d, levels)
+    idx, _ = jax.ffi.ffi_call("mccb200_kd_partition_ffi", (jax.ShapeDtypeStruct((n,), jnp.uint32), _u8(ws)))(
+        y, d=np.int64(d), levels=np.int64(levels))
+    return idx.reshape(-1, leaf_size)
 
 
 def expand_all(y0, k, dt, scale, drift_kind=0, weighted=False, f=None, mean=None, inv_var=None):

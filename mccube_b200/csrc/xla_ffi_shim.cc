@@ -101,6 +101,13 @@ ffi::Error ExpandSelectDrawImpl(cudaStream_t s, F32 y0, F32 f, F32 mean, F32 inv
                                          workspace->typed_data(), workspace->size_bytes(), s));
 }
 
+// ---- BinaryTreePartitioningKernel without the host callback   (mccube/_kernels/tree.py:44-58)
+ffi::Error KdPartitionImpl(cudaStream_t s, F32 y, int64_t d, int64_t levels, Out<U32> idx, Out<U8> workspace) {
+  const auto dims = y.dimensions();
+  return Fail(mccb200_kd_partition(y.typed_data(), (uint64_t)dims[0], (int)d, (int)dims[1], (int)levels,
+                                   idx->typed_data(), workspace->typed_data(), workspace->size_bytes(), s));
+}
+
 // ---- generic path: the whole [n*k, ld] expansion (arbitrary kernels, weights)   (_solvers.py:132-141)
 ffi::Error ExpandAllImpl(cudaStream_t s, F32 y0, F32 f, F32 mean, F32 inv_var, int64_t drift_kind, int64_t weighted,
                          int64_t k, float dt, float scale, Out<F32> y1) {
@@ -255,6 +262,9 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_select_ffi, ExpandSelectImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_select_draw_ffi, ExpandSelectDrawImpl,
     MCCB_STREAM.Arg<F32>() MCCB_DRIFT_ARGS.Arg<U32>().Arg<F32>().Attr<int64_t>("drift_kind").Attr<int64_t>("k")
         .Attr<float>("dt").Attr<float>("scale").Attr<int64_t>("partitionable").Ret<F32>().Ret<U8>(),
+    {ffi::Traits::kCmdBufferCompatible});
+XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_kd_partition_ffi, KdPartitionImpl,
+    MCCB_STREAM.Arg<F32>().Attr<int64_t>("d").Attr<int64_t>("levels").Ret<U32>().Ret<U8>(),
     {ffi::Traits::kCmdBufferCompatible});
 XLA_FFI_DEFINE_HANDLER_SYMBOL(mccb200_expand_all_ffi, ExpandAllImpl,
     MCCB_STREAM.Arg<F32>() MCCB_DRIFT_ARGS.Attr<int64_t>("drift_kind").Attr<int64_t>("weighted").Attr<int64_t>("k")
