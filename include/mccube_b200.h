@@ -152,6 +152,17 @@ MCCB200_API int mccb200_expand_select(const float* y0, uint64_t n, int d, int we
 MCCB200_API int mccb200_expand_select_strided(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
                                               const mccb200_cubature* cub, const uint32_t* idx, int idx_stride,
                                               uint64_t n_out, float* y1, void* stream);
+/* y_out = y_in with the weight column (last of ld) divided by its sum: the renormalised copy MCCSolver.step returns
+ * next to the raw y1 of dense_info (mccube/_solvers.py:146-155), in one streaming pass.  total: device double with the
+ * sum of the weights when a producer supplies it (mccb200_expand_select_wsum), NULL = summed here (workspace: one
+ * double). */
+MCCB200_API int mccb200_normalised_copy(const float* y_in, uint64_t n, int ld, const double* total, float* y_out,
+                                        double* workspace, void* stream);
+/* mccb200_expand_select (weighted = 1, no permutation) that also accumulates the sum of the child weights it writes
+ * into *wsum (device double, zeroed by the call). */
+MCCB200_API int mccb200_expand_select_wsum(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                           const mccb200_cubature* cub, const uint32_t* idx, uint64_t n_out, float* y1,
+                                           double* wsum, void* stream);
 /* Median-split (KD) partitioner on the device: replaces the host callback of mccube/_kernels/tree.py:44-58 (sklearn
  * KDTree / BallTree through jax.pure_callback).  idx_out[n] lists the rows of y [n, ld] (first d columns = coordinates)
  * leaf by leaf: every level splits every node at its median ((end - start) / 2, as sklearn's _recursive_build) along

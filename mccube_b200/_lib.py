@@ -79,6 +79,10 @@ _SIGNATURES = {
     "mccb200_shard_bucket_ids_workspace_bytes": (C.c_size_t, [C.c_int]),
     "mccb200_shard_bucket_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mccb200_normalised_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mccb200_expand_select_wsum": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Drift), C.c_float,
+                                             C.POINTER(Cubature), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
     "mccb200_kd_partition_levels": (C.c_int, [C.c_uint64, C.c_uint64]),
     "mccb200_kd_partition_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
     "mccb200_kd_partition": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -552,6 +556,34 @@ def normalise_weights_(y):
     _check(lib.mccb200_normalise_weights(y.data_ptr(), y.shape[0], y.shape[1], ws.data_ptr(), _stream()),
            "normalise_weights")
     return y
+
+
+def normalised_copy(y, total=None):
+    """A copy of `y` [n, ld] with the weight column divided by its sum (`total`: device float64 [1] holding that sum
+    when the producer already has it)."""
+    lib = load()
+    _require_cuda(y)
+    _f32c(y)
+    out = torch.empty_like(y)
+    ws = torch.empty(1, dtype=torch.float64, device=y.device)
+    _check(lib.mccb200_normalised_copy(y.data_ptr(), y.shape[0], y.shape[1], _ptr(total), out.data_ptr(), ws.data_ptr(),
+                                       _stream()), "normalised_copy")
+    return out
+
+
+def expand_select_wsum(y0, d, drift: Drift, dt, cub: Cubature, idx):
+    """Weighted expand_select that also returns the sum of the child weights (device float64 [1])."""
+    lib = load()
+    _require_cuda(y0, idx)
+    _f32c(y0)
+    _i32c(idx, "expand_select_wsum idx")
+    n, ld = y0.shape
+    out = torch.empty((idx.numel(), ld), dtype=torch.float32, device=y0.device)
+    wsum = torch.empty(1, dtype=torch.float64, device=y0.device)
+    _check(lib.mccb200_expand_select_wsum(y0.data_ptr(), n, d, C.byref(drift), float(np.float32(dt)), C.byref(cub),
+                                          idx.data_ptr(), idx.numel(), out.data_ptr(), wsum.data_ptr(), _stream()),
+           "expand_select_wsum")
+    return out, wsum
 
 
 def stratified_keys(p, d, com):

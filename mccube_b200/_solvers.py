@@ -164,6 +164,7 @@ class MCCSolver(AbstractWrappedSolver):
 
         fusable = (self.fused and self.n_substeps == 1 and not self.weighted)
         y1_hat = None
+        weight_total = None
         # weighted states with the default weighting_function=nop sample uniformly (quirk Q6): the fused
         # kernel carries the weight column along (child weight = w_parent * lambda, k-major quirk Q3)
         fusable_mc = (self.fused and self.n_substeps == 1 and type(kernel) is MonteCarloKernel
@@ -183,7 +184,10 @@ class MCCSolver(AbstractWrappedSolver):
                 self.last_path = "fused:expand_select_draw"
             else:
                 idx = kernel.indices(t0, n * k, kernel.recombination_count, y0c.device)
-                y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
+                if self.weighted:   # the gather also sums the child weights it writes: no pass of its own for them
+                    y1_hat, weight_total = _lib.expand_select_wsum(y0c, d, drift, dt, cub, idx)
+                else:
+                    y1_hat = _lib.expand_select(y0c, d, self.weighted, drift, dt, cub, idx)
                 self.last_path = "fused:mc_indices+expand_select" + ("(weighted)" if self.weighted else "")
         elif self._substeps_fusable(terms, kernel, y0c):
             y1_hat = self._substeps_step(terms, t0, times, y0c, args, kernel)
@@ -196,8 +200,7 @@ class MCCSolver(AbstractWrappedSolver):
             y1_hat = self._generic_step(terms, t0, times, y0c, args, kernel)
         # renormalise the weights after recombination (_solvers.py:146)
         if self.weighted:
-            y1_res = y1_hat.clone()
-            _lib.normalise_weights_(y1_res)
+            y1_res = _lib.normalised_copy(y1_hat, weight_total)   # clone + weights / sum(weights) in one pass
         else:
             y1_res = y1_hat
         dense_info = dict(y0=y0, y1=y1_hat)

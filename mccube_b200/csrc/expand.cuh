@@ -49,6 +49,7 @@ struct ExpandArgs {
   int draw_partitionable;
   uint32_t* draw_idx_out;      // optional: the drawn ids, [n_out]
   int vpr_shift;               // log2(vpr) when the draw is fused (vpr a power of two, 4 .. 32)
+  double* wsum;                // optional (weighted): receives the sum of the child weights written (atomic add)
   int vpr;            // vectors per row = d / VEC
   int rows_per_iter;  // rows covered by one CTA pass = blockDim / vpr
 };

@@ -107,6 +107,7 @@ expand_kernel(const ExpandArgs a) {
     load_vec<VEC>(a.inv_var + col, ivar);
   }
   const bool do_w = a.weighted && col == 0;
+  double wacc = 0.0;
   u32x2 dk_hi{}, dk_lo{};
   uint32_t draw_mult = 0;
   if (DRAW) {
@@ -230,10 +231,13 @@ expand_kernel(const ExpandArgs a) {
         uint32_t jn = (uint32_t)(cc / a.n);
         uint64_t in = cc - (uint64_t)jn * a.n;
         float lam = a.lam ? a.lam[jn] : __fdiv_rn(1.0f, (float)a.k);
-        a.y1[r[u] * a.ld + a.d] = __fmul_rn(a.y0[in * a.ld + a.d], lam);
+        const float wc = __fmul_rn(a.y0[in * a.ld + a.d], lam);
+        a.y1[r[u] * a.ld + a.d] = wc;
+        wacc += (double)wc;
       }
     }
   }
+  if (do_w && a.wsum != nullptr) atomicAdd(a.wsum, wacc);   // one add per weight-writing thread (a few thousand)
 }
 
 template <int VEC>
@@ -292,6 +296,40 @@ weight_div_kernel(float* __restrict__ y, uint64_t n, int ld, const double* __res
     for (int u = 0; u < 8; ++u) y[(r + u * stride) * ld + (ld - 1)] = __fdiv_rn(v[u], s);
   }
   for (; r < n; r += stride) y[r * ld + (ld - 1)] = __fdiv_rn(y[r * ld + (ld - 1)], s);
+}
+
+// out = in with the weight column divided by *total: the clone + renormalisation of MCCSolver.step
+// (mccube/_solvers.py:146-155: y1 keeps the raw weights, the returned state the normalised ones) in one streaming pass
+// over the flat array, 16 bytes per access whatever ld is.
+__global__ void __launch_bounds__(256)
+normalised_copy_kernel(const float* __restrict__ in, uint64_t n, int ld, const double* __restrict__ total,
+                       float* __restrict__ out, int vec_ok) {
+  const float s = (float)*total;
+  const uint64_t len = n * (uint64_t)ld;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t quads = vec_ok ? len / 4 : 0;
+  for (uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (q0 + u * stride < quads) v[u] = __ldcs(reinterpret_cast<const float4*>(in) + q0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t q = q0 + u * stride;
+      if (q >= quads) break;
+      const uint32_t col = (uint32_t)((4 * q) % (uint64_t)ld);     // column of v.x; the weight is column ld - 1
+      const uint32_t to_w = (uint32_t)ld - 1u - col;               // elements until the weight column
+      if (to_w == 0u) v[u].x = __fdiv_rn(v[u].x, s);
+      else if (to_w == 1u) v[u].y = __fdiv_rn(v[u].y, s);
+      else if (to_w == 2u) v[u].z = __fdiv_rn(v[u].z, s);
+      else if (to_w == 3u) v[u].w = __fdiv_rn(v[u].w, s);
+      __stcs(reinterpret_cast<float4*>(out) + q, v[u]);
+    }
+  }
+  for (uint64_t i = quads * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    const float x = in[i];
+    out[i] = (i % (uint64_t)ld == (uint64_t)ld - 1u) ? __fdiv_rn(x, s) : x;
+  }
 }
 
 static int pick_vec(int d, int ld, const void* p0, const void* p1) {
@@ -602,6 +640,48 @@ extern "C" int mccb200_gather_rows(const float* in, int ld, const uint32_t* idx,
   else gather_kernel<1><<<grid, EX_THREADS, 0, st>>>(in, ld, vpr, rpi, 0, 0, idx, n_out, out);
   count_launches(1);
   return check_launch("gather_rows");
+}
+
+/* y_out = y_in with the weight column (the last of ld) divided by its sum: MCCSolver.step's renormalised copy of the
+ * recombined state (mccube/_solvers.py:146-155) without a separate clone.  `total` (device, optional): the sum of the
+ * weights if a producer already has it (mccb200_expand_select_wsum); NULL = computed here into workspace[0]. */
+extern "C" int mccb200_normalised_copy(const float* y_in, uint64_t n, int ld, const double* total, float* y_out,
+                                       double* workspace, void* stream) {
+  MCCB_REQUIRE(y_in && y_out && y_in != y_out && ld >= 2 && (total || workspace), "normalised_copy: bad argument");
+  if (n == 0) return MCCB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 1;
+  if (!total) {
+    if (cudaMemsetAsync(workspace, 0, sizeof(double), st) != cudaSuccess)
+      return fail(MCCB200_ERR_CUDA, "normalised_copy: memset failed");
+    int sgrid = (int)min((n + 2047) / 2048, (uint64_t)sm_count() * 8);
+    weight_sum_kernel<<<sgrid < 1 ? 1 : sgrid, 256, 0, st>>>(y_in, n, ld, workspace);
+    total = workspace;
+    launches += 2;
+  }
+  const int vec_ok = ((((uintptr_t)y_in) | ((uintptr_t)y_out)) & 15) == 0 && ld >= 4;   // ld >= 4: one weight per 16 bytes at most
+  const uint64_t quads = n * (uint64_t)ld / 4;
+  int grid = (int)min((quads + 1023) / 1024 + 1, (uint64_t)sm_count() * 8);
+  normalised_copy_kernel<<<grid, 256, 0, st>>>(y_in, n, ld, total, y_out, vec_ok);
+  count_launches(launches);
+  return check_launch("normalised_copy");
+}
+
+/* mccb200_expand_select for weighted states that also returns the sum of the child weights it wrote (*wsum, a device
+ * double the call zeroes first): the renormalisation that follows needs no pass of its own over the weight column. */
+extern "C" int mccb200_expand_select_wsum(const float* y0, uint64_t n, int d, const mccb200_drift* drift, float dt,
+                                          const mccb200_cubature* cub, const uint32_t* idx, uint64_t n_out, float* y1,
+                                          double* wsum, void* stream) {
+  ExpandArgs a{};
+  int rc = fill_expand_args(a, y0, n, d, 1, drift, dt, cub);
+  if (rc) return rc;
+  MCCB_REQUIRE(idx && y1 && wsum, "expand_select_wsum: NULL argument");
+  if (cudaMemsetAsync(wsum, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess)
+    return fail(MCCB200_ERR_CUDA, "expand_select_wsum: memset failed");
+  count_launches(1);
+  a.idx = idx; a.perm = nullptr; a.out_per_part = 1; a.in_per_part = 1;
+  a.n_out = n_out; a.y1 = y1; a.wsum = wsum;
+  return run_expand(a, (cudaStream_t)stream);
 }
 
 extern "C" int mccb200_normalise_weights(float* y, uint64_t n, int ld, double* workspace, void* stream) {

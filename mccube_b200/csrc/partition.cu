@@ -49,6 +49,70 @@ stratified_keys_kernel(const float* __restrict__ p, uint64_t n, int d, int ld, c
   }
 }
 
+// The same keys for rows that are 16-byte chunks end to end (ld == d, d a multiple of 32): the tile of SKA_ROWS rows is
+// one contiguous block of global memory, copied with 16-byte cp.async into shared memory through a three-stage ring
+// (loads of tiles i+1, i+2 in flight while tile i is reduced), each row's chunks XOR-swizzled by the row number so that
+// a thread reading ITS row chunk by chunk (the sequential order of the sum is part of the contract) meets no bank
+// conflict.  No register staging, no second pass through shared memory.
+constexpr int SKA_ROWS = 128, SKA_STAGES = 3;
+
+__device__ __forceinline__ void ska_cp16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(SKA_ROWS)
+stratified_keys_async_kernel(const float* __restrict__ p, uint64_t n, int d, const float* __restrict__ com,
+                             uint32_t* __restrict__ keys) {
+  extern __shared__ __align__(16) unsigned char ska_smem[];
+  const int cpr = d >> 2;                                          // 16-byte chunks per row (a multiple of 8)
+  const size_t tile_bytes = (size_t)SKA_ROWS * d * 4;
+  float* s_com = reinterpret_cast<float*>(ska_smem + SKA_STAGES * tile_bytes);
+  for (int c = threadIdx.x; c < d; c += SKA_ROWS) s_com[c] = __ldg(com + c);
+  const uint64_t tiles = (n + SKA_ROWS - 1) / SKA_ROWS;
+  const int chunks = SKA_ROWS * cpr;
+
+  auto issue = [&](uint64_t tile, int stage) {
+    if (tile < tiles) {
+      const uint64_t row0 = tile * SKA_ROWS;
+      const float4* src = reinterpret_cast<const float4*>(p + row0 * d);
+      unsigned char* dst = ska_smem + stage * tile_bytes;
+      const uint64_t valid = min((uint64_t)SKA_ROWS, n - row0) * cpr;
+      for (int g = threadIdx.x; g < chunks; g += SKA_ROWS) {
+        if ((uint64_t)g >= valid) break;
+        const int row = g / cpr, c = g - row * cpr;
+        ska_cp16(dst + ((size_t)row * cpr + ((c & ~7) | ((c ^ row) & 7))) * 16, src + g);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  uint64_t tile = blockIdx.x;
+  for (int s = 0; s < SKA_STAGES - 1; ++s) issue(tile + (uint64_t)s * gridDim.x, s);
+  int stage = 0;
+  for (; tile < tiles; tile += gridDim.x) {
+    issue(tile + (uint64_t)(SKA_STAGES - 1) * gridDim.x, (stage + SKA_STAGES - 1) % SKA_STAGES);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SKA_STAGES - 1) : "memory");
+    __syncthreads();                                               // every thread's chunks of this stage have landed
+    const uint64_t r = tile * SKA_ROWS + threadIdx.x;
+    const float4* rowp = reinterpret_cast<const float4*>(ska_smem + stage * tile_bytes) + (size_t)threadIdx.x * cpr;
+    float acc = 0.0f;
+    if (r < n) {
+      for (int c = 0; c < cpr; ++c) {
+        const float4 v = rowp[(c & ~7) | ((c ^ (int)threadIdx.x) & 7)];
+        const float4 m = reinterpret_cast<const float4*>(s_com)[c];
+        float x = __fsub_rn(v.x, m.x); acc = __fadd_rn(acc, __fmul_rn(x, x));
+        x = __fsub_rn(v.y, m.y); acc = __fadd_rn(acc, __fmul_rn(x, x));
+        x = __fsub_rn(v.z, m.z); acc = __fadd_rn(acc, __fmul_rn(x, x));
+        x = __fsub_rn(v.w, m.w); acc = __fadd_rn(acc, __fmul_rn(x, x));
+      }
+      keys[r] = __float_as_uint(__fsqrt_rn(acc));
+    }
+    __syncthreads();                                               // the stage may be refilled
+    stage = (stage + 1) % SKA_STAGES;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void block_minmax(float lo, float hi, float* out_lo, float* out_hi) {
   __shared__ float s_lo[BB_THREADS / 32], s_hi[BB_THREADS / 32];
   for (int o = 16; o; o >>= 1) {
@@ -249,6 +313,21 @@ extern "C" int mccb200_stratified_keys(const float* p, uint64_t n, int d, int ld
                                        void* stream) {
   MCCB_REQUIRE(p && com && keys && d >= 1 && ld >= d, "stratified_keys: bad argument");
   if (n == 0) return MCCB200_OK;
+  if (ld == d && d % 32 == 0 && d <= 128 && (((uintptr_t)p) & 15) == 0 && env_int("MCCB200_STRATIFIED_ASYNC", 1) != 0) {
+    const size_t smem = (size_t)SKA_STAGES * SKA_ROWS * d * 4 + (size_t)d * 4;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+      cudaFuncSetAttribute(stratified_keys_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_dev = dev;
+    }
+    const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / smem));
+    int grid = (int)min((n + SKA_ROWS - 1) / SKA_ROWS, (uint64_t)sm_count() * per_sm);
+    stratified_keys_async_kernel<<<grid, SKA_ROWS, smem, (cudaStream_t)stream>>>(p, n, d, com, keys);
+    count_launches(1);
+    return check_launch("stratified_keys");
+  }
   int grid = (int)min((n + SK_ROWS - 1) / SK_ROWS, (uint64_t)sm_count() * 6);
   stratified_keys_kernel<<<grid, SK_ROWS, 0, (cudaStream_t)stream>>>(p, n, d, ld, com, keys);
   count_launches(1);

@@ -51,6 +51,31 @@ scatter_rows_kernel(const float* __restrict__ in, int ld, const uint32_t* __rest
   }
 }
 
+// The same with 16-byte accesses (ld a multiple of 4, 16-byte aligned bases): ld / 4 threads per row, four rows in
+// flight per thread, streaming loads (the rows are read once) -- the scalar form above moved one word per thread and row.
+__global__ void __launch_bounds__(256)
+scatter_rows_vec4_kernel(const float4* __restrict__ in, int vpr, int rows_per_iter, const uint32_t* __restrict__ slots,
+                         uint64_t slot_offset, uint64_t n_rows, float4* __restrict__ out) {
+  const int rr = threadIdx.x / vpr, c = threadIdx.x - rr * vpr;
+  if (rr >= rows_per_iter) return;
+  const uint64_t step = (uint64_t)gridDim.x * rows_per_iter;
+  for (uint64_t r0 = (uint64_t)blockIdx.x * rows_per_iter + rr; r0 < n_rows; r0 += 4 * step) {
+    uint64_t dst[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t r = r0 + u * step;
+      if (r < n_rows) {
+        dst[u] = (uint64_t)__ldg(slots + r) - slot_offset;
+        v[u] = __ldcs(in + r * vpr + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r0 + u * step < n_rows) __stcs(out + dst[u] * vpr + c, v[u]);
+  }
+}
+
 // list[cursor++] = s for every slot s a rank fills (idx_slots[s] != 0xFFFFFFFF): warp-aggregated append, any order
 __global__ void __launch_bounds__(256)
 compact_slots_kernel(const uint32_t* __restrict__ idx_slots, uint64_t n_slots, uint32_t* __restrict__ list,
@@ -291,6 +316,14 @@ extern "C" int mccb200_scatter_rows(const float* in, int ld, const uint32_t* slo
   MCCB_REQUIRE((in && slots && out) || n_rows == 0, "scatter_rows: NULL argument");
   MCCB_REQUIRE(ld >= 1, "scatter_rows: ld=%d", ld);
   if (n_rows == 0) return MCCB200_OK;
+  if (ld % 4 == 0 && ld / 4 <= 256 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    const int vpr = ld / 4, rpi = 256 / vpr;
+    int grid = (int)min((n_rows + rpi - 1) / rpi, (uint64_t)sm_count() * 8);
+    scatter_rows_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)in, vpr, rpi, slots, slot_offset, n_rows,
+                                                                    (float4*)out);
+    count_launches(1);
+    return check_launch("scatter_rows");
+  }
   const int lanes = ld < 32 ? ld : 32;
   const int rows_per_cta = 256 / lanes;
   int grid = (int)min((n_rows + rows_per_cta - 1) / rows_per_cta, (uint64_t)sm_count() * 16);

@@ -1138,3 +1138,56 @@ def test_device_median_split_partitioner_matches_sklearn_sets(dev, n, d, leaf, w
     out = kern(np.float32(0.0), yt, None, weighted)
     assert out.shape == (count, leaf, y.shape[1])
     assert torch.equal(out.reshape(n, -1), yt[torch.from_numpy(idx.astype(np.int64)).to(dev)])
+
+
+@pytest.mark.parametrize("n,ld", [(1000, 65), (4097, 5), (333, 2), (2048, 4), (10, 3), (70000, 17)])
+def test_normalised_copy_equals_clone_then_normalise(dev, n, ld):
+    """MCCSolver.step's renormalised copy (mccube/_solvers.py:146-155) in one pass: same bits as clone + normalise_weights_,
+    with the sum computed here or handed over by the producer."""
+    rng = np.random.default_rng(11)
+    y = rng.standard_normal((n, ld)).astype(np.float32)
+    y[:, -1] = rng.uniform(0.1, 2.0, n).astype(np.float32)
+    yt = cuda(y, dev)
+    want = _lib.normalise_weights_(yt.clone())
+    got = _lib.normalised_copy(yt)
+    assert torch.equal(yt, cuda(y, dev))                       # the input keeps its raw weights
+    total = yt[:, -1].double().sum().reshape(1)
+    got2 = _lib.normalised_copy(yt, total)
+    s32 = np.float32(total.item())
+    assert torch.equal(got[:, :-1], yt[:, :-1]) and torch.equal(got2[:, :-1], yt[:, :-1])
+    assert torch.equal(got2[:, -1], yt[:, -1] / torch.tensor(s32, device=dev))
+    # the in-kernel sum is a double accumulation in another order: equal after the cast to float32 except at a rounding tie
+    assert torch.allclose(got[:, -1], want[:, -1], rtol=2e-7, atol=0) and abs(float(got[:, -1].double().sum()) - 1.0) < 1e-5
+
+
+def test_weighted_step_sums_child_weights_in_the_gather(dev):
+    """Weighted fused MC step: the gather kernel hands the sum of the child weights to the renormalising copy; the
+    result equals normalising dense_info's raw y1 separately."""
+    n, d = 3000, 16
+    y, mean, inv_var = _setup(n, d, seed=9)
+    w = np.random.default_rng(2).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    yw = cuda(np.concatenate([y, w / w.sum()], axis=1), dev)
+    terms = _terms(d, mean, inv_var, dev)
+    solver = mccube.MCCSolver(dfx.Euler(), mccube.MonteCarloKernel(n, key=3), weighted=True)
+    y1, _, dense, _, _ = solver.step(terms, np.float32(0.0), np.float32(0.05), yw, None, None, False)
+    assert solver.last_path == "fused:mc_indices+expand_select(weighted)"
+    raw = dense["y1"]
+    ref = _lib.normalise_weights_(raw.clone())
+    assert torch.equal(y1[:, :-1], raw[:, :-1])
+    assert torch.allclose(y1[:, -1], ref[:, -1], rtol=2e-7, atol=0)
+    assert abs(float(y1[:, -1].double().sum()) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("n,d", [(4096, 64), (1000, 32), (129, 96), (70001, 128), (5, 64)])
+def test_stratified_keys_async_tiles_equal_oracle_and_staged_kernel(dev, monkeypatch, n, d):
+    """Rows made of whole 16-byte chunks take the cp.async / swizzled-tile kernel: the same keys, bit for bit, as the
+    oracle's sequential fp32 sum (mccube/_kernels/stratified.py:36-45) and as the register-staged kernel."""
+    p = np.random.default_rng(n + d).normal(size=(n, d)).astype(np.float32) * 3
+    pt = cuda(p, dev)
+    _, com, key = ref.stratified_indices(p, 1)
+    comt = cuda(com.astype(np.float32), dev)
+    got = _lib.stratified_keys(pt, d, comt)
+    monkeypatch.setenv("MCCB200_STRATIFIED_ASYNC", "0")
+    staged = _lib.stratified_keys(pt, d, comt)
+    assert torch.equal(got, staged)
+    assert np.array_equal(u32(got), key.view(np.uint32))
