@@ -311,7 +311,7 @@ def extra_workloads(dev, peak_gbs):
         terms, solver = mc_problem(n, d, False, mccube.GaussianDiagDrift(np.full(d, TARGET_MEAN), TARGET_VAR, device=dev))
         ms, path = time_steps(solver, terms, torch.randn((n, d), device=dev), times, 10)
         out["config2_mc_n2^20_d10"] = {"ms_per_step": ms, "particle_steps_per_sec": n / ms * 1e3, "path": path,
-                                       "note": "bit-exact jax.random shuffle: 3 rounds x (threefry bits + stable radix sort of 2^25 pairs)"}
+                                       "note": "bit-exact jax.random shuffle of 2^25 ids, only permutation[:n] materialised: 3 rounds x rank selection over regenerated threefry keys (rng_select.cu)"}
     except Exception as e:  # noqa: BLE001
         out["config2_mc_n2^20_d10"] = {"error": repr(e)}
     torch.cuda.empty_cache()

@@ -308,7 +308,12 @@ normalised_copy_kernel(const float* __restrict__ in, uint64_t n, int ld, const d
   const uint64_t len = n * (uint64_t)ld;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t quads = vec_ok ? len / 4 : 0;
-  for (uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += 4 * stride) {
+  // column of the first element of a thread's quad, advanced by (4 * stride) mod ld from one quad to the next
+  const uint32_t uld = (uint32_t)ld;
+  const uint32_t col_step = (uint32_t)((4 * stride) % (uint64_t)ld);
+  uint64_t q0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t col = (uint32_t)((4 * q0) % (uint64_t)ld);
+  for (; q0 < quads; q0 += 4 * stride) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -316,9 +321,10 @@ normalised_copy_kernel(const float* __restrict__ in, uint64_t n, int ld, const d
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint64_t q = q0 + u * stride;
-      if (q >= quads) break;
-      const uint32_t col = (uint32_t)((4 * q) % (uint64_t)ld);     // column of v.x; the weight is column ld - 1
-      const uint32_t to_w = (uint32_t)ld - 1u - col;               // elements until the weight column
+      const uint32_t to_w = uld - 1u - col;                        // elements until the weight column
+      col += col_step;
+      if (col >= uld) col -= uld;
+      if (q >= quads) continue;
       if (to_w == 0u) v[u].x = __fdiv_rn(v[u].x, s);
       else if (to_w == 1u) v[u].y = __fdiv_rn(v[u].y, s);
       else if (to_w == 2u) v[u].z = __fdiv_rn(v[u].z, s);
