@@ -98,6 +98,9 @@ moments_sum_vec4_kernel(const float* __restrict__ p, uint64_t n, int d, int ld, 
 // 8 warps per SM, tensor pipe 26 % busy).  Four warps, a 32x32 quadrant each; fp32 accumulation over at
 // most 2048 rows, then one fp64 atomic per entry.  Only tiles on or above the diagonal are computed,
 // off-diagonal ones are mirrored.
+bool moments_m2_tc_applicable(const float* p, int d, int ld, const float* w, const float* centre);
+int moments_m2_tc(const float* p, uint64_t n, int ld, const float* centre, double* m2_out, cudaStream_t st);
+
 constexpr int M2_TILE = 64;
 constexpr int M2_ROWS = 32;      // rows per smem stage
 constexpr int M2_PITCH = 72;     // floats: bank = (8 * k + column) mod 32 is distinct over a fragment load
@@ -347,6 +350,8 @@ extern "C" int mccb200_moments_m2(const float* p, uint64_t n, int d, int ld, con
                                   const float* centre, double* m2_out, void* stream) {
   MCCB_REQUIRE(p && centre && m2_out && d >= 1 && ld >= d, "moments_m2: bad argument");
   if (n == 0) return MCCB200_OK;
+  if (mccb::moments_m2_tc_applicable(p, d, ld, w, centre))          // d = 64, unweighted: tcgen05 (moments_tc.cu)
+    return mccb::moments_m2_tc(p, n, ld, centre, m2_out, (cudaStream_t)stream);
   const int tiles = (d + M2_TILE - 1) / M2_TILE;
   const int pairs = tiles * (tiles + 1) / 2;           // tiles on or above the diagonal
   uint64_t want_ctas = (uint64_t)sm_count() * 8 / (uint64_t)pairs + 1;

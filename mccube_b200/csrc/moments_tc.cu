@@ -1,0 +1,277 @@
+// Centred second moment  M2 = sum_r (x_r - c)(x_r - c)^T  of [n, 64] fp32 rows on the 5th-generation tensor cores
+// (sm_100a): the d = 64 case of mccb200_moments_m2, i.e. the jnp.cov of /root/reference/README.md:85-86 that feeds
+// gaussian_wasserstein_metric (mccube/_metrics.py:39-44) at the headline shape.
+//
+// The contraction index is the particle row, so a row-major stage of rows IS both operands in MN-major form
+// (A[m][k] = B[m][k] = x[k][m]): `tcgen05.mma.kind::tf32` with a_major = b_major = MN reads them from shared memory,
+// no transpose.  3xTF32 for fp32-level products: x = hi + lo, and
+//     x x^T ~= hi hi^T + lo hi^T + (lo hi^T)^T
+// -- the three products of the mma.sync kernel collapse into ONE M128 x N64 x K8 instruction per 8 rows:
+// A = [hi ; lo] (128 MN rows), B = hi (64 MN rows) gives D[0:64] = hi^T hi and D[64:128] = lo^T hi in one pass,
+// and the epilogue adds the transpose of the second block.  A third of the tensor work of three M64 products.
+//
+// Shared-memory stage (KS = 64 rows): four planes  hi[:, 0:32], hi[:, 32:64], lo[:, 0:32], lo[:, 32:64],  each KS
+// rows of 128 bytes in the one layout MN-major TF32 operands may use, SWIZZLE_128B_BASE32B (CUTLASS
+// Layout_MN_SW128_32B_Atom: rows of 128 bytes along MN, 4 rows along K per atom, Swizzle<2,5,2> on byte addresses):
+// the 32-byte chunk c of row r of a plane sits at chunk c ^ (r & 3); MN blocks of 32 columns are LBO = KS * 128 bytes
+// apart (the planes), 4-row K groups SBO = 512 bytes (rows are contiguous).
+//
+// Persistent CTA per SM, warp-specialised:
+//   warps 5-16  converters : three groups of four warps on alternate stages; float4 loads straight from global
+//                            memory (the next stage of the group is in flight while the current one is converted),
+//                            centre, split, st.shared into the swizzled planes, fence.proxy.async, arrive
+//   warp 4      MMA issuer : one thread, 8 tcgen05.mma (M128 N64 K8) per stage; tcgen05.commit frees the stage;
+//                            every M2T_FLUSH_STAGES stages the accumulator (64 TMEM columns) is handed to the epilogue
+//                            and the other one is used (fp32 partial sums stay short: 256 rows)
+//   warps 0-3   epilogue   : tcgen05.ld 32x32b -> fp64 registers (thread = accumulator row, 64 columns);
+//                            at the end one fp64 atomic per entry (+ the mirrored one for the lo^T hi block)
+#include "common.cuh"
+
+namespace mccb {
+
+constexpr int M2T_D = 64;
+constexpr int M2T_KS = 64;                        // rows per stage
+constexpr int M2T_STAGES = 6;
+constexpr int M2T_GROUPS = 3;                     // converter groups
+constexpr int M2T_GROUP_WARPS = 4;
+constexpr int M2T_FLUSH_STAGES = 4;               // 256 rows per fp32 partial sum
+constexpr int M2T_PLANE_BYTES = M2T_KS * 128;     // 8 KB
+constexpr int M2T_STAGE_BYTES = 4 * M2T_PLANE_BYTES;   // 32 KB
+constexpr int M2T_CONV_WARP0 = 5;                 // warps 0-3: epilogue (warp id = TMEM lane quarter), 4: MMA, 5..: converters
+constexpr int M2T_THREADS = 32 * (M2T_CONV_WARP0 + M2T_GROUPS * M2T_GROUP_WARPS);
+constexpr int M2T_SMEM = M2T_STAGES * M2T_STAGE_BYTES + 1024 + 256;
+constexpr int M2T_F4_PER_THREAD = M2T_KS * (M2T_D / 4) / (32 * M2T_GROUP_WARPS);   // 8
+
+__device__ __forceinline__ uint32_t m2t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void m2t_bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void m2t_bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void m2t_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (spin & 1023u) == 1023u) {            // a protocol bug must trap, not hang the GPU
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void m2t_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void m2t_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major, SWIZZLE_128B_BASE32B: start address, LBO = distance between 32-column MN blocks (planes), SBO = 4-row K groups
+__device__ __forceinline__ uint64_t m2t_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(M2T_PLANE_BYTES >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)1 << 61;                          // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ void m2t_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(M2T_THREADS, 1)
+moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const float* __restrict__ centre,
+                     uint64_t stages_per_cta, double* __restrict__ out, int debug) {
+  extern __shared__ uint8_t m2t_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(m2t_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M2T_STAGES * M2T_STAGE_BYTES);
+  const uint32_t bar_full = m2t_smem(bars), bar_empty = m2t_smem(bars + M2T_STAGES);
+  const uint32_t bar_afull = m2t_smem(bars + 2 * M2T_STAGES), bar_aempty = m2t_smem(bars + 2 * M2T_STAGES + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * M2T_STAGES + 4);
+  const uint32_t smem_base = m2t_smem(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint64_t total_stages = (n + M2T_KS - 1) / M2T_KS;
+  const uint64_t s0 = (uint64_t)blockIdx.x * stages_per_cta;
+  const uint64_t s1 = min(total_stages, s0 + stages_per_cta);
+  const uint32_t my_stages = s0 < s1 ? (uint32_t)(s1 - s0) : 0u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < M2T_STAGES; ++s) {
+      m2t_bar_init(bar_full + 8 * s, 32 * M2T_GROUP_WARPS);       // every thread of the converting group arrives
+      m2t_bar_init(bar_empty + 8 * s, 1);                         // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      m2t_bar_init(bar_afull + 8 * a, 1);
+      m2t_bar_init(bar_aempty + 8 * a, 128);                      // the four epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {   // two accumulators of 64 fp32 columns (128 lanes)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m2t_smem(s_tmem)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t n_flush = (my_stages + M2T_FLUSH_STAGES - 1) / M2T_FLUSH_STAGES;
+
+  if (warp >= M2T_CONV_WARP0) {
+    // ===== converters: group g takes stages g, g + GROUPS, ... of this CTA =====
+    const int g = (warp - M2T_CONV_WARP0) / M2T_GROUP_WARPS;
+    const int t = threadIdx.x - 32 * (M2T_CONV_WARP0 + g * M2T_GROUP_WARPS);   // 0 .. 127 inside the group
+    // float4 f of a stage: row = f / 16, quad = f % 16; thread t takes f = t + 128 * i  ->  quad = t % 16 for all i
+    const int quad = t & 15;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(centre) + quad);
+    const int plane = quad >> 3, chunk = quad & 7;
+    float4 cur[M2T_F4_PER_THREAD], nxt[M2T_F4_PER_THREAD];
+    auto load = [&](uint32_t st, float4 (&v)[M2T_F4_PER_THREAD]) {
+      const uint64_t row0 = (s0 + st) * M2T_KS;
+#pragma unroll
+      for (int i = 0; i < M2T_F4_PER_THREAD; ++i) {
+        const uint64_t r = row0 + (uint64_t)((t >> 4) + 8 * i);
+        v[i] = r < n ? __ldcs(reinterpret_cast<const float4*>(p + r * (uint64_t)ld) + quad)
+                     : make_float4(c4.x, c4.y, c4.z, c4.w);      // centred to zero: contributes nothing
+      }
+    };
+    if ((uint32_t)g < my_stages) load((uint32_t)g, cur);
+    for (uint32_t st = (uint32_t)g; st < my_stages; st += M2T_GROUPS) {
+      const uint32_t slot = st % M2T_STAGES, use = st / M2T_STAGES;
+      if (st + M2T_GROUPS < my_stages) load(st + M2T_GROUPS, nxt);
+      m2t_bar_wait(bar_empty + 8 * slot, (use & 1u) ^ 1u);
+      uint8_t* sb = smem + slot * M2T_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < M2T_F4_PER_THREAD; ++i) {
+        const int r = (t >> 4) + 8 * i;
+        const float x[4] = {cur[i].x - c4.x, cur[i].y - c4.y, cur[i].z - c4.z, cur[i].w - c4.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t h;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x[e]));
+          hi[e] = __uint_as_float(h);
+          lo[e] = x[e] - hi[e];                                   // exact; the tensor core drops its low 13 bits
+        }
+        const uint32_t off = (uint32_t)plane * M2T_PLANE_BYTES + (uint32_t)r * 128u +
+                             (uint32_t)((((chunk >> 1) ^ (r & 3)) << 5) | ((chunk & 1) << 4));
+        *reinterpret_cast<float4*>(sb + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(sb + 2 * M2T_PLANE_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      m2t_bar_arrive(bar_full + 8 * slot);
+#pragma unroll
+      for (int i = 0; i < M2T_F4_PER_THREAD; ++i) cur[i] = nxt[i];
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // c_format F32, a/b TF32, a_major = b_major = MN, N = 64, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(M2T_D >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (uint32_t st = 0; st < my_stages; ++st) {
+        const uint32_t slot = st % M2T_STAGES, use = st / M2T_STAGES;
+        const uint32_t fl = st / M2T_FLUSH_STAGES, acc = fl & 1u, acc_use = fl >> 1;
+        if (st % M2T_FLUSH_STAGES == 0) {                          // first stage of a partial sum: the accumulator must be drained
+          m2t_bar_wait(bar_aempty + 8 * acc, (acc_use & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        m2t_bar_wait(bar_full + 8 * slot, use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sb = smem_base + slot * M2T_STAGE_BYTES;
+#pragma unroll
+        for (int kg = 0; kg < M2T_KS / 8; ++kg) {
+          const uint64_t desc = m2t_desc(sb + kg * 1024);
+          m2t_mma(tmem_base + acc * M2T_D, desc, desc, idesc, (st % M2T_FLUSH_STAGES != 0 || kg != 0) ? 1u : 0u);
+        }
+        m2t_commit(bar_empty + 8 * slot);                          // the stage may be refilled once these MMAs retire
+        if (st % M2T_FLUSH_STAGES == M2T_FLUSH_STAGES - 1 || st + 1 == my_stages) m2t_commit(bar_afull + 8 * acc);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = accumulator row (TMEM lane), fp64 running sums of its 64 columns =====
+    const int q = warp & 3;                                        // the lane quarter this warp may read
+    const int row = 32 * q + lane;
+    double sum[M2T_D];
+#pragma unroll
+    for (int j = 0; j < M2T_D; ++j) sum[j] = 0.0;
+    for (uint32_t fl = 0; fl < n_flush; ++fl) {
+      const uint32_t acc = fl & 1u, acc_use = fl >> 1;
+      m2t_bar_wait(bar_afull + 8 * acc, acc_use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t v[16];
+        m2t_tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + acc * M2T_D + 16 * h, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum[16 * h + j] += (debug == 1) ? 1.0 : (double)__uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      m2t_bar_arrive(bar_aempty + 8 * acc);
+    }
+    if (my_stages > 0) {
+      if (row < M2T_D) {                                           // hi^T hi
+#pragma unroll
+        for (int j = 0; j < M2T_D; ++j) atomicAdd(out + (size_t)row * M2T_D + j, sum[j]);
+      } else {                                                     // L = lo^T hi: M2 += L + L^T
+        const int i = row - M2T_D;
+#pragma unroll
+        for (int j = 0; j < M2T_D; ++j) {
+          atomicAdd(out + (size_t)i * M2T_D + j, sum[j]);
+          atomicAdd(out + (size_t)j * M2T_D + i, sum[j]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// d = 64, unweighted, rows of whole float4s: the tcgen05 kernel applies (mccb200_moments_m2 falls back otherwise)
+bool moments_m2_tc_applicable(const float* p, int d, int ld, const float* w, const float* centre) {
+  return env_int("MCCB200_M2_TC", 1) != 0 && d == M2T_D && w == nullptr && ld % 4 == 0 &&
+         ((((uintptr_t)p) | ((uintptr_t)centre)) & 15) == 0;
+}
+
+int moments_m2_tc(const float* p, uint64_t n, int ld, const float* centre, double* m2_out, cudaStream_t st) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    if (cudaFuncSetAttribute(moments_m2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M2T_SMEM) != cudaSuccess)
+      return fail(MCCB200_ERR_CUDA, "moments_m2: cannot reserve %d bytes of shared memory", M2T_SMEM);
+    attr_dev = dev;
+  }
+  const uint64_t total_stages = (n + M2T_KS - 1) / M2T_KS;
+  uint64_t ctas = min((uint64_t)sm_count(), total_stages);
+  uint64_t per = (total_stages + ctas - 1) / ctas;
+  per = (per + M2T_FLUSH_STAGES - 1) / M2T_FLUSH_STAGES * M2T_FLUSH_STAGES;
+  ctas = (total_stages + per - 1) / per;
+  moments_m2_tc_kernel<<<(unsigned)ctas, M2T_THREADS, M2T_SMEM, st>>>(p, n, ld, centre, per, m2_out, env_int("MCCB200_M2_TC_DEBUG", 0));
+  count_launches(1);
+  return check_launch("moments_m2(tcgen05)");
+}
+
+}  // namespace mccb
