@@ -17,14 +17,16 @@
 // apart (the planes), 4-row K groups SBO = 512 bytes (rows are contiguous).
 //
 // Persistent CTA per SM, warp-specialised:
-//   warps 5-16  converters : three groups of four warps on alternate stages; float4 loads straight from global
-//                            memory (the next stage of the group is in flight while the current one is converted),
-//                            centre, split, st.shared into the swizzled planes, fence.proxy.async, arrive
-//   warp 4      MMA issuer : one thread, 8 tcgen05.mma (M128 N64 K8) per stage; tcgen05.commit frees the stage;
+//   warps 9-20  converters : six groups of two warps on alternate stages; float4 loads straight from global memory
+//                            (a group's next stage is in flight while the other five convert theirs: ~80 KB of loads
+//                            in flight per SM), centre, split, st.shared into the swizzled planes, fence.proxy.async, arrive
+//   warp 8      MMA issuer : one thread, 8 tcgen05.mma (M128 N64 K8) per stage; tcgen05.commit frees the stage;
 //                            every M2T_FLUSH_STAGES stages the accumulator (64 TMEM columns) is handed to the epilogue
 //                            and the other one is used (fp32 partial sums stay short: 256 rows)
-//   warps 0-3   epilogue   : tcgen05.ld 32x32b -> fp64 registers (thread = accumulator row, 64 columns);
-//                            at the end one fp64 atomic per entry (+ the mirrored one for the lo^T hi block)
+//   warps 0-7   epilogue   : tcgen05.ld 32x32b -> fp64 registers (thread = accumulator row x 32 columns: warp & 3 is
+//                            the TMEM lane quarter it may read, warp >> 2 the column half); at the end one fp64
+//                            atomic per entry (+ the mirrored one for the lo^T hi block).  With four warps holding
+//                            64 doubles each the sums spilled and the epilogue bounded the kernel (1.49 ms).
 #include "common.cuh"
 
 namespace mccb {
@@ -32,15 +34,17 @@ namespace mccb {
 constexpr int M2T_D = 64;
 constexpr int M2T_KS = 64;                        // rows per stage
 constexpr int M2T_STAGES = 6;
-constexpr int M2T_GROUPS = 3;                     // converter groups
-constexpr int M2T_GROUP_WARPS = 4;
+constexpr int M2T_GROUPS = 6;                     // converter groups
+constexpr int M2T_GROUP_WARPS = 2;
 constexpr int M2T_FLUSH_STAGES = 4;               // 256 rows per fp32 partial sum
 constexpr int M2T_PLANE_BYTES = M2T_KS * 128;     // 8 KB
 constexpr int M2T_STAGE_BYTES = 4 * M2T_PLANE_BYTES;   // 32 KB
-constexpr int M2T_CONV_WARP0 = 5;                 // warps 0-3: epilogue (warp id = TMEM lane quarter), 4: MMA, 5..: converters
+constexpr int M2T_MMA_WARP = 8;                   // warps 0-7: epilogue, 8: MMA issuer, 9..: converters
+constexpr int M2T_CONV_WARP0 = 9;
 constexpr int M2T_THREADS = 32 * (M2T_CONV_WARP0 + M2T_GROUPS * M2T_GROUP_WARPS);
 constexpr int M2T_SMEM = M2T_STAGES * M2T_STAGE_BYTES + 1024 + 256;
-constexpr int M2T_F4_PER_THREAD = M2T_KS * (M2T_D / 4) / (32 * M2T_GROUP_WARPS);   // 8
+constexpr int M2T_F4_PER_THREAD = M2T_KS * (M2T_D / 4) / (32 * M2T_GROUP_WARPS);   // 16
+constexpr int M2T_ROW_STEP = 32 * M2T_GROUP_WARPS / 16;                             // rows between a thread's float4s
 
 __device__ __forceinline__ uint32_t m2t_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void m2t_bar_init(uint32_t bar, uint32_t count) {
@@ -76,6 +80,25 @@ __device__ __forceinline__ void m2t_mma(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ uint64_t m2t_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void m2t_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t m2t_add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t m2t_sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void m2t_sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // MN-major, SWIZZLE_128B_BASE32B: start address, LBO = distance between 32-column MN blocks (planes), SBO = 4-row K groups
 __device__ __forceinline__ uint64_t m2t_desc(uint32_t saddr) {
@@ -121,11 +144,11 @@ moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const floa
     }
     for (int a = 0; a < 2; ++a) {
       m2t_bar_init(bar_afull + 8 * a, 1);
-      m2t_bar_init(bar_aempty + 8 * a, 128);                      // the four epilogue warps
+      m2t_bar_init(bar_aempty + 8 * a, 256);                      // the eight epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {   // two accumulators of 64 fp32 columns (128 lanes)
+  if (warp == M2T_MMA_WARP) {   // two accumulators of 64 fp32 columns (128 lanes)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(m2t_smem(s_tmem)), "r"(128u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -138,50 +161,47 @@ moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const floa
   if (warp >= M2T_CONV_WARP0) {
     // ===== converters: group g takes stages g, g + GROUPS, ... of this CTA =====
     const int g = (warp - M2T_CONV_WARP0) / M2T_GROUP_WARPS;
-    const int t = threadIdx.x - 32 * (M2T_CONV_WARP0 + g * M2T_GROUP_WARPS);   // 0 .. 127 inside the group
-    // float4 f of a stage: row = f / 16, quad = f % 16; thread t takes f = t + 128 * i  ->  quad = t % 16 for all i
+    const int t = threadIdx.x - 32 * (M2T_CONV_WARP0 + g * M2T_GROUP_WARPS);   // index inside the group
+    // float4 f of a stage: row = f / 16, quad = f % 16; thread t takes f = t + (group size) * i  ->  quad = t % 16 for all i
     const int quad = t & 15;
     const float4 c4 = __ldg(reinterpret_cast<const float4*>(centre) + quad);
     const int plane = quad >> 3, chunk = quad & 7;
-    float4 cur[M2T_F4_PER_THREAD], nxt[M2T_F4_PER_THREAD];
+    const uint64_t nc01 = m2t_pack(-c4.x, -c4.y), nc23 = m2t_pack(-c4.z, -c4.w);
+    float4 cur[M2T_F4_PER_THREAD];
     auto load = [&](uint32_t st, float4 (&v)[M2T_F4_PER_THREAD]) {
       const uint64_t row0 = (s0 + st) * M2T_KS;
 #pragma unroll
       for (int i = 0; i < M2T_F4_PER_THREAD; ++i) {
-        const uint64_t r = row0 + (uint64_t)((t >> 4) + 8 * i);
-        v[i] = r < n ? __ldcs(reinterpret_cast<const float4*>(p + r * (uint64_t)ld) + quad)
-                     : make_float4(c4.x, c4.y, c4.z, c4.w);      // centred to zero: contributes nothing
+        const uint64_t r = row0 + (uint64_t)((t >> 4) + M2T_ROW_STEP * i);
+        v[i] = (r < n && debug != 3) ? __ldcs(reinterpret_cast<const float4*>(p + r * (uint64_t)ld) + quad)
+                                     : make_float4(c4.x, c4.y, c4.z, c4.w);      // centred to zero: contributes nothing
       }
     };
     if ((uint32_t)g < my_stages) load((uint32_t)g, cur);
     for (uint32_t st = (uint32_t)g; st < my_stages; st += M2T_GROUPS) {
       const uint32_t slot = st % M2T_STAGES, use = st / M2T_STAGES;
-      if (st + M2T_GROUPS < my_stages) load(st + M2T_GROUPS, nxt);
       m2t_bar_wait(bar_empty + 8 * slot, (use & 1u) ^ 1u);
-      uint8_t* sb = smem + slot * M2T_STAGE_BYTES;
+      const uint32_t sb = smem_base + slot * M2T_STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < M2T_F4_PER_THREAD; ++i) {
-        const int r = (t >> 4) + 8 * i;
-        const float x[4] = {cur[i].x - c4.x, cur[i].y - c4.y, cur[i].z - c4.z, cur[i].w - c4.w};
+        const int r = (t >> 4) + M2T_ROW_STEP * i;
+        // x = row - centre; the tensor core reads only the top 19 bits of an operand (sign, exponent, 10 mantissa
+        // bits), so x itself serves as the TF32 high part and lo = x - (x with the low 13 bits cleared), exact in fp32
+        const uint64_t x01 = m2t_add2(m2t_pack(cur[i].x, cur[i].y), nc01), x23 = m2t_add2(m2t_pack(cur[i].z, cur[i].w), nc23);
+        const uint64_t lo01 = m2t_sub2(x01, x01 & 0xFFFFE000FFFFE000ull), lo23 = m2t_sub2(x23, x23 & 0xFFFFE000FFFFE000ull);
         float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint32_t h;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x[e]));
-          hi[e] = __uint_as_float(h);
-          lo[e] = x[e] - hi[e];                                   // exact; the tensor core drops its low 13 bits
-        }
+        m2t_unpack(x01, hi[0], hi[1]); m2t_unpack(x23, hi[2], hi[3]);
+        m2t_unpack(lo01, lo[0], lo[1]); m2t_unpack(lo23, lo[2], lo[3]);
         const uint32_t off = (uint32_t)plane * M2T_PLANE_BYTES + (uint32_t)r * 128u +
                              (uint32_t)((((chunk >> 1) ^ (r & 3)) << 5) | ((chunk & 1) << 4));
-        *reinterpret_cast<float4*>(sb + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(sb + 2 * M2T_PLANE_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        m2t_sts128(sb + off, hi[0], hi[1], hi[2], hi[3]);
+        m2t_sts128(sb + 2 * M2T_PLANE_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       m2t_bar_arrive(bar_full + 8 * slot);
-#pragma unroll
-      for (int i = 0; i < M2T_F4_PER_THREAD; ++i) cur[i] = nxt[i];
+      if (st + M2T_GROUPS < my_stages) load(st + M2T_GROUPS, cur);   // in flight while the other groups convert
     }
-  } else if (warp == 4) {
+  } else if (warp == M2T_MMA_WARP) {
     // ===== MMA issuer =====
     if (lane == 0) {
       // c_format F32, a/b TF32, a_major = b_major = MN, N = 64, M = 128
@@ -199,6 +219,7 @@ moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const floa
         const uint32_t sb = smem_base + slot * M2T_STAGE_BYTES;
 #pragma unroll
         for (int kg = 0; kg < M2T_KS / 8; ++kg) {
+          if (debug == 2) break;                                   // timing experiment: no tensor work
           const uint64_t desc = m2t_desc(sb + kg * 1024);
           m2t_mma(tmem_base + acc * M2T_D, desc, desc, idesc, (st % M2T_FLUSH_STAGES != 0 || kg != 0) ? 1u : 0u);
         }
@@ -207,20 +228,21 @@ moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const floa
       }
     }
   } else {
-    // ===== epilogue: thread = accumulator row (TMEM lane), fp64 running sums of its 64 columns =====
-    const int q = warp & 3;                                        // the lane quarter this warp may read
+    // ===== epilogue: thread = accumulator row (TMEM lane) x 32 columns, fp64 running sums =====
+    const int q = warp & 3, ch = warp >> 2;                        // lane quarter this warp may read, column half
     const int row = 32 * q + lane;
-    double sum[M2T_D];
+    double sum[32];
 #pragma unroll
-    for (int j = 0; j < M2T_D; ++j) sum[j] = 0.0;
+    for (int j = 0; j < 32; ++j) sum[j] = 0.0;
     for (uint32_t fl = 0; fl < n_flush; ++fl) {
       const uint32_t acc = fl & 1u, acc_use = fl >> 1;
       m2t_bar_wait(bar_afull + 8 * acc, acc_use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < 2; ++h) {
         uint32_t v[16];
-        m2t_tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + acc * M2T_D + 16 * h, v);
+        m2t_tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + acc * M2T_D + 32 * ch + 16 * h, v);
+        if (debug == 4 && fl != 0) continue;                       // timing experiment: no fp64 accumulation
 #pragma unroll
         for (int j = 0; j < 16; ++j) sum[16 * h + j] += (debug == 1) ? 1.0 : (double)__uint_as_float(v[j]);
       }
@@ -230,20 +252,20 @@ moments_m2_tc_kernel(const float* __restrict__ p, uint64_t n, int ld, const floa
     if (my_stages > 0) {
       if (row < M2T_D) {                                           // hi^T hi
 #pragma unroll
-        for (int j = 0; j < M2T_D; ++j) atomicAdd(out + (size_t)row * M2T_D + j, sum[j]);
+        for (int j = 0; j < 32; ++j) atomicAdd(out + (size_t)row * M2T_D + 32 * ch + j, sum[j]);
       } else {                                                     // L = lo^T hi: M2 += L + L^T
         const int i = row - M2T_D;
 #pragma unroll
-        for (int j = 0; j < M2T_D; ++j) {
-          atomicAdd(out + (size_t)i * M2T_D + j, sum[j]);
-          atomicAdd(out + (size_t)j * M2T_D + i, sum[j]);
+        for (int j = 0; j < 32; ++j) {
+          atomicAdd(out + (size_t)i * M2T_D + 32 * ch + j, sum[j]);
+          atomicAdd(out + (size_t)(32 * ch + j) * M2T_D + i, sum[j]);
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == M2T_MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
   }
