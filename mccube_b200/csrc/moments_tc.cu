@@ -291,7 +291,9 @@ int moments_m2_tc(const float* p, uint64_t n, int ld, const float* centre, doubl
   uint64_t per = (total_stages + ctas - 1) / ctas;
   per = (per + M2T_FLUSH_STAGES - 1) / M2T_FLUSH_STAGES * M2T_FLUSH_STAGES;
   ctas = (total_stages + per - 1) / per;
+  phase_mark("moments_m2.tcgen05", st);
   moments_m2_tc_kernel<<<(unsigned)ctas, M2T_THREADS, M2T_SMEM, st>>>(p, n, ld, centre, per, m2_out, env_int("MCCB200_M2_TC_DEBUG", 0));
+  phase_mark("end", st);
   count_launches(1);
   return check_launch("moments_m2(tcgen05)");
 }

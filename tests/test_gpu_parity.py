@@ -1191,3 +1191,28 @@ def test_stratified_keys_async_tiles_equal_oracle_and_staged_kernel(dev, monkeyp
     staged = _lib.stratified_keys(pt, d, comt)
     assert torch.equal(got, staged)
     assert np.array_equal(u32(got), key.view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 16385, 300001])
+def test_second_moment_tcgen05_d64(dev, monkeypatch, n):
+    """d = 64 unweighted second moments run on tcgen05 (MN-major TF32 operands, one M128 x N64 x K8 instruction per 8
+    rows for the three 3xTF32 products, csrc/moments_tc.cu): against fp64 numpy within 1e-5 of the largest entry (the
+    bar of jnp.cov in fp32, README.md:85-86), symmetric, and on the tensor-core path (phase mark)."""
+    rs = np.random.default_rng(n)
+    p = (rs.normal(size=(n, 64)) * rs.uniform(0.5, 2, size=64) + rs.normal(size=64) * 3).astype(np.float32)
+    c = p.astype(np.float64).mean(0).astype(np.float32)
+    pt, ct = cuda(p, dev), cuda(c, dev)
+    _lib.profile_enable(True)
+    got = _lib.second_moment(pt, 64, ct)
+    torch.cuda.synchronize()
+    names = [name for name, _ in _lib.profile_read()]
+    _lib.profile_enable(False)
+    assert "moments_m2.tcgen05" in names
+    x = p.astype(np.float64) - c.astype(np.float64)
+    want = x.T @ x
+    g = got.cpu().numpy()
+    assert np.abs(g - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
+    assert np.abs(g - g.T).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)
+    monkeypatch.setenv("MCCB200_M2_TC", "0")                        # the mma.sync kernel stays as the general form
+    old = _lib.second_moment(pt, 64, ct).cpu().numpy()
+    assert np.abs(old - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
