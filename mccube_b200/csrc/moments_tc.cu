@@ -16,6 +16,10 @@
 // the 32-byte chunk c of row r of a plane sits at chunk c ^ (r & 3); MN blocks of 32 columns are LBO = KS * 128 bytes
 // apart (the planes), 4-row K groups SBO = 512 bytes (rows are contiguous).
 //
+// (A K-major form -- thread = one column x four rows, so that the four scalar loads are one 16-byte chunk of a
+// K-major SWIZZLE_128B tile -- gives the same bits at 1.10 ms: with either operand form the stage period follows the
+// operand fetch of the eight instructions per stage; profiles/README.md.)
+//
 // Persistent CTA per SM, warp-specialised:
 //   warps 9-20  converters : six groups of two warps on alternate stages; float4 loads straight from global memory
 //                            (a group's next stage is in flight while the other five convert theirs: ~80 KB of loads
