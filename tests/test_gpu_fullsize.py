@@ -150,3 +150,62 @@ def test_config4_full_covariance_step_full_size(dev):
     want1 = yp + dt * fp + scale * sign
     got1 = y1[rows].cpu().numpy().astype(np.float64)
     assert np.abs(got1 - want1).max() <= 1e-5 * np.abs(want1).max()
+
+
+def test_config5_single_gpu_in_kernel_draw_full_size(dev):
+    """BASELINE config 5's per-GPU share (n = 2^24, d = 64, k = 128: 2^31 children), MonteCarloKernel(with_replacement=True):
+    the gather that draws its own child ids (no index vector in HBM) equals index draw + gather bit for bit; every drawn
+    id is in range and its parent row reproduces the child (Hadamard sign + Euler step recomputed in torch for a sample)."""
+    n, d = 1 << 24, 64
+    y0, terms = _problem(n, d, dev, seed=3)
+    kern = mccube.MonteCarloKernel(n, True, key=7)
+    solver = mccube.MCCSolver(dfx.Euler(), kern)
+    t0, t1 = np.float32(0.2), np.float32(0.25)
+    y1, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    assert solver.last_path == "fused:expand_select_draw"
+    solver.fuse_draw = False
+    y2, *_ = solver.step(terms, t0, t1, y0, None, None, False)
+    assert solver.last_path == "fused:mc_indices+expand_select"
+    assert torch.equal(y1, y2)
+    del y2
+    drift, cub, dt, k, _ = solver._describe(terms, y0, *solver.substep_times(t0, t1)[0], None)
+    idx = kern.indices(t0, n * k, n, dev).to(torch.int64) & 0xFFFFFFFF
+    assert int(idx.min()) >= 0 and int(idx.max()) < n * k
+    rows = torch.arange(0, n, 4099, device=dev)
+    parent, point = idx[rows] // k, idx[rows] % k
+    cols = torch.arange(d, device=dev)
+    # Hadamard row j of the doubled matrix [H; -H]: sign = (-1)^(popcount(j & c)) for j < k/2, negated above
+    half = k // 2
+    jj = (point % half)[:, None] & cols[None, :]
+    pop = torch.zeros_like(jj)
+    for b in range(8):
+        pop += (jj >> b) & 1
+    sign = 1.0 - 2.0 * ((pop & 1) ^ (point >= half)[:, None].long()).float()
+    scale = float(cub.scale)                                         # g * sqrt(dt), as the step computed it
+    yp = y0[parent]
+    f = (torch.full((d,), 2.0, device=dev) - yp) * np.float32(1.0 / 3.0)
+    want = yp + (np.float32(dt) * f + sign * float(scale))
+    assert torch.allclose(y1[rows], want, rtol=1e-5, atol=1e-5)
+
+
+def test_device_median_split_partitioner_large(dev):
+    """2^20 x 64 points, leaves of 64 (14 levels): the device tree is a permutation, and every leaf is separated from its
+    sibling at the median of the widest dimension of their parent (the property sklearn's split rule defines; the host
+    build of this size takes 11 s and is compared at small sizes in test_gpu_parity)."""
+    n, d, leaf = 1 << 20, 64, 64
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    y = torch.randn((n, d), generator=gen, device=dev) * torch.linspace(0.5, 3.0, d, device=dev)
+    levels = _lib.kd_partition_levels(n, leaf)
+    assert levels == 14
+    idx = _lib.kd_partition(y, d, levels).to(torch.int64)
+    assert torch.equal(torch.sort(idx).values, torch.arange(n, device=dev))
+    pts = y[idx].view(n // (2 * leaf), 2 * leaf, d)                    # parents of the leaves
+    spread = pts.max(dim=1).values.double() - pts.min(dim=1).values.double()
+    j = spread.argmax(dim=1)
+    col = torch.gather(pts, 2, j[:, None, None].expand(-1, 2 * leaf, 1)).squeeze(2)
+    assert bool((col[:, :leaf].max(dim=1).values <= col[:, leaf:].min(dim=1).values).all())
+    # the root split: the first half holds the n/2 smallest values of the widest dimension
+    j0 = int((y.max(0).values.double() - y.min(0).values.double()).argmax())
+    med = torch.sort(y[:, j0]).values[n // 2]
+    assert bool((y[idx[: n // 2], j0] <= med).all()) and bool((y[idx[n // 2:], j0] >= med).all())
