@@ -70,9 +70,10 @@ static SelLayout sel_layout(const SelShape& s) {
 
 size_t mc_select_ws(uint64_t n_inputs, uint64_t count) { return sel_layout(sel_shape(n_inputs, count)).total; }
 
-// Selection pays when few outputs are wanted; the radix path keeps tiny and huge inputs.
+// Selection pays when few outputs are wanted; the radix path keeps tiny and huge inputs (above 2^28 inputs the
+// bucket table would pass 2^24 entries or the buckets 16 keys, and the per-bucket ranking is quadratic in the size).
 bool mc_select_worthwhile(uint64_t n_inputs, uint64_t count) {
-  return n_inputs >= (1ull << 16) && n_inputs < 0xFFFFFFFFull && count >= 1 && count * 4 <= n_inputs;
+  return n_inputs >= (1ull << 16) && n_inputs < (1ull << 28) && count >= 1 && count * 4 <= n_inputs;
 }
 
 // Keys of a round, SEL_U threefry blocks per thread and trip: a block serves the pair of positions (i, i + h) in the
