@@ -23,6 +23,12 @@ def test_published_jax_values_non_partitionable():
     assert abs(float(jr.uniform(jr.prng_key(0), 1)[0]) - 0.41845703) < 1e-7
     assert abs(float(jr.normal(jr.prng_key(0), 1)[0]) - (-0.20584226)) < 1e-6
     assert abs(float(jr.normal(jr.prng_key(42), 1)[0]) - (-0.18471177)) < 1e-6
+    # the vector printed in JAX's own README / quickstart for `random.normal(random.PRNGKey(0), (10,))`: ten values pin
+    # the layout of random_bits (word i pairs with word i + ceil(n/2) of one threefry block) and the bits -> uniform ->
+    # normal chain; the last digit depends on the erfinv implementation
+    want = [-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346, -0.5908641, 0.73168886,
+            0.5673026]
+    assert np.allclose(np.asarray(jr.normal(jr.prng_key(0), 10)), want, rtol=0, atol=1e-6)
 
 
 def test_partitionable_structure():
