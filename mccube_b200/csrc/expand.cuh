@@ -123,27 +123,47 @@ inline bool box_dims_vec4(const BoxSpec& s, const ExpandArgs& a) {
   return true;
 }
 
+// Per-thread constants of the 4 vectorised key dims (analytic drift): loaded once, not per parent.
+struct KeyConst4 { float mean[4], ivar[4]; };
+
+__device__ __forceinline__ KeyConst4 key_const4(const ExpandArgs& a, const BoxSpec& s) {
+  KeyConst4 kc;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    kc.mean[q] = a.drift_kind == 2 ? __ldg(a.mean + s.dims[0] + q) : 0.0f;
+    kc.ivar[q] = a.drift_kind == 2 ? __ldg(a.inv_var + s.dims[0] + q) : 0.0f;
+  }
+  return kc;
+}
+
+// the 4 key columns of parent i: packed hand-over of the previous step's gather (16 contiguous bytes per parent
+// instead of a 64-byte DRAM fill per 256-byte row), else from the strided state
+__device__ __forceinline__ float4 key_columns4(const ExpandArgs& a, const BoxSpec& s, uint64_t i) {
+  return a.keycols ? __ldg(reinterpret_cast<const float4*>(a.keycols) + i) : ld_strided4(a.y0 + i * a.ld + s.dims[0]);
+}
+
 // The two candidate child coordinates (- and + noise) of parent i in its 4 vectorised key dims.
-__device__ __forceinline__ void key_children4(const ExpandArgs& a, const BoxSpec& s, uint64_t i, float (&vm)[4],
-                                              float (&vp)[4]) {
-  const int c0 = s.dims[0];
-  // the previous step's gather can hand over its key columns packed (16 contiguous bytes per
-  // parent instead of a 64-byte DRAM fill per 256-byte row)
-  const float4 y4 = a.keycols ? __ldg(reinterpret_cast<const float4*>(a.keycols) + i) : ld_strided4(a.y0 + i * a.ld + c0);
+__device__ __forceinline__ void key_children4(const ExpandArgs& a, const BoxSpec& s, const KeyConst4& kc, uint64_t i,
+                                              const float4 y4, float (&vm)[4], float (&vp)[4]) {
   const float y[4] = {y4.x, y4.y, y4.z, y4.w};
   float f[4] = {0.f, 0.f, 0.f, 0.f};
   if (a.drift_kind == 1) {
-    const float4 f4 = ld_strided4(a.f + i * a.d + c0);
+    const float4 f4 = ld_strided4(a.f + i * a.d + s.dims[0]);
     f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w;
   } else if (a.drift_kind == 2) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) f[q] = __fmul_rn(__fsub_rn(__ldg(a.mean + c0 + q), y[q]), __ldg(a.inv_var + c0 + q));
+    for (int q = 0; q < 4; ++q) f[q] = __fmul_rn(__fsub_rn(kc.mean[q], y[q]), kc.ivar[q]);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     vm[q] = child_value(a, y[q], f[q], -a.scale);
     vp[q] = child_value(a, y[q], f[q], a.scale);
   }
+}
+
+__device__ __forceinline__ void key_children4(const ExpandArgs& a, const BoxSpec& s, uint64_t i, float (&vm)[4],
+                                              float (&vp)[4]) {
+  key_children4(a, s, key_const4(a, s), i, key_columns4(a, s, i), vm, vp);
 }
 
 }  // namespace mccb

@@ -185,12 +185,19 @@ box_bounds_children_kernel(ExpandArgs a, BoxSpec spec, float* __restrict__ parti
   if (VEC4) {
     // 4 consecutive aligned key columns and the Hadamard cubature: one 128-bit load per parent (from the
     // packed key columns, or a 64-byte L2 fill from the strided state), four parents in flight per thread
+    const KeyConst4 kc = key_const4(a, spec);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += 4 * stride) {
       float vm[4][4], vp[4][4];
+      float4 y4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                                  // all four loads first
+        const uint64_t iu = i + (uint64_t)u * stride;
+        y4[u] = key_columns4(a, spec, iu < a.n ? iu : i);            // past the end: repeat parent i (min/max unchanged)
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint64_t iu = i + (uint64_t)u * stride;
-        key_children4(a, spec, iu < a.n ? iu : i, vm[u], vp[u]);   // past the end: repeat parent i (min/max unchanged)
+        key_children4(a, spec, kc, iu < a.n ? iu : i, y4[u], vm[u], vp[u]);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
