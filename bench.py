@@ -171,7 +171,7 @@ def reference_arm(a):
     line = {
         "impl": "reference", "metric": "particle_steps_per_sec", "value": val, "unit": "particle-steps/s",
         "n_gpus": a.gpus, "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic: y0 ~ N(0, I) from numpy default_rng(rank), target N(2 1_d, 3 I_d)",
         "config": {"workload": workload_name(a), "cpu_sample": sample},
         "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": procs, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count(), "blas_threads": host_threads()},
@@ -267,10 +267,31 @@ def build_problem(a, dev):
     else:
         kernel = mccube.MonteCarloKernel(n, a.workload == "mc_replace", key=42)
     solver = mccube.MCCSolver(dfx.Euler(), kernel)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + int(os.environ.get("RANK", "0")))
-    y0 = torch.randn((n, d), generator=gen, device=dev, dtype=torch.float32)
-    return terms, solver, y0
+    return terms, solver, initial_state(n, d, dev)
+
+
+_Y0_CACHE = {}
+
+
+def initial_state(n, d, dev):
+    """y0 ~ N(0, I) from a fixed NumPy generator, as SURVEY.md 8(d) prescribes for the throughput runs:
+    `default_rng(rank)` (rank 0 = the single-GPU run's `default_rng(0)`; every rank of a weak-scaling run owns different
+    particles).  Drawn on the host in 64 MiB chunks and copied up; kept per (n, d) for the workloads that share it."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    key = (n, d, rank, str(dev))
+    if key not in _Y0_CACHE:
+        _Y0_CACHE.clear()                                   # one state at a time: 4 GiB at the headline size
+        rng = np.random.default_rng(rank)
+        y0 = torch.empty((n, d), dtype=torch.float32, device=dev)
+        flat = y0.view(-1)
+        chunk = 1 << 24
+        for off in range(0, n * d, chunk):
+            m = min(chunk, n * d - off)
+            flat[off:off + m].copy_(torch.from_numpy(rng.standard_normal(m, dtype=np.float32)))
+        _Y0_CACHE[key] = y0
+    return _Y0_CACHE[key].clone()
 
 
 def time_steps(solver, terms, y, times, steps, warmup=3):
@@ -963,7 +984,7 @@ def main():
     line = {
         "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic: y0 ~ N(0, I) from numpy default_rng(rank), target N(2 1_d, 3 I_d)",
         "config": {"workload": workload_name(a), "path": path, "n_per_gpu": n, "d": d,
                    "l2": "state is 4 GiB per array (>> 126 MB L2): no flush between iterations",
                    "threefry_partitionable": False, "phase_ms_per_step": phase_ms,
