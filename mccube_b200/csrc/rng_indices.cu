@@ -309,7 +309,10 @@ static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
   p.rounds = replace ? 0 : shuffle_rounds(n_inputs);
   p.off_dk = 0;
   size_t cur = align_up(sizeof(DerivedKeys), 256);
-  if (!replace) {
+  if (!replace && env_int("MCCB200_SHUFFLE_SELECT", 1) != 0 && mc_select_worthwhile(n_inputs, count)) {
+    // the selection path lays its own scratch after dk (19 GiB at 2^31 inputs; the sort path would take 66 GiB)
+    cur += mc_select_ws(n_inputs, count);
+  } else if (!replace) {
     size_t arr = align_up((size_t)n_inputs * 4, 256);
     p.off_keys = cur; cur += arr;
     p.off_va = cur; cur += arr;
@@ -318,8 +321,6 @@ static IdxPlan make_idx_plan(uint64_t n_inputs, uint64_t count, int replace) {
     size_t sw = sort_pairs_ws(n_inputs);
     if (count >= 1 && sort_pairs_top_worthwhile(n_inputs, count)) sw = max(sw, sort_pairs_top_ws(n_inputs, count));
     cur += sw;
-    if (mc_select_worthwhile(n_inputs, count))      // the selection path lays its own scratch over everything after dk
-      cur = max(cur, align_up(sizeof(DerivedKeys), 256) + mc_select_ws(n_inputs, count));
   }
   p.total = cur;
   return p;

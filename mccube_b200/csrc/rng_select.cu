@@ -24,6 +24,7 @@ size_t scan_u32_ws(uint64_t len);
 int scan_u32_exclusive(uint32_t* data, uint64_t len, void* ws, cudaStream_t st, const uint32_t* guard);
 
 struct SelShape {
+  uint32_t window;   // half-width (buckets) of the interpolation-search window: ~6 sigma of a rank's bucket
   uint32_t n;        // inputs
   uint32_t count;    // outputs wanted
   int bucket_bits;   // B
@@ -39,9 +40,13 @@ static SelShape sel_shape(uint64_t n_inputs, uint64_t count) {
   while ((2ull << lg) <= n_inputs) ++lg;          // floor(log2 n)
   s.bucket_bits = lg - 3;                         // 8 .. 16 keys per bucket on average
   if (s.bucket_bits < 4) s.bucket_bits = 4;
-  if (s.bucket_bits > 24) s.bucket_bits = 24;
+  if (s.bucket_bits > 28) s.bucket_bits = 28;          // 2^28 buckets: three 1 GiB tables at 2^31 inputs
   s.shift = 32 - s.bucket_bits;
   s.nb = 1u << s.bucket_bits;
+  // the bucket of rank i is i * nb / n up to a deviation of sigma <= sqrt(n) / 2 ranks
+  const double sigma_buckets = 0.5 * sqrt((double)n_inputs) * (double)s.nb / (double)n_inputs;
+  s.window = 2048;
+  while ((double)s.window < 6.0 * sigma_buckets) s.window <<= 1;
   return s;
 }
 
@@ -70,10 +75,12 @@ static SelLayout sel_layout(const SelShape& s) {
 
 size_t mc_select_ws(uint64_t n_inputs, uint64_t count) { return sel_layout(sel_shape(n_inputs, count)).total; }
 
-// Selection pays when few outputs are wanted; the radix path keeps tiny and huge inputs (above 2^28 inputs the
-// bucket table would pass 2^24 entries or the buckets 16 keys, and the per-bucket ranking is quadratic in the size).
+// Selection pays when few outputs are wanted and the bucket table stays in L2: measured against the sort shuffle
+// (count = n / 32) 2^25: 1.7 vs 3.1 ms, 2^27: 9.4 vs 11.1, 2^28: 28 vs 22, 2^29: 75 vs 44, 2^31: 291 vs 195 ms -- past
+// 2^27 inputs the 2^25+ counters no longer fit the 126 MB L2 and every histogram atomic goes to DRAM.  The results are
+// identical at every size (experiments/bench_select.py, shuffle_2p31.py).
 bool mc_select_worthwhile(uint64_t n_inputs, uint64_t count) {
-  return n_inputs >= (1ull << 16) && n_inputs < (1ull << 28) && count >= 1 && count * 4 <= n_inputs;
+  return n_inputs >= (1ull << 16) && n_inputs <= (1ull << 27) && count >= 1 && count * 4 <= n_inputs;
 }
 
 // Keys of a round, SEL_U threefry blocks per thread and trip: a block serves the pair of positions (i, i + h) in the
@@ -153,7 +160,7 @@ sel_locate_kernel(const uint32_t* __restrict__ queries, SelShape s, uint32_t nbl
     // largest b with prefix[b] <= i.  The keys are uniform: rank i sits near bucket i * nb / n (within a few hundred
     // buckets), so the search starts in a window around that guess and widens only if the window misses.
     const uint32_t guess = min((uint32_t)(((uint64_t)i * s.nb) / s.n), nbl - 1u);
-    uint32_t lo = guess > 2048u ? guess - 2048u : 0u, hi = min(nbl, guess + 2048u);
+    uint32_t lo = guess > s.window ? guess - s.window : 0u, hi = (uint32_t)min((uint64_t)nbl, (uint64_t)guess + s.window);
     if (__ldg(prefix + lo) > i) lo = 0u;
     if (hi < nbl && __ldg(prefix + hi) <= i) hi = nbl;
     while (lo + 1 < hi) {
