@@ -144,14 +144,20 @@ kd_splitdim_kernel(const uint32_t* __restrict__ mm, int d, uint32_t nodes, uint3
   dims[i] = arg;
 }
 
-// key of every position along its node's split dimension, and the node id of the position
+// key of every position along its node's split dimension, and the node id of the position.  node_of holds the node
+// of the PREVIOUS level on entry (positions never leave their node): the node of this level is its left or right
+// child, one comparison against the child boundary instead of a binary search over all node starts.
 __global__ void __launch_bounds__(256)
 kd_keys_kernel(const float* __restrict__ y, int ld, uint32_t n, const uint32_t* __restrict__ idx,
-               const uint32_t* __restrict__ node_start, uint32_t nodes, const uint32_t* __restrict__ dims,
+               const uint32_t* __restrict__ node_start, int level, const uint32_t* __restrict__ dims,
                uint32_t* __restrict__ keys, uint32_t* __restrict__ node_of) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-    const uint32_t node = kd_node_of(node_start, nodes, p);
+    uint32_t node = 0;
+    if (level > 0) {
+      const uint32_t left = 2u * node_of[p];
+      node = left + (p >= __ldg(node_start + left + 1) ? 1u : 0u);
+    }
     keys[p] = kd_order_bits(__ldg(y + (size_t)__ldg(idx + p) * ld + __ldg(dims + node)));
     node_of[p] = node;
   }
@@ -245,7 +251,7 @@ extern "C" int mccb200_kd_partition(const float* y, uint64_t n, int d, int ld, i
     }
 #undef MCCB_KD_MM
     kd_splitdim_kernel<<<(nodes + 255) / 256, 256, 0, st>>>(mm, d, nodes, dims);
-    kd_keys_kernel<<<grid_n, 256, 0, st>>>(y, ld, n32, cur_idx, node_start, nodes, dims, keys, node_of);
+    kd_keys_kernel<<<grid_n, 256, 0, st>>>(y, ld, n32, cur_idx, node_start, level, dims, keys, node_of);
     int rc = sort_pairs_impl(keys, nullptr, n, 32, nullptr, pos[0], w + p.off_sort, p.sort_bytes, st);
     if (rc) return rc;
     const uint32_t* order = pos[0];
