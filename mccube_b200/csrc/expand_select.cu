@@ -106,7 +106,9 @@ expand_kernel(const ExpandArgs a) {
     load_vec<VEC>(a.mean + col, mean);
     load_vec<VEC>(a.inv_var + col, ivar);
   }
-  const bool do_w = a.weighted && col == 0;
+  // weighted states always take the scalar mapping (run_expand_select): the vector instantiations carry no weight code
+  // (the fp64 weight sum cost the VEC = 4 kernels 5 registers = one resident CTA per SM: 1.43 -> 1.58 ms)
+  const bool do_w = VEC == 1 && a.weighted && col == 0;
   double wacc = 0.0;
   u32x2 dk_hi{}, dk_lo{};
   uint32_t draw_mult = 0;
