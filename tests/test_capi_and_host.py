@@ -327,3 +327,49 @@ def test_c_abi_argument_errors_without_a_gpu(lib):
     assert lib.mccb200_gaussian_full_drift_tc_supported(1 << 20, 512, 512) == 1
     assert lib.mccb200_gaussian_full_drift_tc_supported(100, 48, 48) == 0
     assert lib.mccb200_gaussian_full_drift_tc_supported(100, 64, 66) == 0
+
+
+def test_round2_entry_points_validate_and_size_without_a_gpu(lib):
+    """The entry points added in round 2: shape predicates, level counts and workspace sizes are pure host functions;
+    argument validation reports through the status code + message before anything touches the device."""
+    import ctypes as C
+
+    lib.mccb200_last_error.restype = C.c_char_p
+    # in-kernel index draw: unweighted rows of 4 .. 32 float4
+    for d, ld, w, ok in ((64, 64, 0, 1), (16, 16, 0, 1), (128, 128, 0, 1), (12, 12, 0, 0), (64, 65, 1, 0), (256, 256, 0, 0),
+                         (8, 8, 0, 0)):
+        assert lib.mccb200_expand_select_draw_supported(d, ld, w) == ok, (d, ld, w)
+    assert lib.mccb200_expand_select_draw_workspace_bytes() >= 64
+    fake = C.c_void_p(256)
+    drift = _lib.Drift()
+    cub = _lib.Cubature()
+    cub.k = 128
+    rng = _lib.make_rng((0, 42), 0.0)
+    assert lib.mccb200_expand_select_draw(fake, 1 << 26, 64, C.byref(drift), 0.05, C.byref(cub), C.byref(rng), 1 << 10, fake,
+                                          None, fake, 256, None) != 0       # n * k = 2^33 child ids
+    assert b"child ids" in lib.mccb200_last_error()
+    # median-split tree: levels = floor(log2(n / leaf)); sklearn's tree has floor(log2((n - 1) // leaf)) split levels
+    for n, leaf in ((1 << 20, 64), (1000, 10), (777, 7), (512, 512), (4096, 64), (3000, 100), (65, 64), (63, 64)):
+        want = 0
+        while n >= leaf and (n >> (want + 1)) >= leaf:
+            want += 1
+        got = lib.mccb200_kd_partition_levels(n, leaf)
+        assert got == want, (n, leaf)
+        if n > leaf:
+            sk = int(np.log2(max(1, (n - 1) // leaf)))
+            assert got in (sk, sk + 1)
+    lib.mccb200_kd_partition_workspace_bytes.restype = C.c_size_t
+    small = lib.mccb200_kd_partition_workspace_bytes(1 << 16, 8, 10)
+    big = lib.mccb200_kd_partition_workspace_bytes(1 << 20, 64, 14)
+    assert 0 < small < big
+    assert lib.mccb200_kd_partition(None, 100, 8, 8, 3, None, None, 0, None) != 0
+    assert b"kd_partition" in lib.mccb200_last_error()
+    assert lib.mccb200_kd_partition(fake, 100, 300, 300, 3, fake, fake, 1 << 30, None) != 0     # d > 256
+    # selection shuffle: a quarter of the scratch of the sort shuffle at config 2's size, and only up to 2^27 inputs
+    sel = lib.mccb200_mc_indices_workspace_bytes(1 << 25, 1 << 20, 0)
+    assert sel < 3 * 4 * (1 << 25) + lib.mccb200_sort_pairs_workspace_bytes(1 << 25)
+    assert lib.mccb200_mc_indices_workspace_bytes(1 << 28, 1 << 20, 0) >= 3 * 4 * (1 << 28)
+    # renormalised copy / id bucketing
+    assert lib.mccb200_normalised_copy(None, 10, 5, None, None, None, None) != 0
+    assert b"normalised_copy" in lib.mccb200_last_error()
+    assert lib.mccb200_shard_bucket_ids_workspace_bytes(8) > 0
