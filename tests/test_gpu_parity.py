@@ -1213,6 +1213,9 @@ def test_second_moment_tcgen05_d64(dev, monkeypatch, n):
     g = got.cpu().numpy()
     assert np.abs(g - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
     assert np.abs(g - g.T).max() <= 1e-6 * max(np.abs(want).max(), 1e-30)
+    monkeypatch.setenv("MCCB200_M2_TC", "2")                        # second form: A = [hi ; lo] in tensor memory, B = hi in smem
+    ts = _lib.second_moment(pt, 64, ct).cpu().numpy()
+    assert np.abs(ts - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
     monkeypatch.setenv("MCCB200_M2_TC", "0")                        # the mma.sync kernel stays as the general form
     old = _lib.second_moment(pt, 64, ct).cpu().numpy()
     assert np.abs(old - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
