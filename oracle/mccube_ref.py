@@ -231,6 +231,44 @@ class BinaryTreePartitioningKernel:
         return particles[self.indices(particles, weighted)]
 
 
+def median_split_levels(n: int, leaf_size: int) -> int:
+    """Split levels of the device tree: floor(log2(n / leaf_size)); sklearn's own tree has
+    floor(log2((n - 1) // leaf_size)) of them (sklearn/neighbors/_binary_tree.pxi, `n_levels`)."""
+    levels = 0
+    while n >= leaf_size and (n >> (levels + 1)) >= leaf_size:
+        levels += 1
+    return levels
+
+
+def median_split_indices(points, levels: int) -> np.ndarray:
+    """Restatement of sklearn's `_recursive_build` partition rule (the tree the reference builds through
+    `jax.pure_callback`, mccube/_kernels/tree.py:44-58), level by level as `csrc/kd_split.cu` does it: a node is the
+    positions [start, end) of the index array; its split dimension is the one of largest max - min over its points
+    (first on ties, compared in float64 as sklearn's float64 trees do); its points are ordered along that dimension
+    by a STABLE sort (sklearn: `nth_element`, whose order inside the halves is platform dependent) and it is cut at
+    (end - start) // 2.  The point SET of every node equals sklearn's; the order inside a leaf is this function's
+    definition (sorted along the last split dimension, ties in the previous order)."""
+    pts = np.asarray(points)
+    n = pts.shape[0]
+    idx = np.arange(n, dtype=np.int64)
+    bounds = [(0, n)]
+    for _ in range(levels):
+        nxt = []
+        for s, e in bounds:
+            if e > s:
+                node = pts[idx[s:e]]
+                spread = node.max(axis=0).astype(np.float64) - node.min(axis=0).astype(np.float64)
+                j = int(np.argmax(spread))
+                # -0.0 orders before +0.0 in the device's integer image of a float; numpy treats them as equal
+                key = node[:, j].astype(np.float64)
+                key = np.where((node[:, j] == 0) & np.signbit(node[:, j]), -np.finfo(np.float64).tiny, key)
+                idx[s:e] = idx[s:e][np.argsort(key, kind="stable")]
+            mid = s + (e - s) // 2
+            nxt += [(s, mid), (mid, e)]
+        bounds = nxt
+    return idx
+
+
 def box_keys(p, lo, inv_h, dims, bits):
     """Integer box key of `BoxPartitionKernel` (NEW kernel -- absent from the reference,
     SURVEY.md F2; this function is its definition).

@@ -1219,3 +1219,18 @@ def test_second_moment_tcgen05_d64(dev, monkeypatch, n):
     monkeypatch.setenv("MCCB200_M2_TC", "0")                        # the mma.sync kernel stays as the general form
     old = _lib.second_moment(pt, 64, ct).cpu().numpy()
     assert np.abs(old - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-30)
+
+
+@pytest.mark.parametrize("n,d,leaf", [(4096, 8, 64), (1000, 5, 10), (777, 3, 7), (3000, 64, 100), (1 << 15, 130, 32), (100, 2, 1)])
+def test_device_median_split_equals_the_oracle_exactly(dev, n, d, leaf):
+    """Index parity of csrc/kd_split.cu: the device tree equals the oracle's restatement of sklearn's split rule
+    (`oracle.mccube_ref.median_split_indices`, itself checked against sklearn's node sets on the CPU) position by
+    position -- same split dimensions, same medians, same stable order inside the leaves."""
+    rng = np.random.default_rng(n + d)
+    y = (rng.standard_normal((n, d)) * rng.uniform(0.5, 3.0, d)).astype(np.float32)
+    y[rng.integers(0, n, 5), rng.integers(0, d, 5)] = 0.0           # a few exact zeros and duplicates
+    y[1] = y[0]
+    levels = _lib.kd_partition_levels(n, leaf)
+    assert levels == ref.median_split_levels(n, leaf)
+    got = _lib.kd_partition(cuda(y, dev), d, levels).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, ref.median_split_indices(y, levels))

@@ -210,3 +210,26 @@ def test_oracle_random_properties():
         assert u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
 
     run()
+
+
+def test_median_split_oracle_matches_sklearn_node_sets():
+    """The oracle's level-by-level restatement of sklearn's `_recursive_build` (the tree the reference builds in its host
+    callback, mccube/_kernels/tree.py:44-58) puts into every sklearn leaf's range of `idx_array` exactly the points sklearn
+    put there -- KDTree and BallTree alike, ragged counts included -- and levels = floor(log2(n / leaf)) is sklearn's depth
+    or one more."""
+    from sklearn.neighbors import BallTree, KDTree
+
+    rng = np.random.default_rng(0)
+    for n, d, leaf, tree in ((4096, 8, 64, KDTree), (1000, 5, 10, BallTree), (777, 3, 7, KDTree), (3000, 64, 100, BallTree),
+                             (512, 40, 512, KDTree)):
+        y = (rng.standard_normal((n, d)) * rng.uniform(0.5, 3.0, d)).astype(np.float32)
+        levels = ref.median_split_levels(n, leaf)
+        sk_levels = int(np.log2(max(1, (n - 1) // leaf)))
+        assert levels in (sk_levels, sk_levels + 1)
+        idx = ref.median_split_indices(y, levels)
+        assert np.array_equal(np.sort(idx), np.arange(n))
+        _, sk_idx, node_data, _ = tree(y.astype(np.float64), leaf).get_arrays()
+        leaves = [(int(nd["idx_start"]), int(nd["idx_end"])) for nd in node_data if nd["is_leaf"]]
+        assert sum(e - s for s, e in leaves) == n
+        for s, e in leaves:
+            assert set(idx[s:e].tolist()) == set(np.asarray(sk_idx[s:e]).tolist())
