@@ -142,36 +142,70 @@ sel_hist_kernel(const DerivedKeys* __restrict__ dk, int round, SelShape s, uint3
   }
 }
 
-// queries (ranks; nullptr = 0 .. count-1) -> start and size of the bucket and the rank inside it; marks the bucket.
+// queries (ranks; nullptr = 0 .. count-1) -> bucket, bucket size and the rank inside it; marks the bucket.
 // prefix = exclusive scan of the counts over nbl + 1 entries (prefix[nbl] = keys in the first nbl buckets).  A rank
 // beyond that raises `overflow` (the round is then re-run over all buckets).
+//
+// The members of the queried buckets are stored COMPACTLY (about a fifth of the keys: the region then stays in L2
+// instead of being 8-byte writes scattered over n * 8 bytes): the query that marks a bucket first reserves the
+// bucket's slots -- one atomic per CTA and trip on `region_top` after a block-wide scan of the reservations -- and
+// leaves the bucket's base in cursor[bucket]; the scatter pass advances it, the ranking pass reads its end.
 __global__ void __launch_bounds__(256)
 sel_locate_kernel(const uint32_t* __restrict__ queries, SelShape s, uint32_t nbl, const uint32_t* __restrict__ prefix,
                   uint32_t* __restrict__ qs, uint32_t* __restrict__ qc, uint32_t* __restrict__ qr,
-                  uint32_t* __restrict__ bitmap, uint32_t* __restrict__ overflow, const uint32_t* __restrict__ guard) {
+                  uint32_t* __restrict__ bitmap, uint32_t* __restrict__ cursor, uint32_t* __restrict__ region_top,
+                  uint32_t* __restrict__ overflow, const uint32_t* __restrict__ guard) {
   if (guard && *guard == 0u) return;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < s.count; q += gridDim.x * blockDim.x) {
-    const uint32_t i = queries ? queries[q] : q;
-    if (i >= __ldg(prefix + nbl)) {
-      if (overflow) *overflow = 1u;
-      qc[q] = 0u;
-      continue;
+  __shared__ uint32_t warp_tot[8];
+  __shared__ uint32_t block_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t trips = (s.count + stride - 1) / stride;          // uniform: the block scan needs every thread
+  for (uint32_t t = 0; t < trips; ++t) {
+    const uint32_t q = t * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t reserve = 0, lo = 0;
+    if (q < s.count) {
+      const uint32_t i = queries ? queries[q] : q;
+      if (i >= __ldg(prefix + nbl)) {
+        if (overflow) *overflow = 1u;
+        qc[q] = 0u;
+      } else {
+        // largest b with prefix[b] <= i.  The keys are uniform: rank i sits near bucket i * nb / n (within a few
+        // sigma), so the search starts in a window around that guess and widens only if the window misses.
+        const uint32_t guess = min((uint32_t)(((uint64_t)i * s.nb) / s.n), nbl - 1u);
+        lo = guess > s.window ? guess - s.window : 0u;
+        uint32_t hi = (uint32_t)min((uint64_t)nbl, (uint64_t)guess + s.window);
+        if (__ldg(prefix + lo) > i) lo = 0u;
+        if (hi < nbl && __ldg(prefix + hi) <= i) hi = nbl;
+        while (lo + 1 < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(prefix + mid) <= i) lo = mid; else hi = mid;
+        }
+        const uint32_t start = __ldg(prefix + lo);
+        const uint32_t cnt = __ldg(prefix + lo + 1u) - start;
+        qs[q] = lo;
+        qc[q] = cnt;
+        qr[q] = i - start;
+        const uint32_t bit = 1u << (lo & 31);
+        if ((atomicOr(bitmap + (lo >> 5), bit) & bit) == 0u) reserve = cnt;   // first to mark it: reserves its slots
+      }
     }
-    // largest b with prefix[b] <= i.  The keys are uniform: rank i sits near bucket i * nb / n (within a few hundred
-    // buckets), so the search starts in a window around that guess and widens only if the window misses.
-    const uint32_t guess = min((uint32_t)(((uint64_t)i * s.nb) / s.n), nbl - 1u);
-    uint32_t lo = guess > s.window ? guess - s.window : 0u, hi = (uint32_t)min((uint64_t)nbl, (uint64_t)guess + s.window);
-    if (__ldg(prefix + lo) > i) lo = 0u;
-    if (hi < nbl && __ldg(prefix + hi) <= i) hi = nbl;
-    while (lo + 1 < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(prefix + mid) <= i) lo = mid; else hi = mid;
+    uint32_t x = reserve;                                          // inclusive scan over the CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-    const uint32_t start = __ldg(prefix + lo);
-    qs[q] = start;
-    qc[q] = __ldg(prefix + lo + 1u) - start;
-    qr[q] = i - start;
-    atomicOr(bitmap + (lo >> 5), 1u << (lo & 31));
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (int w = 0; w < 8; ++w) { const uint32_t v = warp_tot[w]; warp_tot[w] = run; run += v; }
+      block_base = run ? atomicAdd(region_top, run) : 0u;
+    }
+    __syncthreads();
+    if (reserve) cursor[lo] = block_base + warp_tot[wid] + x - reserve;
+    __syncthreads();                                               // warp_tot / block_base are rewritten next trip
   }
 }
 
@@ -194,9 +228,9 @@ sel_scatter_kernel(const DerivedKeys* __restrict__ dk, int round, SelShape s, ui
       want[e] = pos[e] != 0xFFFFFFFFu && b < nbl && ((__ldg(bitmap + (b >> 5)) >> (b & 31)) & 1u);
     }
 #pragma unroll
-    for (int e = 0; e < 2 * SEL_U; ++e) {             // then every atomic (and its prefix load) before the first store
+    for (int e = 0; e < 2 * SEL_U; ++e) {             // then every atomic before the first store
       const uint32_t b = keys[e] >> s.shift;
-      slot[e] = want[e] ? __ldg(prefix + b) + atomicAdd(cursor + b, 1u) : 0u;
+      slot[e] = want[e] ? atomicAdd(cursor + b, 1u) : 0u;         // the bucket's base was left there by sel_locate_kernel
     }
 #pragma unroll
     for (int e = 0; e < 2 * SEL_U; ++e)
@@ -210,7 +244,8 @@ sel_scatter_kernel(const DerivedKeys* __restrict__ dk, int round, SelShape s, ui
 // pair is ranked.  Buckets of more than 16 members (rare: the mean is 8 .. 16) are ranked from memory.
 __global__ void __launch_bounds__(256)
 sel_answer_kernel(SelShape s, const uint32_t* __restrict__ qs, const uint32_t* __restrict__ qc,
-                  const uint32_t* __restrict__ qr, const uint2* __restrict__ members, uint32_t* __restrict__ out,
+                  const uint32_t* __restrict__ qr, const uint32_t* __restrict__ cursor, const uint2* __restrict__ members,
+                  uint32_t* __restrict__ out,
                   const uint32_t* __restrict__ guard) {
   if (guard && *guard == 0u) return;
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
@@ -225,7 +260,10 @@ sel_answer_kernel(SelShape s, const uint32_t* __restrict__ qs, const uint32_t* _
   for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < s.count; base += warps * 32u) {
     const uint32_t q = base + lane;
     uint32_t st = 0, c = 0, r = 0;
-    if (q < s.count) { st = __ldg(qs + q); c = __ldg(qc + q); r = __ldg(qr + q); }
+    if (q < s.count) {
+      c = __ldg(qc + q); r = __ldg(qr + q);
+      if (c) st = cursor[__ldg(qs + q)] - c;                 // the scatter pass left the END of the bucket's members there
+    }
     uint64_t nxt = fetch(__shfl_sync(0xffffffffu, st, half), __shfl_sync(0xffffffffu, c, half));
     for (int it = 0; it < 16; ++it) {
       const int src = 2 * it + half;
@@ -305,6 +343,7 @@ int mc_select_impl(const DerivedKeys* dk, int rounds, int partitionable, uint64_
   uint32_t* qr = (uint32_t*)(w + L.off_qr);
   uint32_t* qbuf[2] = {(uint32_t*)(w + L.off_q0), (uint32_t*)(w + L.off_q1)};
   uint32_t* flag = (uint32_t*)(w + L.off_flag);
+  uint32_t* region_top = flag + 8;                 // slots of the compact member region handed out so far
   const int sms = sm_count();
   const uint32_t work = partitionable ? s.n : (s.n + 1u) / 2u;
   const int grid_n = (int)min(((uint64_t)work + 256 * SEL_U - 1) / (256 * SEL_U), (uint64_t)sms * 8);
@@ -333,10 +372,10 @@ int mc_select_impl(const DerivedKeys* dk, int rounds, int partitionable, uint64_
                           const uint32_t* guard) {
     uint32_t* hist = hists[r & 1];
     const int grid_z = (int)min(((uint64_t)nbl + 256) / 256, (uint64_t)sms * 4);
-    sel_zero_kernel<<<grid_z, 256, 0, st>>>(cursor, nbl, bitmap, ((size_t)nbl + 31) / 32, nullptr, 0, guard);
-    sel_locate_kernel<<<grid_q, 256, 0, st>>>(queries, s, nbl, hist, qs, qc, qr, bitmap, overflow, guard);
+    sel_zero_kernel<<<grid_z, 256, 0, st>>>(region_top, 1, bitmap, ((size_t)nbl + 31) / 32, nullptr, 0, guard);
+    sel_locate_kernel<<<grid_q, 256, 0, st>>>(queries, s, nbl, hist, qs, qc, qr, bitmap, cursor, region_top, overflow, guard);
     sel_scatter_kernel<<<grid_n, 256, 0, st>>>(dk, r, s, nbl, partitionable, bitmap, hist, cursor, members, guard);
-    sel_answer_kernel<<<grid_w, 256, 0, st>>>(s, qs, qc, qr, members, out, guard);
+    sel_answer_kernel<<<grid_w, 256, 0, st>>>(s, qs, qc, qr, cursor, members, out, guard);
     count_launches(4);
   };
 
