@@ -876,9 +876,15 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
             __threadfence_block();
             const uint2* jq = reinterpret_cast<const uint2*>(rank_block(r) + FQ_CAP * 4);
             const uint32_t bar = bar0 + 8u * (uint32_t)next_load;
+#if defined(FZ_EXP) && FZ_EXP == 4   /* timing experiment: the transform warps only consume the jobs (ranking alone, in situ) */
+            if (lane == 0) fz_mbar_expect_tx(bar, 0u);
+            __syncwarp();
+            if (false) {
+#else
             if (lane == 0) fz_mbar_expect_tx(bar, cnt * o.row_bytes);
             __syncwarp();
             if ((uint32_t)lane < cnt) {
+#endif
               const uint32_t child = jq[(fetch[q] + (uint32_t)lane) & (FZ_JQ - 1)].x;
               fz_bulk_row(buf0 + (uint32_t)next_load * stage_bytes + (uint32_t)lane * o.row_bytes,
                           a.y0 + (uint64_t)(child >> logk) * ld, o.row_bytes, bar, pol_stream);
@@ -904,7 +910,11 @@ box_rank_fused_kernel(const BoxPrkParams p, const FusedOut o) {
         const uint2* jq = reinterpret_cast<const uint2*>(rb + FQ_CAP * 4);
         const uint32_t head = st_head[s], cnt = st_cnt[s];
         const char* buf = reinterpret_cast<const char*>(xb) + (size_t)s * stage_bytes;
+#if defined(FZ_EXP) && FZ_EXP == 4
+        if (false) {
+#else
         if (sub < vpr) {
+#endif
 #pragma unroll 4
           for (uint32_t t = (uint32_t)rs; t < cnt; t += (uint32_t)rpp) {
             const uint2 job = jq[(head + t) & (FZ_JQ - 1)];
